@@ -1,0 +1,291 @@
+"""Import the UNMODIFIED reference implementation (authoring container only).
+
+TEST INFRASTRUCTURE.  Used by ``oracle/gen_golden.py`` (to freeze fixtures under
+``tests/golden/``) and by the ``not gpu`` tests that validate the restated oracle
+against the real reference when ``/root/reference`` is present.  ``/root/reference``
+does not exist on the GPU box, so nothing on the ``-m gpu`` / ``smoke()`` /
+``bench.py`` path may call into this module.
+
+Mechanism
+---------
+* ``nemo.collections.asr.parts.numba.rnnt_loss`` needs only torch + numba, but its
+  parent packages' ``__init__`` pull in hydra / lightning (absent).  We register bare
+  namespace modules for the parents so their ``__init__`` never run.
+* ``RNNTJoint`` / ``CTCLoss`` / ``RNNTLoss`` / the ``cl_baseline_*`` hooks cannot be
+  imported as modules (``nemo.core`` → hydra).  Their *source text* is lifted from the
+  reference files with ``ast`` at run time and executed against light stubs
+  (``typecheck`` → identity decorator, ``Loss`` → ``torch.nn.Module``).  No reference
+  source is copied into this repository; the code is executed where it lies.
+"""
+from __future__ import annotations
+
+import ast
+import os
+import sys
+import types
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+REF_ROOT = "/root/reference"
+NEMO_ROOT = os.path.join(REF_ROOT, "NeMo")
+ASR = os.path.join(NEMO_ROOT, "nemo", "collections", "asr")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(ASR, "parts", "numba", "rnnt_loss"))
+
+
+def _require():
+    if not available():
+        raise RuntimeError("reference tree not present at /root/reference (authoring container only)")
+
+
+def _stub_namespaces():
+    _require()
+    if NEMO_ROOT not in sys.path:
+        sys.path.insert(0, NEMO_ROOT)
+    for name in (
+        "nemo",
+        "nemo.collections",
+        "nemo.collections.asr",
+        "nemo.collections.asr.parts",
+        "nemo.collections.asr.parts.numba",
+    ):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(NEMO_ROOT, *name.split("."))]
+            sys.modules[name] = m
+
+
+def load_rnnt_loss():
+    """-> (RNNTLossNumba, rnnt_numpy.RNNTLoss) of the reference, CPU path."""
+    _stub_namespaces()
+    from nemo.collections.asr.parts.numba.rnnt_loss.rnnt_numpy import RNNTLoss as RNNTLossNumpy
+    from nemo.collections.asr.parts.numba.rnnt_loss.rnnt_pytorch import RNNTLossNumba
+
+    return RNNTLossNumba, RNNTLossNumpy
+
+
+# --------------------------------------------------------------------------- ast lifting
+
+
+def _parse(path: str) -> Tuple[str, ast.Module]:
+    with open(path, "r") as fh:
+        src = fh.read()
+    return src, ast.parse(src)
+
+
+def _strip_decorators(src: str, node: ast.AST, drop=("typecheck",)) -> str:
+    """Source of a def with the named decorators removed (others, e.g. @property, kept)."""
+    seg = ast.get_source_segment(src, node)
+    lines = seg.split("\n")
+    out = []
+    for ln in lines:
+        s = ln.strip()
+        if s.startswith("@") and any(s[1:].startswith(d) for d in drop):
+            continue
+        out.append(ln)
+    # decorators are not part of get_source_segment for FunctionDef in py>=3.8 (lineno is the def line)
+    deco = []
+    for d in getattr(node, "decorator_list", []):
+        dsrc = ast.get_source_segment(src, d)
+        if not any(dsrc.startswith(x) for x in drop):
+            deco.append("@" + dsrc)
+    return "\n".join(deco + out)
+
+
+def _class_methods(path: str, cls_name: str, names: Optional[List[str]] = None) -> Dict[str, str]:
+    src, tree = _parse(path)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == cls_name:
+            res = {}
+            for item in node.body:
+                if isinstance(item, (ast.FunctionDef,)):
+                    if names is None or item.name in names:
+                        key = item.name
+                        # property setters share the name; keep first (getter) unless unseen
+                        if key in res:
+                            continue
+                        res[key] = _strip_decorators(src, item)
+            return res
+    raise KeyError(cls_name)
+
+
+def _functions(path: str, names: List[str]) -> Dict[str, str]:
+    src, tree = _parse(path)
+    res = {}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            res[node.name] = _strip_decorators(src, node, drop=("record",))
+    missing = set(names) - set(res)
+    if missing:
+        raise KeyError(missing)
+    return res
+
+
+class _Logging:
+    def warning(self, *a, **k):
+        pass
+
+    def info(self, *a, **k):
+        pass
+
+
+def _build_class(cls_name: str, methods: Dict[str, str], bases: tuple, ns: Dict[str, Any]):
+    import textwrap
+
+    body = "\n\n".join(textwrap.indent(textwrap.dedent(m), "    ") for m in methods.values())
+    code = f"class {cls_name}(*__bases__):\n{body}\n"
+    ns = dict(ns)
+    ns["__bases__"] = bases
+    exec(compile(code, f"<reference:{cls_name}>", "exec"), ns)
+    return ns[cls_name]
+
+
+def load_joint_class():
+    """The reference's RNNTJoint (modules/rnnt.py:1175-1767) + AbstractRNNTJoint.joint
+    (rnnt_abstract.py:70-100), rebuilt on torch.nn.Module from the reference source text."""
+    _require()
+    import torch
+
+    names = [
+        "__init__", "forward", "project_encoder", "project_prednet", "joint_after_projection",
+        "_joint_net_modules", "num_classes_with_blank", "num_extra_outputs", "loss", "set_loss",
+        "wer", "set_wer", "fuse_loss_wer", "set_fuse_loss_wer", "fused_batch_size", "set_fused_batch_size",
+    ]
+    meths = _class_methods(os.path.join(ASR, "modules", "rnnt.py"), "RNNTJoint", names)
+    meths.update(_class_methods(os.path.join(ASR, "modules", "rnnt_abstract.py"), "AbstractRNNTJoint", ["joint"]))
+
+    class _Base(torch.nn.Module):
+        def is_adapter_available(self):
+            return False
+
+    ns = dict(torch=torch, Dict=Dict, Any=Any, Optional=Optional, List=List, Union=Union, Tuple=Tuple,
+              logging=_Logging())
+    return _build_class("RNNTJoint", meths, (_Base,), ns)
+
+
+def load_rnnt_loss_facade():
+    """The reference's RNNTLoss facade (losses/rnnt.py:333-508), default loss = warprnnt_numba."""
+    _require()
+    import torch
+
+    RNNTLossNumba, _ = load_rnnt_loss()
+    meths = _class_methods(os.path.join(ASR, "losses", "rnnt.py"), "RNNTLoss", ["__init__", "reduce", "forward"])
+
+    def resolve_rnnt_loss(loss_name, blank_idx, loss_kwargs=None):
+        # reference: losses/rnnt.py:206-330, branch 'warprnnt_numba' (:243-247); 'default' -> it (:158)
+        assert loss_name in ("default", "warprnnt_numba")
+        loss_kwargs = {} if loss_kwargs is None else dict(loss_kwargs)
+        fastemit_lambda = loss_kwargs.pop("fastemit_lambda", 0.0)
+        clamp = loss_kwargs.pop("clamp", -1.0)
+        return RNNTLossNumba(blank=blank_idx, reduction="none", fastemit_lambda=fastemit_lambda, clamp=clamp)
+
+    class _Cfg:
+        force_float32 = False
+
+    class _NumbaUtils:
+        @staticmethod
+        def is_numba_cuda_fp16_supported(return_reason=False):
+            return (False, "stub") if return_reason else False
+
+    ns = dict(torch=torch, List=List, resolve_rnnt_loss=resolve_rnnt_loss,
+              RNNT_LOSS_RESOLVER={"default": _Cfg, "warprnnt_numba": _Cfg}, numba_utils=_NumbaUtils,
+              logging=_Logging(), logging_mode=None)
+    return _build_class("RNNTLoss", meths, (torch.nn.Module,), ns)
+
+
+def load_ctc_loss_class():
+    """The reference's CTCLoss (losses/ctc.py:25-81), rebuilt on torch.nn.CTCLoss."""
+    _require()
+    import torch
+
+    meths = _class_methods(os.path.join(ASR, "losses", "ctc.py"), "CTCLoss", ["__init__", "reduce", "forward"])
+    ns = dict(torch=torch, nn=torch.nn)
+    return _build_class("CTCLoss", meths, (torch.nn.CTCLoss,), ns)
+
+
+def load_conv_asr_decoder_forward():
+    """Source-lifted ConvASRDecoder.forward (modules/conv_asr.py:458-490) as a free function."""
+    _require()
+    import torch
+
+    meths = _class_methods(os.path.join(ASR, "modules", "conv_asr.py"), "ConvASRDecoder", ["forward"])
+
+    class _Base(torch.nn.Module):
+        def is_adapter_available(self):
+            return False
+
+    return _build_class("ConvASRDecoderFwd", meths, (_Base,), dict(torch=torch))
+
+
+def load_cl_hooks():
+    """-> dict with the reference's get_penalty_grads (cl_baseline_ewc.py:69-81), penalty
+    (cl_baseline_mas.py:70-75) and the utils.py:273-321 parameter helpers."""
+    _require()
+    import torch
+
+    ns: Dict[str, Any] = dict(torch=torch)
+    srcs = {}
+    srcs.update(_functions(os.path.join(REF_ROOT, "cl_baseline_ewc.py"), ["get_penalty_grads"]))
+    srcs.update(_functions(os.path.join(REF_ROOT, "cl_baseline_mas.py"), ["penalty"]))
+    srcs.update(_functions(os.path.join(REF_ROOT, "utils.py"),
+                           ["get_params", "get_params_clone", "get_zero_params", "get_grads", "set_grads",
+                            "freeze_layer"]))
+    for name, s in srcs.items():
+        exec(compile(s, f"<reference:{name}>", "exec"), ns)
+    return {k: ns[k] for k in srcs}
+
+
+def kat_literals():
+    """Known-answer vectors held by the reference's own tests, lifted as literals.
+
+    RNNT: tests/collections/asr/numba/rnnt_loss/test_rnnt_pytorch.py (test_case_small :81-133,
+    test_case_big_tensor :189-318, test_case_small_clamp :357-404).
+    CTC:  tests/collections/asr/k2/test_ctc.py (test_case_small :85-121, _blank_last :124-188).
+    """
+    _require()
+    import numpy as np
+
+    def grab(path, cls, fn, var_names):
+        src, tree = _parse(path)
+        out = {}
+        for node in tree.body:
+            if isinstance(node, ast.ClassDef) and node.name == cls:
+                for item in node.body:
+                    if isinstance(item, ast.FunctionDef) and item.name == fn:
+                        for st in ast.walk(item):
+                            if isinstance(st, ast.Assign) and len(st.targets) == 1 and isinstance(st.targets[0], ast.Name):
+                                nm = st.targets[0].id
+                                if nm in var_names and nm not in out:
+                                    v = st.value
+                                    # unwrap np.array(<literal>) and np.array(<literal>).astype(dtype)
+                                    while isinstance(v, ast.Call):
+                                        if isinstance(v.func, ast.Attribute) and v.func.attr == "astype":
+                                            v = v.func.value
+                                        elif v.args:
+                                            v = v.args[0]
+                                        else:
+                                            break
+                                    out[nm] = ast.literal_eval(v)
+        missing = set(var_names) - set(out)
+        if missing:
+            raise KeyError((fn, missing))
+        return out
+
+    tdir = os.path.join(NEMO_ROOT, "tests", "collections", "asr")
+    rp = os.path.join(tdir, "numba", "rnnt_loss", "test_rnnt_pytorch.py")
+    cp = os.path.join(tdir, "k2", "test_ctc.py")
+    res = {}
+    d = grab(rp, "TestRNNTLossPytorch", "test_case_small", ["acts", "labels", "expected_cost", "expected_grads"])
+    res.update({f"rnnt_small_{k}": np.asarray(v) for k, v in d.items()})
+    d = grab(rp, "TestRNNTLossPytorch", "test_case_big_tensor",
+             ["activations", "labels", "expected_costs", "expected_grads"])
+    res.update({f"rnnt_big_{k}": np.asarray(v) for k, v in d.items()})
+    d = grab(rp, "TestRNNTLossPytorch", "test_case_small_clamp",
+             ["acts", "labels", "expected_cost", "expected_grads", "GRAD_CLAMP"])
+    res.update({f"rnnt_clamp_{k}": np.asarray(v) for k, v in d.items()})
+    d = grab(cp, "TestCTCLossK2", "test_case_small", ["acts", "labels", "expected_cost", "expected_grads"])
+    res.update({f"ctc_small_{k}": np.asarray(v) for k, v in d.items()})
+    d = grab(cp, "TestCTCLossK2", "test_case_small_blank_last", ["acts", "labels", "expected_cost", "expected_grads"])
+    res.update({f"ctc_blank_last_{k}": np.asarray(v) for k, v in d.items()})
+    return res
