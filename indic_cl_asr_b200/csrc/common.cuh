@@ -1,0 +1,126 @@
+// common.cuh — shared helpers for libclasr_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/clasr_b200.h"
+
+namespace clasr {
+
+constexpr int kNumSMs = 148;  // B200
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define CLASR_CHECK_ARG(cond, ...)              \
+  do {                                          \
+    if (!(cond)) {                              \
+      clasr::set_error(__VA_ARGS__);            \
+      return CLASR_STATUS_INVALID_VALUE;        \
+    }                                           \
+  } while (0)
+
+#define CLASR_CHECK_LAUNCH(name)                                              \
+  do {                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                     \
+    if (e__ != cudaSuccess) {                                                 \
+      clasr::set_error("%s: %s", name, cudaGetErrorString(e__));              \
+      return CLASR_STATUS_CUDA_ERROR;                                         \
+    }                                                                         \
+    clasr::count_launch();                                                    \
+  } while (0)
+
+__device__ __forceinline__ float neg_inf() { return -INFINITY; }
+
+// log(exp(a)+exp(b)) as rnnt_helper.log_sum_exp (reference rnnt_helper.py:32-44): -inf aware.
+__device__ __forceinline__ float log_sum_exp(float a, float b) {
+  if (a == -INFINITY) return b;
+  if (b == -INFINITY) return a;
+  float mx = fmaxf(a, b), mn = fminf(a, b);
+  return mx + log1pf(expf(mn - mx));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 128-bit accesses (read-once / write-once data: keep it out of L1)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+// same, for buffers the kernel also writes (no .nc: the read-only contract does not hold)
+__device__ __forceinline__ float4 ld_stream_rw(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float ld_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+// Lattice workspace layout shared by the materialised and fused transducer paths.
+// Diagonal-major ("skewed"): cell (t,u) of utterance b lives at ((b*ND + t+u)*U1 + u), ND = T+U1-1, so the
+// anti-diagonal wavefront reads/writes contiguous memory.
+struct LatticeWs {
+  float2* lp;     // [B,ND,U1] (log P(blank|t,u), log P(label_u|t,u))
+  float* alpha;   // [B,ND,U1]
+  float* beta;    // [B,ND,U1]
+  float* denom;   // [B,ND,U1]  negative log-sum-exp of the logits row (reduce.py:186-248)
+  float* ll_fwd;  // [B]
+  float* ll_bwd;  // [B]
+  int ND;
+};
+
+inline size_t lattice_ws_bytes(int B, int T, int U1) {
+  size_t cells = (size_t)B * (size_t)(T + U1 - 1) * (size_t)U1;
+  size_t bytes = cells * (sizeof(float2) + 3 * sizeof(float)) + 2 * (size_t)B * sizeof(float);
+  return (bytes + 255) / 256 * 256;
+}
+
+inline LatticeWs lattice_ws_carve(void* ws, int B, int T, int U1) {
+  LatticeWs w;
+  size_t cells = (size_t)B * (size_t)(T + U1 - 1) * (size_t)U1;
+  char* p = (char*)ws;
+  w.lp = (float2*)p;    p += cells * sizeof(float2);
+  w.alpha = (float*)p;  p += cells * sizeof(float);
+  w.beta = (float*)p;   p += cells * sizeof(float);
+  w.denom = (float*)p;  p += cells * sizeof(float);
+  w.ll_fwd = (float*)p; p += (size_t)B * sizeof(float);
+  w.ll_bwd = (float*)p;
+  w.ND = T + U1 - 1;
+  return w;
+}
+
+// launched from rnnt_loss.cu; reused by the fused joint
+int launch_rnnt_lattice(const LatticeWs& w, const int64_t* act_lens, const int64_t* label_lens, int B, int T, int U1,
+                        float fastemit_lambda, float* costs, cudaStream_t stream);
+
+}  // namespace clasr

@@ -1,0 +1,346 @@
+"""RNNTJoint with the reference's interface (NeMo/nemo/collections/asr/modules/rnnt.py:1175-1767).
+
+Kept: constructor arguments, parameter names (``pred.*``, ``enc.*``, ``joint_net.<i>.*`` /
+``joint_net.<i>.<lang>.*``) so state_dicts interchange, keyword-only ``forward``, ``joint`` /
+``project_encoder`` / ``project_prednet`` / ``joint_after_projection``, ``set_loss`` / ``set_wer`` /
+``fuse_loss_wer`` / ``fused_batch_size`` accessors, the continual-learning hooks ``store_sub_enc``,
+``store_sub_logits``, ``detach_sub_enc``, ``store_list`` / ``temp_logits``, and the error behaviour of the
+fused branch (:1331,1393-1416).
+
+Two compute strategies sit behind ``forward(fuse_loss_wer=True)``:
+
+``fused_impl='tcgen05'`` (default)
+    ONE pass over the whole batch: a tcgen05/TMEM GEMM whose epilogue forms the log-softmax denominator and
+    gathers the blank/label log-probs, the alpha/beta wavefront, and a second GEMM pass that recomputes the
+    logits tile-wise and contracts the gradient — the [B,T,U,V+1] tensor never exists in HBM, so the
+    reference's memory-driven sub-batch loop (:1425) is unnecessary.  Per-sample losses are identical to the
+    sub-batched ones (padding never contributes), and ``loss.reduce`` is applied to the same [B] vector.
+``fused_impl='materialised'``
+    the reference's structure — sub-batch loop, cuBLAS joint via torch, then this library's transducer-loss
+    kernels on the materialised logits.  Also what serves the hooks that must hand tensors back
+    (``store_sub_enc`` / ``store_sub_logits`` with ``detach_sub_enc=False``).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Union
+
+import torch
+
+from .. import _lib
+from .._typecheck import kwargs_only
+
+__all__ = ["RNNTJoint"]
+
+_ACTIVATIONS = ("relu", "sigmoid", "tanh")
+
+
+class RNNTJoint(torch.nn.Module):
+    def __init__(
+        self,
+        jointnet: Dict[str, Any],
+        num_classes: int,
+        num_extra_outputs: int = 0,
+        vocabulary: Optional[List] = None,
+        log_softmax: Optional[bool] = None,
+        preserve_memory: bool = False,
+        fuse_loss_wer: bool = False,
+        fused_batch_size: Optional[int] = None,
+        experimental_fuse_loss_wer: Any = None,
+        language_masks=None,
+        multilingual: bool = False,
+        language_keys: Optional[List] = None,
+        token_id_offsets=None,
+        offset_token_ids_by_token_id=None,
+        fused_impl: str = "tcgen05",
+        precision: str = "fp16x3",
+    ):
+        super().__init__()
+        self.vocabulary = vocabulary
+        self._vocab_size = num_classes
+        self._num_extra_outputs = num_extra_outputs
+        self._num_classes = num_classes + 1 + num_extra_outputs  # +1 blank
+        self.language_masks = language_masks
+        self.token_id_offsets = token_id_offsets
+        self.offset_token_ids_by_token_id = offset_token_ids_by_token_id
+        self.multilingual = multilingual
+        self.language_keys = language_keys
+
+        if experimental_fuse_loss_wer is not None:
+            fuse_loss_wer = experimental_fuse_loss_wer
+        self._fuse_loss_wer = fuse_loss_wer
+        self._fused_batch_size = fused_batch_size
+        if fuse_loss_wer and (fused_batch_size is None):
+            raise ValueError("If `fuse_loss_wer` is set, then `fused_batch_size` cannot be None!")
+        self._loss = None
+        self._wer = None
+
+        self.log_softmax = log_softmax
+        self.preserve_memory = preserve_memory  # accepted for compatibility; nothing here needs empty_cache()
+
+        self.encoder_hidden = jointnet["encoder_hidden"]
+        self.pred_hidden = jointnet["pred_hidden"]
+        self.joint_hidden = jointnet["joint_hidden"]
+        self.activation = jointnet["activation"]
+        dropout = jointnet.get("dropout", 0.0)
+        self._dropout_p = float(dropout or 0.0)
+
+        self.pred, self.enc, self.joint_net = self._joint_net_modules(
+            num_classes=self._num_classes, pred_n_hidden=self.pred_hidden, enc_n_hidden=self.encoder_hidden,
+            joint_n_hidden=self.joint_hidden, activation=self.activation, dropout=dropout)
+
+        self._rnnt_export = False
+        self.temperature = 1.0
+        self.store_sub_enc = False
+        self.detach_sub_enc = True
+        self.store_sub_logits = False
+
+        if fused_impl not in ("tcgen05", "materialised"):
+            raise ValueError("fused_impl must be 'tcgen05' or 'materialised'")
+        if precision not in _lib.PREC:
+            raise ValueError(f"precision must be one of {sorted(_lib.PREC)}")
+        self.fused_impl = fused_impl
+        self.precision = precision
+
+    # ------------------------------------------------------------------ construction (:1667-1710)
+    def _joint_net_modules(self, num_classes, pred_n_hidden, enc_n_hidden, joint_n_hidden, activation, dropout):
+        pred = torch.nn.Linear(pred_n_hidden, joint_n_hidden)
+        enc = torch.nn.Linear(enc_n_hidden, joint_n_hidden)
+        if activation not in _ACTIVATIONS:
+            raise ValueError("Unsupported activation for joint step - please pass one of [relu, sigmoid, tanh]")
+        act = {"relu": lambda: torch.nn.ReLU(inplace=True), "sigmoid": torch.nn.Sigmoid,
+               "tanh": torch.nn.Tanh}[activation.lower()]()
+        if self.multilingual:
+            final = torch.nn.ModuleDict()
+            per_lang = self._vocab_size // len(self.language_keys) + 1
+            for lang in self.language_keys:
+                final[lang] = torch.nn.Linear(joint_n_hidden, per_lang)
+        else:
+            final = torch.nn.Linear(joint_n_hidden, num_classes)
+        layers = [act] + ([torch.nn.Dropout(p=dropout)] if dropout else []) + [final]
+        return pred, enc, torch.nn.Sequential(*layers)
+
+    def is_adapter_available(self) -> bool:  # adapters are outside the hot path
+        return False
+
+    # ------------------------------------------------------------------ small accessors (:1723-1766)
+    @property
+    def num_classes_with_blank(self):
+        return self._num_classes
+
+    @property
+    def num_extra_outputs(self):
+        return self._num_extra_outputs
+
+    @property
+    def loss(self):
+        return self._loss
+
+    def set_loss(self, loss):
+        if not self._fuse_loss_wer:
+            raise ValueError("Attempting to set loss module even though `fuse_loss_wer` is not set!")
+        self._loss = loss
+
+    @property
+    def wer(self):
+        return self._wer
+
+    def set_wer(self, wer):
+        if not self._fuse_loss_wer:
+            raise ValueError("Attempting to set WER module even though `fuse_loss_wer` is not set!")
+        self._wer = wer
+
+    @property
+    def fuse_loss_wer(self):
+        return self._fuse_loss_wer
+
+    def set_fuse_loss_wer(self, fuse_loss_wer, loss=None, metric=None):
+        self._fuse_loss_wer = fuse_loss_wer
+        self._loss = loss
+        self._wer = metric
+
+    @property
+    def fused_batch_size(self):
+        return self._fused_batch_size
+
+    def set_fused_batch_size(self, fused_batch_size):
+        self._fused_batch_size = fused_batch_size
+
+    # ------------------------------------------------------------------ joint maths (:1563-1665)
+    def project_encoder(self, encoder_output: torch.Tensor) -> torch.Tensor:
+        return self.enc(encoder_output)
+
+    def project_prednet(self, prednet_output: torch.Tensor) -> torch.Tensor:
+        return self.pred(prednet_output)
+
+    def joint(self, f: torch.Tensor, g: torch.Tensor, language_ids=None) -> torch.Tensor:
+        return self.joint_after_projection(self.project_encoder(f), self.project_prednet(g), language_ids)
+
+    def _final_linear(self, language_ids=None) -> torch.nn.Linear:
+        last = self.joint_net[-1]
+        if isinstance(last, torch.nn.ModuleDict):
+            if language_ids is None:
+                raise ValueError("multilingual joint needs language_ids")
+            if len(set(language_ids)) != 1:
+                return None  # mixed-language batch: handled per sample
+            return last[language_ids[0]]
+        return last
+
+    def joint_after_projection(self, f: torch.Tensor, g: torch.Tensor, language_ids=None) -> torch.Tensor:
+        """Materialising joint: [B,T,H] x [B,U,H] -> logits [B,T,U,V+1] (cuBLAS through torch)."""
+        inp = f.unsqueeze(dim=2) + g.unsqueeze(dim=1)
+        if language_ids is not None and isinstance(self.joint_net[-1], torch.nn.ModuleDict):
+            for module in self.joint_net[:-1]:
+                inp = module(inp)
+            lin = self._final_linear(language_ids)
+            if lin is not None:
+                res = lin(inp)
+            else:
+                res = torch.stack([self.joint_net[-1][lang](x) for x, lang in zip(inp, language_ids)])
+        else:
+            res = self.joint_net(inp)
+        del inp
+        if self.store_sub_logits:
+            self.temp_logits = res.clone()
+        apply_ls = (not res.is_cuda) if self.log_softmax is None else bool(self.log_softmax)
+        if apply_ls:
+            if self.temperature != 1.0:
+                res = (res / self.temperature).log_softmax(dim=-1)
+            else:
+                res = res.log_softmax(dim=-1)
+        return res
+
+    # ------------------------------------------------------------------ forward (:1375-1561)
+    @kwargs_only
+    def forward(
+        self,
+        encoder_outputs: torch.Tensor,
+        decoder_outputs: Optional[torch.Tensor],
+        encoder_lengths: Optional[torch.Tensor] = None,
+        transcripts: Optional[torch.Tensor] = None,
+        transcript_lengths: Optional[torch.Tensor] = None,
+        compute_wer: bool = False,
+        language_ids=None,
+    ) -> Union[torch.Tensor, List[Optional[torch.Tensor]]]:
+        encoder_outputs = encoder_outputs.transpose(1, 2)  # (B, T, D)
+        if decoder_outputs is not None:
+            decoder_outputs = decoder_outputs.transpose(1, 2)  # (B, U, D)
+
+        if not self._fuse_loss_wer:
+            if decoder_outputs is None:
+                raise ValueError(
+                    "decoder_outputs passed is None, and `fuse_loss_wer` is not set. "
+                    "decoder_outputs can only be None for fused step!")
+            return self.joint(encoder_outputs, decoder_outputs, language_ids=language_ids)
+
+        if self._loss is None or self._wer is None:
+            raise ValueError("`fuse_loss_wer` flag is set, but `loss` and `wer` modules were not provided! ")
+        if self._fused_batch_size is None:
+            raise ValueError("If `fuse_loss_wer` is set, then `fused_batch_size` cannot be None!")
+        if (encoder_lengths is None) or (transcript_lengths is None):
+            raise ValueError("`fuse_loss_wer` is set, therefore encoder and target lengths must be provided as well!")
+
+        needs_tensors = self.store_sub_enc or self.store_sub_logits
+        use_tcgen05 = (
+            self.fused_impl == "tcgen05" and decoder_outputs is not None and not needs_tensors
+            and self._tcgen05_supported(language_ids)
+        )
+        if use_tcgen05:
+            losses = self._forward_fused_tcgen05(encoder_outputs, decoder_outputs, encoder_lengths, transcripts,
+                                                 transcript_lengths, language_ids)
+            wer, wer_num, wer_denom = self._wer_pass(encoder_outputs, encoder_lengths, transcripts,
+                                                     transcript_lengths, language_ids) if compute_wer else (None,) * 3
+            return losses, wer, wer_num, wer_denom
+        return self._forward_fused_materialised(encoder_outputs, decoder_outputs, encoder_lengths, transcripts,
+                                                transcript_lengths, compute_wer, language_ids)
+
+    # -- the reference's structure: sub-batch loop over materialised logits ------------------------
+    def _sub_batches(self, batch_size):
+        for begin in range(0, batch_size, self._fused_batch_size):
+            yield begin, min(begin + self._fused_batch_size, batch_size)
+
+    def _wer_update(self, sub_enc, sub_enc_lens, sub_transcripts, sub_transcript_lens, lang_ids):
+        kw = dict(predictions=sub_enc.transpose(1, 2).detach(), predictions_lengths=sub_enc_lens,
+                  targets=sub_transcripts.detach(), targets_lengths=sub_transcript_lens)
+        if lang_ids is not None:
+            kw["lang_ids"] = lang_ids
+        self.wer.update(**kw)
+        res = self.wer.compute()
+        self.wer.reset()
+        return res
+
+    def _wer_pass(self, enc, enc_lens, transcripts, transcript_lens, language_ids):
+        wers, nums, denoms = [], [], []
+        for begin, end in self._sub_batches(int(enc.size(0))):
+            sl = slice(begin, end)
+            mt, mu = int(enc_lens[sl].max()), int(transcript_lens[sl].max())
+            w, n, d = self._wer_update(enc[sl, :mt], enc_lens[sl], transcripts[sl, :mu], transcript_lens[sl],
+                                       None if language_ids is None else language_ids[begin:end])
+            wers.append(w), nums.append(n), denoms.append(d)
+        return sum(wers) / len(wers), sum(nums), sum(denoms)
+
+    def _forward_fused_materialised(self, enc, dec, enc_lens, transcripts, transcript_lens, compute_wer,
+                                    language_ids):
+        losses, target_lengths, stored = [], [], []
+        wers, nums, denoms = [], [], []
+        for begin, end in self._sub_batches(int(enc.size(0))):
+            sl = slice(begin, end)
+            sub_enc_lens, sub_tr_lens = enc_lens[sl], transcript_lens[sl]
+            max_t, max_u = int(sub_enc_lens.max()), int(sub_tr_lens.max())
+            sub_enc, sub_tr = enc[sl], transcripts[sl]
+            lang = None if language_ids is None else language_ids[begin:end]
+            if dec is not None:
+                sub_enc = sub_enc[:, :max_t]
+                sub_dec = dec[sl, : max_u + 1]
+                sub_joint = self.joint(sub_enc, sub_dec, language_ids=lang)
+                sub_tr = sub_tr[:, :max_u]
+                for flag, src in ((self.store_sub_enc, sub_joint),
+                                  (self.store_sub_logits, getattr(self, "temp_logits", None) if self.store_sub_logits else None)):
+                    if flag:
+                        keep = src.detach().clone() if (self.detach_sub_enc and src.requires_grad) else src.clone()
+                        stored.append(keep)
+                reduction = self.loss.reduction
+                self.loss.reduction = None
+                losses.append(self.loss(log_probs=sub_joint, targets=sub_tr, input_lengths=sub_enc_lens,
+                                        target_lengths=sub_tr_lens))
+                target_lengths.append(sub_tr_lens)
+                self.loss.reduction = reduction
+            else:
+                losses = None
+            if compute_wer:
+                w, n, d = self._wer_update(sub_enc, sub_enc_lens, sub_tr, sub_tr_lens, lang)
+                wers.append(w), nums.append(n), denoms.append(d)
+        if losses is not None:
+            losses = self.loss.reduce(losses, target_lengths)
+        if compute_wer:
+            wer, wer_num, wer_denom = sum(wers) / len(wers), sum(nums), sum(denoms)
+        else:
+            wer = wer_num = wer_denom = None
+        if self.store_sub_enc or self.store_sub_logits:
+            self.store_list = stored
+        return losses, wer, wer_num, wer_denom
+
+    # -- B200 path: fused joint + loss, logits never materialised -----------------------------------
+    def _tcgen05_supported(self, language_ids) -> bool:
+        if self._dropout_p > 0.0 and self.training:
+            return False  # TODO(fused dropout): Philox mask regenerated in the recompute pass
+        if self.temperature != 1.0 or self.log_softmax:
+            return False
+        if self.joint_hidden % 64 != 0:
+            return False
+        if isinstance(self.joint_net[-1], torch.nn.ModuleDict):
+            return language_ids is not None and len(set(language_ids)) == 1
+        return True
+
+    def _forward_fused_tcgen05(self, enc, dec, enc_lens, transcripts, transcript_lens, language_ids):
+        from ..fused import fused_joint_rnnt_loss
+
+        lin = self._final_linear(language_ids)
+        f = self.project_encoder(enc)   # [B,T,H]  (small cuBLAS GEMM)
+        g = self.project_prednet(dec)   # [B,U1,H]
+        loss_mod = self.loss
+        per_sample = fused_joint_rnnt_loss(
+            f, g, lin.weight, lin.bias, transcripts, enc_lens, transcript_lens,
+            blank=loss_mod._blank, activation=self.activation, precision=self.precision,
+            fastemit_lambda=float(getattr(loss_mod, "fastemit_lambda", 0.0)),
+            clamp=float(getattr(loss_mod, "clamp", 0.0)))
+        return loss_mod.reduce(per_sample, transcript_lens.long())
