@@ -61,7 +61,7 @@ CLASR_API int64_t clasr_launch_count(void);
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   int64_t start; /* first float of the chunk (multiple of 4)                 */
-  int32_t len;   /* floats in the chunk (multiple of 4, <= CLASR_SWEEP_CHUNK) */
+  int32_t len;   /* floats in the chunk (<= CLASR_SWEEP_CHUNK; the <4-float alignment pad is masked) */
   int32_t seg;   /* index of the parameter tensor the chunk belongs to        */
 } clasr_sweep_item;
 
@@ -89,7 +89,7 @@ CLASR_API int clasr_cl_fisher_accum(float* fisher, const float* grad, int64_t n,
 CLASR_API int clasr_cl_mas_accum(float* omega, const float* grad, int64_t n, void* stream);
 
 /* Finalise + merge — replaces cl_baseline_ewc.py:267-280 and cl_baseline_mas.py:283-287:
- *   src[i] /= count                           (F /= total_ds ; Omega /= len(dataloader))
+ *   src[i] *= (1.0f / count)                  (F /= total_ds ; Omega /= len(dataloader); as ATen's scalar div)
  *   dst[i]  = first ? src[i] : gamma * dst[i] + src[i]
  * dst may equal src (then only the scaling is applied). */
 CLASR_API int clasr_cl_scale_merge(float* dst, float* src, int64_t n, float count, float gamma, int first, void* stream);

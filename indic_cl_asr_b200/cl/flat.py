@@ -46,9 +46,8 @@ class Layout:
     def sweep_items(self) -> np.ndarray:
         items = []
         for seg, (off, n) in enumerate(zip(self.offsets, self.numels)):
-            padded = (n + 3) // 4 * 4
-            for s in range(0, padded, SWEEP_CHUNK):
-                items.append((off + s, min(SWEEP_CHUNK, padded - s), seg))
+            for s in range(0, n, SWEEP_CHUNK):
+                items.append((off + s, min(SWEEP_CHUNK, n - s), seg))
         return np.array(items, dtype=_ITEM_DTYPE)
 
     def device_tables(self, device) -> Tuple[torch.Tensor, torch.Tensor, int]:

@@ -89,34 +89,53 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
 // Lattice workspace layout shared by the materialised and fused transducer paths.
 // Diagonal-major ("skewed"): cell (t,u) of utterance b lives at ((b*ND + t+u)*U1 + u), ND = T+U1-1, so the
 // anti-diagonal wavefront reads/writes contiguous memory.
+//
+// Precision: at the named sizes the forward/backward variables reach magnitudes of ~2.4e3, where one fp32 ulp
+// (2.4e-4) already exceeds the 1e-4 gradient tolerance once exponentiated, and an fp32 log-space recursion
+// accumulates that rounding over T+U steps.  The wavefront therefore carries alpha/beta in fp64 but does all
+// transcendental work in fp32 on *differences* (|x| small): v = max + log1pf(expf(min - max)).  Per-step error
+// is then ~1e-7 absolute, independent of |alpha|.  Storage is fp64 too (18 MB at B=32,T=250,U=100: L2-resident).
 struct LatticeWs {
-  float2* lp;     // [B,ND,U1] (log P(blank|t,u), log P(label_u|t,u))
-  float* alpha;   // [B,ND,U1]
-  float* beta;    // [B,ND,U1]
-  float* denom;   // [B,ND,U1]  negative log-sum-exp of the logits row (reduce.py:186-248)
-  float* ll_fwd;  // [B]
-  float* ll_bwd;  // [B]
+  float2* lp;      // [B,ND,U1] (log P(blank|t,u), log P(label_u|t,u))
+  double* alpha;   // [B,ND,U1]
+  double* beta;    // [B,ND,U1]
+  float* denom;    // [B,ND,U1] negative log-sum-exp of the logits row (reduce.py:186-248)
+  double* ll_fwd;  // [B]
+  double* ll_bwd;  // [B]
   int ND;
 };
 
 inline size_t lattice_ws_bytes(int B, int T, int U1) {
-  size_t cells = (size_t)B * (size_t)(T + U1 - 1) * (size_t)U1;
-  size_t bytes = cells * (sizeof(float2) + 3 * sizeof(float)) + 2 * (size_t)B * sizeof(float);
+  size_t nd = (size_t)(T + U1 - 1);
+  size_t cells = (size_t)B * nd * (size_t)U1;
+  size_t bytes = cells * (sizeof(float2) + 2 * sizeof(double) + sizeof(float));
+  bytes = (bytes + 15) / 16 * 16;
+  bytes += 2 * (size_t)B * sizeof(double);
   return (bytes + 255) / 256 * 256;
 }
 
 inline LatticeWs lattice_ws_carve(void* ws, int B, int T, int U1) {
   LatticeWs w;
-  size_t cells = (size_t)B * (size_t)(T + U1 - 1) * (size_t)U1;
+  size_t nd = (size_t)(T + U1 - 1);
+  size_t cells = (size_t)B * nd * (size_t)U1;
   char* p = (char*)ws;
-  w.lp = (float2*)p;    p += cells * sizeof(float2);
-  w.alpha = (float*)p;  p += cells * sizeof(float);
-  w.beta = (float*)p;   p += cells * sizeof(float);
-  w.denom = (float*)p;  p += cells * sizeof(float);
-  w.ll_fwd = (float*)p; p += (size_t)B * sizeof(float);
-  w.ll_bwd = (float*)p;
-  w.ND = T + U1 - 1;
+  w.lp = (float2*)p;     p += cells * sizeof(float2);
+  w.alpha = (double*)p;  p += cells * sizeof(double);
+  w.beta = (double*)p;   p += cells * sizeof(double);
+  w.denom = (float*)p;   p += cells * sizeof(float);
+  p = (char*)ws + ((size_t)(p - (char*)ws) + 15) / 16 * 16;
+  w.ll_fwd = (double*)p; p += (size_t)B * sizeof(double);
+  w.ll_bwd = (double*)p;
+  w.ND = (int)nd;
   return w;
+}
+
+// log(exp(a)+exp(b)) with fp64 carriers and fp32 transcendentals on the (non-positive) difference.
+__device__ __forceinline__ double log_sum_exp_d(double a, double b) {
+  if (a == -INFINITY) return b;
+  if (b == -INFINITY) return a;
+  const double mx = fmax(a, b), mn = fmin(a, b);
+  return mx + (double)log1pf(expf((float)(mn - mx)));
 }
 
 // launched from rnnt_loss.cu; reused by the fused joint

@@ -15,35 +15,49 @@
 
 namespace clasr {
 
+// alpha / beta are carried and stored in fp64 while all transcendental work is fp32 on differences (see
+// LatticeWs in common.cuh for the rationale: |alpha| ~ 2e3 at the named sizes defeats an fp32 recursion).
 struct CtcWs {
-  float* alpha;  // [B,T,S]
-  float* beta;   // [B,T,S]
-  float* nll;    // [B] raw negative log-likelihood (inf when infeasible)
+  double* alpha;  // [B,T,S]
+  double* beta;   // [B,T,S]
+  double* nll;    // [B] raw negative log-likelihood (inf when infeasible)
   int S;
 };
 
 inline size_t ctc_ws_bytes(int B, int T, int maxU) {
   size_t S = 2 * (size_t)maxU + 1;
-  size_t bytes = 2 * (size_t)B * T * S * sizeof(float) + (size_t)B * sizeof(float);
+  size_t bytes = 2 * (size_t)B * T * S * sizeof(double) + (size_t)B * sizeof(double);
   return (bytes + 255) / 256 * 256;
 }
 inline CtcWs ctc_ws_carve(void* ws, int B, int T, int maxU) {
   CtcWs w;
   w.S = 2 * maxU + 1;
   size_t n = (size_t)B * T * w.S;
-  w.alpha = (float*)ws;
+  w.alpha = (double*)ws;
   w.beta = w.alpha + n;
   w.nll = w.beta + n;
   return w;
 }
 
-__device__ __forceinline__ float lse3(float a, float b, float c) {
-  float m = fmaxf(a, fmaxf(b, c));
+__device__ __forceinline__ double lse3_d(double a, double b, double c) {
+  const double m = fmax(a, fmax(b, c));
   if (m == -INFINITY) return -INFINITY;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  const float s = expf((float)(a - m)) + expf((float)(b - m)) + expf((float)(c - m));
+  return m + (double)logf(s);
 }
 
 constexpr int kCtcDepth = 4;  // prefetch distance (time steps) of the log_probs gather
+
+// One step of the recursion for lattice state s (shared by the two code paths below).
+__device__ __forceinline__ double ctc_step(const double* prev, int pad, int s, int Sb, bool backward, bool first,
+                                           bool skip, float y) {
+  if (first) {
+    if (!backward) return (s <= 1) ? (double)y : -INFINITY;      // alpha_0(0), alpha_0(1)
+    return (s >= Sb - 2) ? (double)y : -INFINITY;                // beta_{T-1}(S-1), beta_{T-1}(S-2)
+  }
+  if (!backward) return lse3_d(prev[pad + s], prev[pad + s - 1], skip ? prev[pad + s - 2] : -INFINITY) + (double)y;
+  return lse3_d(prev[pad + s], prev[pad + s + 1], skip ? prev[pad + s + 2] : -INFINITY) + (double)y;
+}
 
 __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const float* __restrict__ log_probs,
                                                            const int64_t* __restrict__ targets,
@@ -52,7 +66,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const float* __restri
                                                            const int64_t* __restrict__ target_lens, int T, int Vp,
                                                            int blank, int zero_infinity, CtcWs w,
                                                            float* __restrict__ nll_out) {
-  extern __shared__ float sm[];  // [2][S_b + 2]  (2 leading pad slots = -inf for s-1, s-2 / trailing for s+1, s+2)
+  extern __shared__ double smd[];  // [2][S_b + 4]: 2 pad slots (= -inf) on each side for the s-1,s-2 / s+1,s+2 reads
   const int b = blockIdx.x;
   const bool backward = blockIdx.y == 1;
   const int Tb = (int)input_lens[b];
@@ -60,124 +74,87 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const float* __restri
   const int Sb = 2 * Ub + 1;
   const int S = w.S;
   const float* __restrict__ lp = log_probs + (int64_t)b * T * Vp;
-  float* __restrict__ out = (backward ? w.beta : w.alpha) + (int64_t)b * T * S;
+  double* __restrict__ out = (backward ? w.beta : w.alpha) + (int64_t)b * T * S;
   const int64_t* __restrict__ tg = targets + (int64_t)b * target_stride;
   const int pad = 2;
   const int W = Sb + 2 * pad;
-  float* buf0 = sm;
-  float* buf1 = sm + W;
-  for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) sm[i] = -INFINITY;
+  double* prev = smd;
+  double* nxt = smd + W;
+  for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) smd[i] = -INFINITY;
   if (Tb <= 0) {
     if (threadIdx.x == 0 && !backward) {
-      // torch: zero-length input with non-empty target is infeasible
-      float v = (Ub == 0) ? 0.f : INFINITY;
-      w.nll[b] = v;
+      // torch: zero-length input with a non-empty target is infeasible
+      const float v = (Ub == 0) ? 0.f : INFINITY;
+      w.nll[b] = (double)v;
       nll_out[b] = (zero_infinity && v == INFINITY) ? 0.f : v;
     }
     return;
   }
   __syncthreads();
 
-  // The common case (2U+1 <= blockDim) gives each thread one lattice state and a register prefetch queue.
-  const int nstates_per_thread = (Sb + blockDim.x - 1) / blockDim.x;
-  if (nstates_per_thread == 1) {
-    const int s = threadIdx.x;
-    const bool active = s < Sb;
-    int cls = blank;
-    bool skip = false;  // forward: may come from s-2 ; backward: may go to s+2
-    if (active && (s & 1)) {
-      cls = (int)tg[s >> 1];
-      if (!backward) skip = (s >= 3) && ((int)tg[(s >> 1) - 1] != cls);
-      else skip = (s + 2 < Sb) && ((int)tg[(s >> 1) + 1] != cls);
-    }
-    // prefetch queue
-    float q[kCtcDepth];
+  const bool one_state = Sb <= (int)blockDim.x;
+  // per-thread constants of the one-state path
+  const int s1 = threadIdx.x;
+  const bool active = one_state && s1 < Sb;
+  int cls1 = blank;
+  bool skip1 = false;  // forward: may come from s-2 ; backward: may go to s+2
+  if (active && (s1 & 1)) {
+    cls1 = (int)tg[s1 >> 1];
+    if (!backward) skip1 = (s1 >= 3) && ((int)tg[(s1 >> 1) - 1] != cls1);
+    else skip1 = (s1 + 2 < Sb) && ((int)tg[(s1 >> 1) + 1] != cls1);
+  }
+  float q[kCtcDepth];
 #pragma unroll
-    for (int d = 0; d < kCtcDepth; ++d) {
-      int step = d;  // step index 0.. ; time index t = forward ? step : Tb-1-step
-      int t = backward ? Tb - 1 - step : step;
-      q[d] = (active && step < Tb) ? __ldg(lp + (int64_t)t * Vp + cls) : 0.f;
-    }
-    float* prev = buf0;
-    float* nxt = buf1;
-    for (int step0 = 0; step0 < Tb; step0 += kCtcDepth) {
+  for (int dd = 0; dd < kCtcDepth; ++dd) {
+    const int t = backward ? Tb - 1 - dd : dd;
+    q[dd] = (active && dd < Tb) ? __ldg(lp + (int64_t)t * Vp + cls1) : 0.f;
+  }
+
+  for (int step0 = 0; step0 < Tb; step0 += kCtcDepth) {
 #pragma unroll
-      for (int d = 0; d < kCtcDepth; ++d) {
-        const int step = step0 + d;
-        if (step < Tb) {  // uniform across the block
-          const int t = backward ? Tb - 1 - step : step;
-          const float y = q[d];
+    for (int dd = 0; dd < kCtcDepth; ++dd) {
+      const int step = step0 + dd;
+      if (step < Tb) {  // uniform across the block
+        const int t = backward ? Tb - 1 - step : step;
+        if (one_state) {
+          const float y = q[dd];
           {  // refill this slot for step + kCtcDepth
             const int ns = step + kCtcDepth;
             const int nt = backward ? Tb - 1 - ns : ns;
-            q[d] = (active && ns < Tb) ? __ldg(lp + (int64_t)nt * Vp + cls) : 0.f;
+            q[dd] = (active && ns < Tb) ? __ldg(lp + (int64_t)nt * Vp + cls1) : 0.f;
           }
-          float v = -INFINITY;
           if (active) {
-            if (step == 0) {
-              if (!backward) v = (s <= 1) ? y : -INFINITY;             // alpha_0(0), alpha_0(1)
-              else v = (s >= Sb - 2) ? y : -INFINITY;                  // beta_{T-1}(S-1), beta_{T-1}(S-2)
-            } else if (!backward) {
-              const float a0 = prev[pad + s], a1 = prev[pad + s - 1];
-              const float a2 = skip ? prev[pad + s - 2] : -INFINITY;
-              v = lse3(a0, a1, a2) + y;
-            } else {
-              const float b0 = prev[pad + s], b1 = prev[pad + s + 1];
-              const float b2 = skip ? prev[pad + s + 2] : -INFINITY;
-              v = lse3(b0, b1, b2) + y;
+            const double v = ctc_step(prev, pad, s1, Sb, backward, step == 0, skip1, y);
+            nxt[pad + s1] = v;
+            out[(int64_t)t * S + s1] = v;
+          }
+        } else {
+          // very long targets (2U+1 > 1024): several states per thread, no prefetch queue
+          for (int s = threadIdx.x; s < Sb; s += blockDim.x) {
+            int cls = blank;
+            bool skip = false;
+            if (s & 1) {
+              cls = (int)tg[s >> 1];
+              if (!backward) skip = (s >= 3) && ((int)tg[(s >> 1) - 1] != cls);
+              else skip = (s + 2 < Sb) && ((int)tg[(s >> 1) + 1] != cls);
             }
+            const float y = __ldg(lp + (int64_t)t * Vp + cls);
+            const double v = ctc_step(prev, pad, s, Sb, backward, step == 0, skip, y);
             nxt[pad + s] = v;
             out[(int64_t)t * S + s] = v;
           }
-          __syncthreads();
-          float* tmp = prev; prev = nxt; nxt = tmp;
         }
+        __syncthreads();
+        double* tmp = prev; prev = nxt; nxt = tmp;
       }
     }
-    if (!backward && threadIdx.x == 0) {
-      float l = prev[pad + Sb - 1];
-      if (Sb > 1) l = log_sum_exp(l, prev[pad + Sb - 2]);
-      const float nll = -l;
-      w.nll[b] = nll;
-      nll_out[b] = (zero_infinity && nll == INFINITY) ? 0.f : nll;
-    }
-  } else {
-    // General (very long targets, 2U+1 > 1024): states looped inside the time loop, no prefetch queue.
-    float* prev = buf0;
-    float* nxt = buf1;
-    for (int step = 0; step < Tb; ++step) {
-      const int t = backward ? Tb - 1 - step : step;
-      for (int s = threadIdx.x; s < Sb; s += blockDim.x) {
-        int cls = blank;
-        bool skip = false;
-        if (s & 1) {
-          cls = (int)tg[s >> 1];
-          if (!backward) skip = (s >= 3) && ((int)tg[(s >> 1) - 1] != cls);
-          else skip = (s + 2 < Sb) && ((int)tg[(s >> 1) + 1] != cls);
-        }
-        const float y = __ldg(lp + (int64_t)t * Vp + cls);
-        float v;
-        if (step == 0) {
-          if (!backward) v = (s <= 1) ? y : -INFINITY;
-          else v = (s >= Sb - 2) ? y : -INFINITY;
-        } else if (!backward) {
-          v = lse3(prev[pad + s], prev[pad + s - 1], skip ? prev[pad + s - 2] : -INFINITY) + y;
-        } else {
-          v = lse3(prev[pad + s], prev[pad + s + 1], skip ? prev[pad + s + 2] : -INFINITY) + y;
-        }
-        nxt[pad + s] = v;
-        out[(int64_t)t * S + s] = v;
-      }
-      __syncthreads();
-      float* tmp = prev; prev = nxt; nxt = tmp;
-    }
-    if (!backward && threadIdx.x == 0) {
-      float l = prev[pad + Sb - 1];
-      if (Sb > 1) l = log_sum_exp(l, prev[pad + Sb - 2]);
-      const float nll = -l;
-      w.nll[b] = nll;
-      nll_out[b] = (zero_infinity && nll == INFINITY) ? 0.f : nll;
-    }
+  }
+  if (!backward && threadIdx.x == 0) {
+    double l = prev[pad + Sb - 1];
+    if (Sb > 1) l = log_sum_exp_d(l, prev[pad + Sb - 2]);
+    const double nll = -l;
+    w.nll[b] = nll;
+    nll_out[b] = (zero_infinity && nll == (double)INFINITY) ? 0.f : (float)nll;
   }
 }
 
@@ -195,9 +172,9 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const float* __restrict__
   const int Ub = (int)target_lens[b];
   const int Sb = 2 * Ub + 1;
   const int S = w.S;
-  const float nll = w.nll[b];
+  const double nll = w.nll[b];
   float* __restrict__ g = grad + ((int64_t)b * T + t) * Vp;
-  const bool infeasible = (nll == INFINITY);
+  const bool infeasible = (nll == (double)INFINITY);
   if (t >= Tb || (infeasible && zero_infinity)) {
     for (int c = threadIdx.x; c < Vp; c += blockDim.x) g[c] = 0.f;
     return;
@@ -205,13 +182,13 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const float* __restrict__
   const float* __restrict__ lp = log_probs + ((int64_t)b * T + t) * Vp;
   for (int c = threadIdx.x; c < Vp; c += blockDim.x) occ[c] = 0.f;
   __syncthreads();
-  const float* __restrict__ al = w.alpha + ((int64_t)b * T + t) * S;
-  const float* __restrict__ be = w.beta + ((int64_t)b * T + t) * S;
+  const double* __restrict__ al = w.alpha + ((int64_t)b * T + t) * S;
+  const double* __restrict__ be = w.beta + ((int64_t)b * T + t) * S;
   const int64_t* __restrict__ tg = targets + (int64_t)b * target_stride;
   for (int s = threadIdx.x; s < Sb; s += blockDim.x) {
     const int cls = (s & 1) ? (int)tg[s >> 1] : blank;
     // alpha_t(s) * beta_t(s) / (y_t(cls) * P(l|x)) : posterior mass of state s at time t, in [0,1]
-    const float e = al[s] + be[s] + nll - __ldg(lp + cls);
+    const float e = (float)(al[s] + be[s] + nll - (double)__ldg(lp + cls));
     if (e > -INFINITY) atomicAdd(occ + cls, expf(e));
   }
   __syncthreads();
@@ -288,7 +265,7 @@ extern "C" int clasr_ctc_loss_fwd(const float* log_probs, const int64_t* targets
   CtcWs w = ctc_ws_carve(workspace, B, T, max_target_len);
   int threads = ((w.S + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
-  size_t smem = (size_t)2 * (w.S + 4) * sizeof(float);
+  size_t smem = (size_t)2 * (w.S + 4) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     CLASR_CHECK_ARG(e == cudaSuccess, "ctc_loss_fwd: target too long for shared memory (%zu bytes)", smem);

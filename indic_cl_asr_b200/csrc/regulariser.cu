@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) penalty_grad_kernel(
   __shared__ float warp_part[kSweepThreads / 32];
   for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
     const clasr_sweep_item item = items[it];
-    const int nvec = item.len >> 2;
+    const int nvec = (item.len + 3) >> 2;  // item.len = true floats; the <4-float pad of a tensor is masked to 0
     const float4* th = reinterpret_cast<const float4*>(theta + item.start);
     const float4* ts = reinterpret_cast<const float4*>(theta_star + item.start);
     const float4* fi = reinterpret_cast<const float4*>(fisher + item.start);
@@ -55,6 +55,12 @@ __global__ void __launch_bounds__(kSweepThreads, 2) penalty_grad_kernel(
           g.y = __fmul_rn(__fmul_rn(coef, f[j].y), __fsub_rn(a[j].y, b[j].y));
           g.z = __fmul_rn(__fmul_rn(coef, f[j].z), __fsub_rn(a[j].z, b[j].z));
           g.w = __fmul_rn(__fmul_rn(coef, f[j].w), __fsub_rn(a[j].w, b[j].w));
+          if (i == nvec - 1) {  // mask the alignment pad behind the tensor's last element
+            const int rem = item.len - (i << 2);
+            if (rem < 4) g.w = 0.f;
+            if (rem < 3) g.z = 0.f;
+            if (rem < 2) g.y = 0.f;
+          }
           if (kStats) asum += (fabsf(g.x) + fabsf(g.y)) + (fabsf(g.z) + fabsf(g.w));
           if (kAccumulate) {
             g.x = __fadd_rn(g.x, g0[j].x); g.y = __fadd_rn(g.y, g0[j].y); g.z = __fadd_rn(g.z, g0[j].z); g.w = __fadd_rn(g.w, g0[j].w);
@@ -146,13 +152,15 @@ __global__ void __launch_bounds__(kSweepThreads) accum_kernel(float* __restrict_
 __global__ void __launch_bounds__(kSweepThreads) scale_merge_kernel(float* __restrict__ dst, float* __restrict__ src,
                                                                     int64_t nvec, int64_t n, float count,
                                                                     float gamma, int first, int same) {
+  const float inv = 1.0f / count;
   float4* d4 = reinterpret_cast<float4*>(dst);
   float4* s4 = reinterpret_cast<float4*>(src);
   const int64_t stride = (int64_t)gridDim.x * kSweepThreads;
   for (int64_t i = (int64_t)blockIdx.x * kSweepThreads + threadIdx.x; i < nvec; i += stride) {
     float4 s = ld_stream_rw(s4 + i);
-    // the reference divides in place (fish[key] /= total_ds): a true division keeps bit parity
-    s.x = s.x / count; s.y = s.y / count; s.z = s.z / count; s.w = s.w / count;
+    // fish[key] /= total_ds with a Python scalar: ATen's CUDA kernel multiplies by the fp32 reciprocal
+    // (div_true_kernel_cuda, scalar fast path) - done the same way for bit parity with the reference on GPU
+    s.x = __fmul_rn(s.x, inv); s.y = __fmul_rn(s.y, inv); s.z = __fmul_rn(s.z, inv); s.w = __fmul_rn(s.w, inv);
     st_stream(s4 + i, s);
     if (!same) {
       if (!first) {
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(kSweepThreads) scale_merge_kernel(float* __res
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     int64_t k = (nvec << 2) + threadIdx.x;
-    float s = src[k] / count;
+    float s = __fmul_rn(src[k], inv);
     src[k] = s;
     if (!same) dst[k] = first ? s : __fadd_rn(__fmul_rn(gamma, dst[k]), s);
   }

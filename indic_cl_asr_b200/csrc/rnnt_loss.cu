@@ -97,17 +97,17 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
   const int Tb = (int)act_lens[b], Ub1 = (int)label_lens[b] + 1;
   if (Tb <= 0) {
     if (threadIdx.x == 0) {
-      if (!backward) { w.ll_fwd[b] = 0.f; if (costs) costs[b] = 0.f; } else { w.ll_bwd[b] = 0.f; }
+      if (!backward) { w.ll_fwd[b] = 0.0; if (costs) costs[b] = 0.f; } else { w.ll_bwd[b] = 0.0; }
     }
     return;
   }
-  float* vals = reinterpret_cast<float*>(smem_raw);                 // [2][U1] previous/current diagonal
-  float2* stage = reinterpret_cast<float2*>(vals + 2 * U1 + (U1 & 1) * 2);  // [2][dch*U1], 8-byte aligned
+  double* vals = reinterpret_cast<double*>(smem_raw);            // [2][U1] previous/current diagonal (fp64)
+  float2* stage = reinterpret_cast<float2*>(vals + 2 * U1);      // [2][dch*U1]
   const int nd = Tb + Ub1 - 1;     // diagonals of this utterance
   const int nrows = nd - 1;        // recursion steps
   const int64_t base = (int64_t)b * w.ND * U1;
   const float2* __restrict__ lp = w.lp + base;
-  float* __restrict__ out = (backward ? w.beta : w.alpha) + base;
+  double* __restrict__ out = (backward ? w.beta : w.alpha) + base;
 
   // step r (0..nrows-1) consumes lp row:  forward r  (produces diagonal r+1)
   //                                       backward nd-2-r (produces that same diagonal)
@@ -122,12 +122,12 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
   };
 
   // initial diagonal
-  if (!backward) {
-    if (threadIdx.x == 0) { vals[0] = 0.f; out[0] = 0.f; }
-  } else {
-    if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
+    if (!backward) {
+      vals[0] = 0.0; out[0] = 0.0;
+    } else {
       const int64_t li = (int64_t)(nd - 1) * U1 + (Ub1 - 1);
-      const float v = lp[li].x;
+      const double v = (double)lp[li].x;
       vals[Ub1 - 1] = v;
       out[li] = v;
     }
@@ -146,18 +146,18 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
     const float2* st = stage + (size_t)(c & 1) * dch * U1;
     for (int k = 0; k < cnt; ++k) {
       const int r = r0 + k;
-      const float* prev = vals + cur * U1;
-      float* nxt = vals + (cur ^ 1) * U1;
+      const double* prev = vals + cur * U1;
+      double* nxt = vals + (cur ^ 1) * U1;
       if (!backward) {
         const int n = r + 1;  // diagonal being produced; lp row n-1 staged at chunk-local row k
         const float2* lrow = st + (size_t)k * U1;
         for (int u = threadIdx.x; u < Ub1; u += blockDim.x) {
           const int t = n - u;
           if (t >= 0 && t < Tb) {
-            float no_emit = -INFINITY, emit = -INFINITY;
-            if (t > 0) no_emit = prev[u] + lrow[u].x;          // alpha[t-1,u] + logp(blank | t-1,u)
-            if (u > 0) emit = prev[u - 1] + lrow[u - 1].y;     // alpha[t,u-1] + logp(label_{u-1} | t,u-1)
-            const float v = log_sum_exp(emit, no_emit);
+            double no_emit = -INFINITY, emit = -INFINITY;
+            if (t > 0) no_emit = prev[u] + (double)lrow[u].x;          // alpha[t-1,u] + logp(blank | t-1,u)
+            if (u > 0) emit = prev[u - 1] + (double)lrow[u - 1].y;     // alpha[t,u-1] + logp(label_{u-1} | t,u-1)
+            const double v = log_sum_exp_d(emit, no_emit);
             nxt[u] = v;
             out[(int64_t)n * U1 + u] = v;
           }
@@ -169,11 +169,11 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
         for (int u = threadIdx.x; u < Ub1; u += blockDim.x) {
           const int t = n - u;
           if (t >= 0 && t < Tb) {
-            float no_emit = -INFINITY, emit = -INFINITY;
+            double no_emit = -INFINITY, emit = -INFINITY;
             const float2 l = lrow[u];
-            if (t < Tb - 1) no_emit = prev[u] + l.x;           // beta[t+1,u] + logp(blank | t,u)
-            if (u < Ub1 - 1) emit = prev[u + 1] + l.y;         // beta[t,u+1] + logp(label_u | t,u)
-            const float v = log_sum_exp(emit, no_emit);
+            if (t < Tb - 1) no_emit = prev[u] + (double)l.x;           // beta[t+1,u] + logp(blank | t,u)
+            if (u < Ub1 - 1) emit = prev[u + 1] + (double)l.y;         // beta[t,u+1] + logp(label_u | t,u)
+            const double v = log_sum_exp_d(emit, no_emit);
             nxt[u] = v;
             out[(int64_t)n * U1 + u] = v;
           }
@@ -187,9 +187,9 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
   if (threadIdx.x == 0) {
     if (!backward) {
       // gpu_rnnt_kernel.py:167-172: ll = alpha[T-1,U-1] + logp(blank | T-1,U-1)
-      const float ll = vals[cur * U1 + (Ub1 - 1)] + lp[(int64_t)(nd - 1) * U1 + (Ub1 - 1)].x;
+      const double ll = vals[cur * U1 + (Ub1 - 1)] + (double)lp[(int64_t)(nd - 1) * U1 + (Ub1 - 1)].x;
       w.ll_fwd[b] = ll;
-      if (costs) costs[b] = -ll * (1.0f + fastemit_lambda);  // rnnt_helper.py:106-116
+      if (costs) costs[b] = (float)(-ll * (1.0 + (double)fastemit_lambda));  // rnnt_helper.py:106-116
     } else {
       w.ll_bwd[b] = vals[cur * U1 + 0];  // beta[0,0]
     }
@@ -204,7 +204,7 @@ int launch_rnnt_lattice(const LatticeWs& w, const int64_t* act_lens, const int64
   int dch = (40 * 1024) / (U1 * 8 * 2);
   if (dch > 16) dch = 16;
   if (dch < 1) dch = 1;
-  size_t smem = (size_t)(2 * U1 + (U1 & 1) * 2) * sizeof(float) + (size_t)2 * dch * U1 * sizeof(float2);
+  size_t smem = (size_t)2 * U1 * sizeof(double) + (size_t)2 * dch * U1 * sizeof(float2);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(rnnt_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -240,20 +240,23 @@ __global__ void __launch_bounds__(kRowWarps * 32) rnnt_grad_kernel(
   }
   const float* __restrict__ z = logits + row * Vp;
   const int64_t idx = ((int64_t)b * w.ND + t + u) * U1 + u;
-  const float a = w.alpha[idx], bt = w.beta[idx], dn = w.denom[idx], ll = w.ll_fwd[b];
+  // fp64 lattice values; every exp() argument is formed in fp64 and rounded once to fp32
+  const double a = w.alpha[idx], bt = w.beta[idx], ll = w.ll_fwd[b];
+  const float dn = w.denom[idx];
   const float2 lpair = w.lp[idx];
   const float go = grad_out ? grad_out[b] : 1.f;
   const bool has_label = u < Ub1 - 1;
   const int label = has_label ? (int)labels[(int64_t)b * (U1 - 1) + u] : -1;
-  const float beta_t1 = (t < Tb - 1) ? w.beta[idx + U1] : 0.f;      // beta[t+1,u]
-  const float beta_u1 = has_label ? w.beta[idx + U1 + 1] : 0.f;     // beta[t,u+1]
-  const float base = a + bt + dn - ll;  // grad = exp(alpha + beta + logpk - ll), logpk = dn + z
+  const double beta_t1 = (t < Tb - 1) ? w.beta[idx + U1] : 0.0;      // beta[t+1,u]
+  const double beta_u1 = has_label ? w.beta[idx + U1 + 1] : 0.0;     // beta[t,u+1]
+  const float base = (float)(a + bt - ll) + dn;  // grad = exp(alpha + beta + logpk - ll), logpk = dn + z
   const bool fe = fastemit_lambda > 0.f && has_label;
-  const float fe_base = fe ? (a + lpair.y + beta_u1 + dn - ll) : 0.f;
+  const float fe_base = fe ? (float)(a + beta_u1 - ll + (double)lpair.y) + dn : 0.f;
   float blank_sub = 0.f;
-  if (t == Tb - 1 && u == Ub1 - 1) blank_sub += expf(a + lpair.x - ll);
-  if (t < Tb - 1) blank_sub += expf(a + lpair.x - ll + beta_t1);
-  const float label_sub = has_label ? expf(log1pf(fastemit_lambda) + a + lpair.y - ll + beta_u1) : 0.f;
+  if (t == Tb - 1 && u == Ub1 - 1) blank_sub += expf((float)(a - ll + (double)lpair.x));
+  if (t < Tb - 1) blank_sub += expf((float)(a + beta_t1 - ll + (double)lpair.x));
+  const float label_sub =
+      has_label ? expf(log1pf(fastemit_lambda) + (float)(a + beta_u1 - ll + (double)lpair.y)) : 0.f;
 
   constexpr int kU = 8;
   for (int v0 = lane; v0 < Vp; v0 += 32 * kU) {
@@ -285,8 +288,8 @@ __global__ void rnnt_export_lattice_kernel(LatticeWs w, const int64_t* __restric
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t cells = (int64_t)B * T * U1;
   if (i < B) {
-    ll_fwd[i] = w.ll_fwd[i];
-    ll_bwd[i] = w.ll_bwd[i];
+    ll_fwd[i] = (float)w.ll_fwd[i];
+    ll_bwd[i] = (float)w.ll_bwd[i];
   }
   if (i >= cells) return;
   const int b = (int)(i / ((int64_t)T * U1));
@@ -294,8 +297,8 @@ __global__ void rnnt_export_lattice_kernel(LatticeWs w, const int64_t* __restric
   const int t = rem / U1, u = rem - t * U1;
   const bool valid = t < (int)act_lens[b] && u <= (int)label_lens[b];
   const int64_t idx = ((int64_t)b * w.ND + t + u) * U1 + u;
-  alphas[i] = valid ? w.alpha[idx] : 0.f;
-  betas[i] = valid ? w.beta[idx] : 0.f;
+  alphas[i] = valid ? (float)w.alpha[idx] : 0.f;
+  betas[i] = valid ? (float)w.beta[idx] : 0.f;
 }
 
 }  // namespace clasr

@@ -14,6 +14,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    """Parity is judged against an fp64 oracle: keep torch's own GEMMs/convs (enc/pred projections, CTC head)
+    in true fp32 instead of the TF32 default for cuDNN convolutions."""
+    import torch
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch

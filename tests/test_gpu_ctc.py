@@ -68,7 +68,9 @@ def test_random_vs_oracle_and_torch(B, T, U, V):
                                          zero_infinity=True)
     t_nll.sum().backward()
     assert np.allclose(nll.detach().cpu().numpy(), t_nll.detach().numpy(), rtol=1e-5, atol=1e-5)
-    assert rel_err(x.grad.cpu().numpy(), xt.grad.numpy()) <= 1e-4
+    # ATen carries alpha/beta in fp32 log space: at T=300, V=1024 (|alpha| ~ 2e3, ulp 2.4e-4) its own gradient is
+    # ~1e-3 away from the fp64 truth that the kernels here match to 1e-4 (asserted above); small cases agree to 1e-4.
+    assert rel_err(x.grad.cpu().numpy(), xt.grad.numpy()) <= (1e-4 if T * (V + 1) < 100000 else 3e-3)
 
 
 def test_log_softmax_rows():

@@ -145,7 +145,7 @@ def test_error_behaviour_matches_reference():
     with pytest.raises(ValueError, match="Output length mismatch"):
         fn(x, lab, al, torch.tensor([1, 1], device=DEV))
     with pytest.raises(ValueError, match="must be 4D"):
-        fn(x[0], lab, al, ll)
+        fn(x.unsqueeze(-1), lab, al, ll)
 
 
 def test_gradient_accumulates_across_graphs():
@@ -205,4 +205,9 @@ def test_full_size_properties():
         oc = c_port.rnnt_loss_cpu(zc, labels[b:b + 1, :Ub].cpu(), torch.tensor([Tb]), torch.tensor([Ub]), V)
         oc.sum().backward()
         assert abs(costs[b].item() - oc.item()) <= 1e-5 * abs(oc.item())
-        assert rel_err(grads[b, :Tb, :Ub + 1].cpu().numpy(), zc.grad[0].numpy()) <= 1e-4
+        # the fp32 restatement of the reference carries ~1e-3 error in its own occupancies at this size
+        # (|alpha| ~ 2e3, one fp32 ulp = 2.4e-4): gradient parity is judged against the fp64 oracle.
+        assert rel_err(grads[b, :Tb, :Ub + 1].cpu().numpy(), zc.grad[0].numpy()) <= 2e-3
+        o64c, o64g = rnnt_oracle.rnnt_loss_and_grad(sub.numpy(), labels[b:b + 1, :Ub].cpu().numpy(), [Tb], [Ub], V)
+        assert abs(costs[b].item() - o64c[0]) <= 1e-5 * abs(o64c[0])
+        assert rel_err(grads[b, :Tb, :Ub + 1].cpu().numpy(), o64g[0]) <= 1e-4
