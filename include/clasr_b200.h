@@ -44,7 +44,7 @@ extern "C" {
 
 /* Precision of the fused joint's tensor-core operands. */
 #define CLASR_PREC_BF16 0   /* single bf16 pass (config 5, "bf16 joint GEMM") */
-#define CLASR_PREC_FP16X3 1 /* hi/lo fp16 split, 3 MMAs per product: fp32-level accuracy (config 2, "fp32") */
+#define CLASR_PREC_BF16X3 1 /* hi/lo bf16 split, 3 MMAs per product: fp32-grade accuracy (config 2, "fp32") */
 
 CLASR_API int clasr_version(void);
 CLASR_API const char* clasr_last_error(void);
@@ -160,6 +160,15 @@ CLASR_API int clasr_ctc_loss_bwd(const float* log_probs, const int64_t* targets,
  * backward fused with an incoming gradient: dx = dy - exp(y) * sum(dy). */
 CLASR_API int clasr_log_softmax_fwd(const float* x, float* y, int64_t rows, int cols, void* stream);
 CLASR_API int clasr_log_softmax_bwd(const float* y, const float* dy, float* dx, int64_t rows, int cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3b. Tensor-core GEMM building block:  C[M,N] = A[M,K] . B[N,K]^T  (fp32 in/out, row-major, tcgen05 + TMEM,
+ *     operands converted to bf16 or split bf16 hi/lo in `workspace`).  Replaces the cuBLAS calls behind
+ *     nn.Linear backward for the joint's output layer (modules/rnnt.py:1634-1641 under autograd).
+ * ------------------------------------------------------------------------------------------ */
+CLASR_API size_t clasr_gemm_workspace_bytes(int M, int N, int K, int precision);
+CLASR_API int clasr_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int precision,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * 4. Fused joint + transducer loss — replaces the fused branch of RNNTJoint.forward

@@ -21,7 +21,7 @@ _lib = None
 
 STATUS_SUCCESS = 0
 ACT = {"relu": 0, "sigmoid": 1, "tanh": 2}
-PREC = {"bf16": 0, "fp16x3": 1}
+PREC = {"bf16": 0, "bf16x3": 1}
 
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
@@ -45,6 +45,8 @@ _PROTOS: Dict[str, Tuple[object, List[object]]] = {
     "clasr_ctc_loss_bwd": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "clasr_log_softmax_fwd": (_i, [_vp, _vp, _i64, _i, _vp]),
     "clasr_log_softmax_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "clasr_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "clasr_gemm_nt": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "clasr_joint_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "clasr_joint_rnnt_fwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, _vp, _vp, _vp, _sz, _vp]),
     "clasr_joint_rnnt_bwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

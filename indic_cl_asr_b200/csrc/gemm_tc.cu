@@ -1,0 +1,318 @@
+// gemm_tc.cu — warp-specialised tcgen05 GEMM  C[M,N] (+)= A[M,K] . B[N,K]^T  (bf16 operands, fp32 accumulate in
+// TMEM), the building block of the joint backward (dHid = dZ.W, dW = dZ^T.Hid) and the bring-up vehicle for the
+// TMA / UMMA-descriptor / TMEM plumbing the fused joint kernels share (tc_common.cuh).
+//
+// Precision modes (CLASR_PREC_*):
+//   BF16    one MMA per product, operands rounded to bf16                  (config 5, "bf16 joint GEMM")
+//   BF16X3  operands split x = hi + lo (bf16 each); hi.hi + hi.lo + lo.hi accumulate into the same TMEM tile:
+//           ~2^-17 relative per product, i.e. fp32-grade results from the bf16 tensor pipe at 3 MMAs/product
+//           (config 2 "fp32": rel 1e-5 loss / 1e-4 grads cannot be met by a single bf16 or tf32 pass).
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0  TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx
+//   warp 1  MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) and tcgen05.commit
+//   warp 2  TMEM allocator 512 columns = 2 accumulator stages x BN(256) fp32 columns
+//   warps 4-7 epilogue     tcgen05.ld (32 lanes x 32 columns) -> 128-byte row segments -> global
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace clasr {
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
+      return CLASR_STATUS_CUDA_ERROR;
+    }
+    encode = (EncodeFn)fn;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu stride=%llu box=%ux%u", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_elems, box_rows,
+              box_cols);
+    return CLASR_STATUS_CUDA_ERROR;
+  }
+  return CLASR_STATUS_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 [rows, cols] -> bf16 hi (and lo) [rows, cols_pad], cols_pad multiple of 8, pad zero-filled
+// ------------------------------------------------------------------------------------------------
+__global__ void split_bf16_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t src_ld,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int cols_pad) {
+  const int64_t n = rows * (int64_t)cols_pad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols_pad;
+    const int c = (int)(i - r * cols_pad);
+    const float x = c < cols ? src[r * src_ld + c] : 0.f;
+    __nv_bfloat16 h, l;
+    tc::split_bf16(x, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+int launch_split_bf16(const float* src, int64_t rows, int cols, int64_t src_ld, void* hi, void* lo, int cols_pad,
+                      cudaStream_t s) {
+  const int64_t n = rows * (int64_t)cols_pad;
+  int grid = (int)((n + 255) / 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  if (grid < 1) grid = 1;
+  split_bf16_kernel<<<grid, 256, 0, s>>>(src, rows, cols, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, cols_pad);
+  CLASR_CHECK_LAUNCH("split_bf16");
+  return CLASR_STATUS_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int kBM = 128;
+constexpr int kBN = 256;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 256;
+
+template <int kTerms>
+struct GemmSmem {
+  static constexpr int kParts = kTerms == 1 ? 1 : 2;
+  static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+  static constexpr int kBBytes = kBN * kBK * 2;  // 32 KB
+  static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
+  static constexpr int kStages = kTerms == 1 ? 4 : 2;
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static constexpr int kTotalBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K;
+  float* C;
+  int64_t ldc;
+  int atomic_add;  // 0: C = result ; 1: atomicAdd into C (split accumulation across launches / K-slices)
+  int k_begin, k_end;  // K range of this launch (multiples of kBK), for split-K
+};
+
+template <int kTerms>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, GemmParams p) {
+  using S = GemmSmem<kTerms>;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + S::kRingBytes);
+  uint64_t* full = bars;                      // [kStages]
+  uint64_t* empty = bars + S::kStages;        // [kStages]
+  uint64_t* tmem_full = bars + 2 * S::kStages;      // [2]
+  uint64_t* tmem_empty = bars + 2 * S::kStages + 2; // [2]
+  uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * S::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int n_tiles = (p.N + kBN - 1) / kBN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int kb_begin = p.k_begin / kBK;
+  const int kb_end = (p.k_end + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA_hi);
+    tc::prefetch_tmap(&tmB_hi);
+    if (kTerms > 1) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S::kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_base_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM;
+        const int n0 = (tile % n_tiles) * kBN;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * S::kStageBytes;
+          tc::mbar_expect_tx(&full[stage], S::kStageBytes);
+          tc::tma_load_2d(st, &tmA_hi, &full[stage], kb * kBK, m0);
+          tc::tma_load_2d(st + S::kParts * S::kABytes, &tmB_hi, &full[stage], kb * kBK, n0);
+          if (kTerms > 1) {
+            tc::tma_load_2d(st + S::kABytes, &tmA_lo, &full[stage], kb * kBK, m0);
+            tc::tma_load_2d(st + S::kParts * S::kABytes + S::kBBytes, &tmB_lo, &full[stage], kb * kBK, n0);
+          }
+          if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (single thread) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(kBM, kBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBN;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t a_hi = tc::smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t a_lo = a_hi + S::kABytes;
+          const uint32_t b_hi = a_hi + S::kParts * S::kABytes;
+          const uint32_t b_lo = b_hi + S::kBBytes;
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk) {
+            const uint32_t koff = kk * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle span
+            const uint32_t first = (kb == kb_begin && kk == 0) ? 0u : 1u;
+            tc::umma_ss(d_tmem, tc::make_desc_kmajor_sw128(a_hi + koff), tc::make_desc_kmajor_sw128(b_hi + koff),
+                        idesc, first);
+            if (kTerms > 1) {
+              tc::umma_ss(d_tmem, tc::make_desc_kmajor_sw128(a_hi + koff), tc::make_desc_kmajor_sw128(b_lo + koff),
+                          idesc, 1u);
+              tc::umma_ss(d_tmem, tc::make_desc_kmajor_sw128(a_lo + koff), tc::make_desc_kmajor_sw128(b_hi + koff),
+                          idesc, 1u);
+            }
+          }
+          tc::umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: TMEM -> registers -> global =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * kBM;
+      const int n0 = (tile % n_tiles) * kBN;
+      tc::mbar_wait(&tmem_full[acc], acc_phase);
+      tc::tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      float* crow = p.C + (int64_t)row * p.ldc;
+      const bool vec_ok = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kBN + c * 32, r);
+        tc::tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) {
+          if (p.atomic_add) {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(crow + col0 + j, __uint_as_float(r[j]));
+          } else if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+              *reinterpret_cast<float4*>(crow + col0 + j) = v;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// C[M,N] = A[M,K] B[N,K]^T from pre-split bf16 operands (K padded to Kp, multiple of 8; rows of Kp elements)
+int launch_gemm_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int M, int N, int K,
+                   int Kp, float* C, int64_t ldc, int precision, int atomic_add, cudaStream_t s) {
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&ta_hi, A_hi, M, Kp, Kp, kBM, kBK))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tb_hi, B_hi, N, Kp, Kp, kBN, kBK))) return rc;
+  const bool x3 = precision == CLASR_PREC_BF16X3;
+  if (x3) {
+    if ((rc = make_tmap_bf16_2d(&ta_lo, A_lo, M, Kp, Kp, kBM, kBK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tb_lo, B_lo, N, Kp, Kp, kBN, kBK))) return rc;
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+  GemmParams p{M, N, K, C, ldc, atomic_add, 0, K};
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  if (x3) {
+    cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<3>::kTotalBytes);
+    gemm_tc_kernel<3><<<grid, kGemmThreads, GemmSmem<3>::kTotalBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  } else {
+    cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<1>::kTotalBytes);
+    gemm_tc_kernel<1><<<grid, kGemmThreads, GemmSmem<1>::kTotalBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  }
+  CLASR_CHECK_LAUNCH("gemm_tc");
+  return CLASR_STATUS_SUCCESS;
+}
+
+}  // namespace clasr
+
+using namespace clasr;
+
+static inline int pad8(int k) { return (k + 7) / 8 * 8; }
+
+extern "C" size_t clasr_gemm_workspace_bytes(int M, int N, int K, int precision) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const size_t parts = precision == CLASR_PREC_BF16X3 ? 2 : 1;
+  const size_t kp = pad8(K);
+  size_t a = ((size_t)M * kp * 2 + 255) / 256 * 256, b = ((size_t)N * kp * 2 + 255) / 256 * 256;
+  return parts * (a + b);
+}
+
+extern "C" int clasr_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int precision,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  CLASR_CHECK_ARG(A && B && C && workspace, "gemm_nt: null pointer");
+  CLASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_nt: non-positive dimension");
+  CLASR_CHECK_ARG(precision == CLASR_PREC_BF16 || precision == CLASR_PREC_BF16X3, "gemm_nt: bad precision");
+  CLASR_CHECK_ARG(workspace_bytes >= clasr_gemm_workspace_bytes(M, N, K, precision), "gemm_nt: workspace too small");
+  CLASR_CHECK_ARG((((uintptr_t)workspace) & 255) == 0, "gemm_nt: workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool x3 = precision == CLASR_PREC_BF16X3;
+  const int kp = pad8(K);
+  const size_t a_sz = ((size_t)M * kp * 2 + 255) / 256 * 256, b_sz = ((size_t)N * kp * 2 + 255) / 256 * 256;
+  char* w = (char*)workspace;
+  void* a_hi = w; w += a_sz;
+  void* a_lo = x3 ? w : nullptr; if (x3) w += a_sz;
+  void* b_hi = w; w += b_sz;
+  void* b_lo = x3 ? w : nullptr;
+  int rc;
+  if ((rc = launch_split_bf16(A, M, K, K, a_hi, a_lo, kp, s))) return rc;
+  if ((rc = launch_split_bf16(B, N, K, K, b_hi, b_lo, kp, s))) return rc;
+  return launch_gemm_tc(a_hi, a_lo, b_hi, b_lo, M, N, K, kp, C, N, precision, 0, s);
+}

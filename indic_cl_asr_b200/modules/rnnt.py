@@ -52,7 +52,7 @@ class RNNTJoint(torch.nn.Module):
         token_id_offsets=None,
         offset_token_ids_by_token_id=None,
         fused_impl: str = "tcgen05",
-        precision: str = "fp16x3",
+        precision: str = "bf16x3",
     ):
         super().__init__()
         self.vocabulary = vocabulary

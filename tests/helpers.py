@@ -35,7 +35,7 @@ def joint_params(joint):
 
 
 def run_step_and_oracle(device="cuda:0", B=3, T=20, U=7, V=40, H=64, De=32, Dp=32, activation="tanh", seed=0,
-                        fused_impl="tcgen05", precision="fp16x3", ctc_weight=0.3, e_lambda=10.0):
+                        fused_impl="tcgen05", precision="bf16x3", ctc_weight=0.3, e_lambda=10.0):
     """One training step of the hot path on `device` (joint -> RNNT loss, CTC head -> CTC loss, mixed loss
     backward, EWC penalty sweep) and the same step through the CPU oracle.  Returns error metrics."""
     from indic_cl_asr_b200 import CTCLoss, ConvASRDecoder, RNNTJoint, RNNTLoss

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def build_from_fixture(c, fused_impl, precision="fp16x3"):
+def build_from_fixture(c, fused_impl, precision="bf16x3"):
     B, T, U, De, Dp, H, V, fbs = [int(x) for x in c["cfg"]]
     j = RNNTJoint(jointnet=dict(encoder_hidden=De, pred_hidden=Dp, joint_hidden=H, activation=str(c["activation"]),
                                 dropout=0.0),
