@@ -1,0 +1,99 @@
+"""Autograd binding of the fused joint + transducer loss (C ABI: clasr_joint_rnnt_fwd / _bwd).
+
+Inputs are the joint's projections f = enc(encoder_outputs) [B,T,H] and g = pred(decoder_outputs) [B,U+1,H]
+(reference modules/rnnt.py:1563-1585) and the output layer's weight/bias; the result is the per-sample
+transducer cost vector that the reference obtains from joint_after_projection (:1587-1665) followed by
+RNNTLoss with reduction=None (:1475-1508) — without the [B,T,U+1,V+1] logits ever existing in HBM.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+__all__ = ["fused_joint_rnnt_loss", "fused_joint_forward_stats"]
+
+
+def _ws(f, B, T, U1, H, Vp, prec):
+    L = _lib.lib()
+    nbytes = L.clasr_joint_workspace_bytes(B, T, U1, H, Vp, prec)
+    return torch.empty(nbytes, dtype=torch.uint8, device=f.device), nbytes
+
+
+class _FusedJointRNNT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision, fastemit_lambda,
+                clamp, want_sumsq):
+        _lib.require_cuda(f, "f")
+        if clamp < 0:
+            raise ValueError("`clamp` must be 0.0 or positive float value.")
+        f = f.contiguous().float()
+        g = g.contiguous().float()
+        weight = weight.contiguous().float()
+        bias = bias.contiguous().float()
+        labels = labels.contiguous().long()
+        act_lens = act_lens.contiguous().long()
+        label_lens = label_lens.contiguous().long()
+        B, T, H = f.shape
+        U1 = g.shape[1]
+        Vp = weight.shape[0]
+        if g.shape[0] != B or g.shape[2] != H or weight.shape[1] != H or bias.shape[0] != Vp:
+            raise ValueError("fused joint: inconsistent shapes")
+        if labels.shape[0] != B or (U1 > 1 and labels.shape[1] < U1 - 1):
+            raise ValueError("fused joint: transcripts must be [B, >= U]")
+        if labels.shape[1] != U1 - 1:
+            labels = labels[:, : U1 - 1].contiguous()
+        prec = _lib.PREC[precision]
+        ws, nbytes = _ws(f, B, T, U1, H, Vp, prec)
+        costs = torch.empty(B, dtype=torch.float32, device=f.device)
+        sumsq = torch.zeros(B, T, U1, dtype=torch.float32, device=f.device) if want_sumsq else None
+        L = _lib.lib()
+        with torch.cuda.device(f.device):
+            st = L.clasr_joint_rnnt_fwd(
+                f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
+                act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, int(blank), _lib.ACT[activation], prec,
+                float(fastemit_lambda), costs.data_ptr(), _lib.ptr(sumsq), ws.data_ptr(), nbytes,
+                _lib.stream_ptr(f.device))
+        _lib.check(st, "joint_rnnt_fwd")
+        ctx.save_for_backward(f, g, weight, bias, labels, act_lens, label_lens, ws)
+        ctx.args = (int(blank), _lib.ACT[activation], prec, float(fastemit_lambda), float(clamp), nbytes)
+        if want_sumsq:
+            ctx.mark_non_differentiable(sumsq)
+            return costs, sumsq
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_costs, *unused):
+        f, g, weight, bias, labels, act_lens, label_lens, ws = ctx.saved_tensors
+        blank, act, prec, fastemit_lambda, clamp, nbytes = ctx.args
+        B, T, H = f.shape
+        U1 = g.shape[1]
+        Vp = weight.shape[0]
+        go = grad_costs.contiguous().float().view(-1)
+        d_f = torch.empty_like(f)
+        d_g = torch.empty_like(g)
+        d_w = torch.empty_like(weight)
+        d_b = torch.empty_like(bias)
+        L = _lib.lib()
+        with torch.cuda.device(f.device):
+            st = L.clasr_joint_rnnt_bwd(
+                f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
+                act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, blank, act, prec, fastemit_lambda, clamp,
+                go.data_ptr(), d_f.data_ptr(), d_g.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ws.data_ptr(), nbytes,
+                _lib.stream_ptr(f.device))
+        _lib.check(st, "joint_rnnt_bwd")
+        return (d_f, d_g, d_w, d_b) + (None,) * 9
+
+
+def fused_joint_rnnt_loss(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh",
+                          precision="bf16x3", fastemit_lambda=0.0, clamp=0.0):
+    """Per-sample transducer costs [B]."""
+    return _FusedJointRNNT.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision,
+                                 fastemit_lambda, clamp, False)
+
+
+def fused_joint_forward_stats(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh",
+                              precision="bf16x3"):
+    """(costs [B], sum_v z^2 [B,T,U+1]) — the second is what MAS needs from the joint logits."""
+    return _FusedJointRNNT.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision, 0.0,
+                                 0.0, True)
