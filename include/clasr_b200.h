@@ -169,6 +169,11 @@ CLASR_API int clasr_log_softmax_bwd(const float* y, const float* dy, float* dx, 
 CLASR_API size_t clasr_gemm_workspace_bytes(int M, int N, int K, int precision);
 CLASR_API int clasr_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int precision,
                             void* workspace, size_t workspace_bytes, void* stream);
+/* General form: a_trans != 0 means A is given as [K,M] (M contiguous, consumed as an MN-major UMMA operand with no
+ * transpose copy), likewise b_trans for B given as [K,N]; k_splits > 1 cuts K into independent slices that are
+ * accumulated with fp32 atomics (C is zero-filled first) so that short-and-wide outputs still fill 148 SMs. */
+CLASR_API int clasr_gemm_ex(const float* A, const float* B, float* C, int M, int N, int K, int a_trans, int b_trans,
+                            int k_splits, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * 4. Fused joint + transducer loss — replaces the fused branch of RNNTJoint.forward
@@ -188,11 +193,19 @@ CLASR_API int clasr_joint_rnnt_fwd(const float* f, const float* g, const float* 
                          float* costs, float* sumsq /* [B,T,U1] sum_v z^2 for MAS, or NULL */, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Backward.  `workspace` is the one the forward call filled (lattice, W split, tile table).  `scratch` holds the
+ * GEMM operands of the backward pass (dZ and the hidden activations as bf16 hi/lo in compact tile-row order, dHid,
+ * dW accumulator); it is caller-owned and reusable across steps.
+ * ROUND-1 STATE: pass 2 recomputes the logits tile-wise on the tensor cores (they are still never stored), but the
+ * softmax-fused gradient dZ is staged through `scratch` as bf16 hi/lo before the two tcgen05 GEMMs
+ * (dHid = dZ.W, dW = dZ^T.Hid) consume it; fusing those contractions into the recompute kernel is next. */
+CLASR_API size_t clasr_joint_bwd_scratch_bytes(int B, int T, int U1, int H, int Vp, int precision);
 CLASR_API int clasr_joint_rnnt_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
                          const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B, int T,
                          int U1, int H, int Vp, int blank, int activation, int precision, float fastemit_lambda,
                          float clamp, const float* grad_out /* [B] */, float* d_f, float* d_g, float* d_w_out,
-                         float* d_b_out, void* workspace, size_t workspace_bytes, void* stream);
+                         float* d_b_out, void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                         void* stream);
 
 #ifdef __cplusplus
 }

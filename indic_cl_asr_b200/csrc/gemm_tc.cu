@@ -99,8 +99,12 @@ struct GemmParams {
   int M, N, K;
   float* C;
   int64_t ldc;
-  int atomic_add;  // 0: C = result ; 1: atomicAdd into C (split accumulation across launches / K-slices)
-  int k_begin, k_end;  // K range of this launch (multiples of kBK), for split-K
+  int atomic_add;  // 0: C = result ; 1: atomicAdd into C (required when k_splits > 1; C must be pre-zeroed)
+  int k_splits;    // the K range is cut into this many slices, each an independent tile
+  int a_mn;        // 0: A given as [M,K] (K contiguous) ; 1: A given as [K,M] (M contiguous)
+  int b_mn;        // 0: B given as [N,K] (K contiguous) ; 1: B given as [K,N] (N contiguous)
+  const int* m_dev;  // optional device-side M (<= M): lets a ragged row count stay on the device (no host sync)
+  const int* k_dev;  // optional device-side K (<= K)
 };
 
 template <int kTerms>
@@ -119,11 +123,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int Mdyn = p.m_dev ? min(p.M, *p.m_dev) : p.M;
+  const int Kdyn = p.k_dev ? min(p.K, *p.k_dev) : p.K;
+  const int m_tiles = (Mdyn + kBM - 1) / kBM;
   const int n_tiles = (p.N + kBN - 1) / kBN;
-  const int num_tiles = m_tiles * n_tiles;
-  const int kb_begin = p.k_begin / kBK;
-  const int kb_end = (p.k_end + kBK - 1) / kBK;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int kb_total = (Kdyn + kBK - 1) / kBK;
+  const int kb_per_split = max(1, (kb_total + p.k_splits - 1) / p.k_splits);
+  const int k_splits = max(1, (kb_total + kb_per_split - 1) / kb_per_split);  // no empty slice
+  const int num_tiles = mn_tiles * k_splits;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA_hi);
@@ -147,17 +155,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBM;
-        const int n0 = (tile % n_tiles) * kBN;
+        const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+        const int m0 = (mn / n_tiles) * kBM;
+        const int n0 = (mn % n_tiles) * kBN;
+        const int kb_begin = ks * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * S::kStageBytes;
           tc::mbar_expect_tx(&full[stage], S::kStageBytes);
-          tc::tma_load_2d(st, &tmA_hi, &full[stage], kb * kBK, m0);
-          tc::tma_load_2d(st + S::kParts * S::kABytes, &tmB_hi, &full[stage], kb * kBK, n0);
-          if (kTerms > 1) {
-            tc::tma_load_2d(st + S::kABytes, &tmA_lo, &full[stage], kb * kBK, m0);
-            tc::tma_load_2d(st + S::kParts * S::kABytes + S::kBBytes, &tmB_lo, &full[stage], kb * kBK, n0);
+          for (int part = 0; part < S::kParts; ++part) {
+            const CUtensorMap* ta = part == 0 ? &tmA_hi : &tmA_lo;
+            const CUtensorMap* tb = part == 0 ? &tmB_hi : &tmB_lo;
+            uint8_t* sa = st + part * S::kABytes;
+            uint8_t* sb = st + S::kParts * S::kABytes + part * S::kBBytes;
+            if (!p.a_mn) {
+              tc::tma_load_2d(sa, ta, &full[stage], kb * kBK, m0);
+            } else {  // [K rows][64 M] boxes, one per 64-wide M block
+              for (int j = 0; j < kBM / 64; ++j) tc::tma_load_2d(sa + j * 8192, ta, &full[stage], m0 + 64 * j, kb * kBK);
+            }
+            if (!p.b_mn) {
+              tc::tma_load_2d(sb, tb, &full[stage], kb * kBK, n0);
+            } else {
+              for (int j = 0; j < kBN / 64; ++j) tc::tma_load_2d(sb + j * 8192, tb, &full[stage], n0 + 64 * j, kb * kBK);
+            }
           }
           if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
@@ -166,13 +186,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else if (warp == 1) {
     // ================= MMA issuer (single thread) =================
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(kBM, kBN);
+      const uint32_t idesc = tc::make_idesc_bf16(kBM, kBN, p.a_mn, p.b_mn);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        const int ks = tile / mn_tiles;
+        const int kb_begin = ks * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
         tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBN;
@@ -185,15 +207,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t b_lo = b_hi + S::kBBytes;
 #pragma unroll
           for (int kk = 0; kk < kBK / 16; ++kk) {
-            const uint32_t koff = kk * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle span
+            // one MMA consumes 16 K: 32 bytes inside the 128-byte swizzle span (K-major) or two 8-row
+            // swizzle atoms = 2048 bytes (MN-major)
+            const uint32_t aoff = p.a_mn ? kk * 2048 : kk * 32;
+            const uint32_t boff = p.b_mn ? kk * 2048 : kk * 32;
+            auto adesc = [&](uint32_t base) {
+              return p.a_mn ? tc::make_desc_mnmajor_sw128(base + aoff, 8192) : tc::make_desc_kmajor_sw128(base + aoff);
+            };
+            auto bdesc = [&](uint32_t base) {
+              return p.b_mn ? tc::make_desc_mnmajor_sw128(base + boff, 8192) : tc::make_desc_kmajor_sw128(base + boff);
+            };
             const uint32_t first = (kb == kb_begin && kk == 0) ? 0u : 1u;
-            tc::umma_ss(d_tmem, tc::make_desc_kmajor_sw128(a_hi + koff), tc::make_desc_kmajor_sw128(b_hi + koff),
-                        idesc, first);
+            tc::umma_ss(d_tmem, adesc(a_hi), bdesc(b_hi), idesc, first);
             if (kTerms > 1) {
-              tc::umma_ss(d_tmem, tc::make_desc_kmajor_sw128(a_hi + koff), tc::make_desc_kmajor_sw128(b_lo + koff),
-                          idesc, 1u);
-              tc::umma_ss(d_tmem, tc::make_desc_kmajor_sw128(a_lo + koff), tc::make_desc_kmajor_sw128(b_hi + koff),
-                          idesc, 1u);
+              tc::umma_ss(d_tmem, adesc(a_hi), bdesc(b_lo), idesc, 1u);
+              tc::umma_ss(d_tmem, adesc(a_lo), bdesc(b_hi), idesc, 1u);
             }
           }
           tc::umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
@@ -209,8 +237,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * kBM;
-      const int n0 = (tile % n_tiles) * kBN;
+      const int mn = tile % mn_tiles;
+      const int m0 = (mn / n_tiles) * kBM;
+      const int n0 = (mn % n_tiles) * kBN;
       tc::mbar_wait(&tmem_full[acc], acc_phase);
       tc::tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -222,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kBN + c * 32, r);
         tc::tmem_ld_wait();
         const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) {
+        if (row < Mdyn && col0 < p.N) {
           if (p.atomic_add) {
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) atomicAdd(crow + col0 + j, __uint_as_float(r[j]));
@@ -252,23 +281,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
 }
 
-// C[M,N] = A[M,K] B[N,K]^T from pre-split bf16 operands (K padded to Kp, multiple of 8; rows of Kp elements)
-int launch_gemm_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int M, int N, int K,
-                   int Kp, float* C, int64_t ldc, int precision, int atomic_add, cudaStream_t s) {
+// C[M,N] (+)= op(A) . op(B)^T from pre-split bf16 operands.
+//   a_mn == 0: A is [M, lda] with K contiguous      a_mn == 1: A is [K, lda] with M contiguous
+//   b_mn == 0: B is [N, ldb] with K contiguous      b_mn == 1: B is [K, ldb] with N contiguous
+// lda / ldb in elements (multiples of 8).  k_splits > 1 requires atomic_add and a zero-initialised C.
+int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
+                   int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
+                   int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev) {
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
-  if ((rc = make_tmap_bf16_2d(&ta_hi, A_hi, M, Kp, Kp, kBM, kBK))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tb_hi, B_hi, N, Kp, Kp, kBN, kBK))) return rc;
   const bool x3 = precision == CLASR_PREC_BF16X3;
+  auto mk = [&](CUtensorMap* t, const void* base, int64_t ld, int mn, int rows_mn, int box_mn) -> int {
+    if (!mn) return make_tmap_bf16_2d(t, base, rows_mn, K, ld, box_mn, kBK);       // [MN rows, K cols]
+    return make_tmap_bf16_2d(t, base, K, rows_mn, ld, kBK, 64);                    // [K rows, MN cols], 64x64 boxes
+  };
+  if ((rc = mk(&ta_hi, A_hi, lda, a_mn, M, kBM))) return rc;
+  if ((rc = mk(&tb_hi, B_hi, ldb, b_mn, N, kBN))) return rc;
   if (x3) {
-    if ((rc = make_tmap_bf16_2d(&ta_lo, A_lo, M, Kp, Kp, kBM, kBK))) return rc;
-    if ((rc = make_tmap_bf16_2d(&tb_lo, B_lo, N, Kp, Kp, kBN, kBK))) return rc;
+    if ((rc = mk(&ta_lo, A_lo, lda, a_mn, M, kBM))) return rc;
+    if ((rc = mk(&tb_lo, B_lo, ldb, b_mn, N, kBN))) return rc;
   } else {
     ta_lo = ta_hi;
     tb_lo = tb_hi;
   }
-  GemmParams p{M, N, K, C, ldc, atomic_add, 0, K};
-  const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
+  const int kb_total = (K + kBK - 1) / kBK;
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > kb_total) k_splits = kb_total;
+  const int per = (kb_total + k_splits - 1) / k_splits;
+  k_splits = (kb_total + per - 1) / per;  // no empty slice
+  if (k_splits > 1 && !atomic_add) {
+    set_error("gemm_tc: split-K needs atomic accumulation");
+    return CLASR_STATUS_INVALID_VALUE;
+  }
+  GemmParams p{M, N, K, C, ldc, atomic_add, k_splits, a_mn, b_mn, m_dev, k_dev};
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN) * k_splits;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (x3) {
     cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<3>::kTotalBytes);
@@ -290,29 +336,42 @@ static inline int pad8(int k) { return (k + 7) / 8 * 8; }
 extern "C" size_t clasr_gemm_workspace_bytes(int M, int N, int K, int precision) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const size_t parts = precision == CLASR_PREC_BF16X3 ? 2 : 1;
-  const size_t kp = pad8(K);
-  size_t a = ((size_t)M * kp * 2 + 255) / 256 * 256, b = ((size_t)N * kp * 2 + 255) / 256 * 256;
+  // either orientation of either operand fits: rows x pad8(cols)
+  size_t a = ((size_t)pad8(M) * pad8(K) * 2 + 255) / 256 * 256, b = ((size_t)pad8(N) * pad8(K) * 2 + 255) / 256 * 256;
   return parts * (a + b);
 }
 
-extern "C" int clasr_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int precision,
-                             void* workspace, size_t workspace_bytes, void* stream) {
-  CLASR_CHECK_ARG(A && B && C && workspace, "gemm_nt: null pointer");
-  CLASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_nt: non-positive dimension");
-  CLASR_CHECK_ARG(precision == CLASR_PREC_BF16 || precision == CLASR_PREC_BF16X3, "gemm_nt: bad precision");
-  CLASR_CHECK_ARG(workspace_bytes >= clasr_gemm_workspace_bytes(M, N, K, precision), "gemm_nt: workspace too small");
-  CLASR_CHECK_ARG((((uintptr_t)workspace) & 255) == 0, "gemm_nt: workspace must be 256-byte aligned");
+extern "C" int clasr_gemm_ex(const float* A, const float* B, float* C, int M, int N, int K, int a_trans, int b_trans,
+                             int k_splits, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  CLASR_CHECK_ARG(A && B && C && workspace, "gemm: null pointer");
+  CLASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: non-positive dimension");
+  CLASR_CHECK_ARG(precision == CLASR_PREC_BF16 || precision == CLASR_PREC_BF16X3, "gemm: bad precision");
+  CLASR_CHECK_ARG(workspace_bytes >= clasr_gemm_workspace_bytes(M, N, K, precision), "gemm: workspace too small");
+  CLASR_CHECK_ARG((((uintptr_t)workspace) & 255) == 0, "gemm: workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   const bool x3 = precision == CLASR_PREC_BF16X3;
-  const int kp = pad8(K);
-  const size_t a_sz = ((size_t)M * kp * 2 + 255) / 256 * 256, b_sz = ((size_t)N * kp * 2 + 255) / 256 * 256;
+  const size_t a_sz = ((size_t)pad8(M) * pad8(K) * 2 + 255) / 256 * 256;
+  const size_t b_sz = ((size_t)pad8(N) * pad8(K) * 2 + 255) / 256 * 256;
   char* w = (char*)workspace;
   void* a_hi = w; w += a_sz;
   void* a_lo = x3 ? w : nullptr; if (x3) w += a_sz;
   void* b_hi = w; w += b_sz;
   void* b_lo = x3 ? w : nullptr;
+  // a_trans: A is given as [K, M] row-major; else [M, K].  Same for B with N.
+  const int a_rows = a_trans ? K : M, a_cols = a_trans ? M : K;
+  const int b_rows = b_trans ? K : N, b_cols = b_trans ? N : K;
   int rc;
-  if ((rc = launch_split_bf16(A, M, K, K, a_hi, a_lo, kp, s))) return rc;
-  if ((rc = launch_split_bf16(B, N, K, K, b_hi, b_lo, kp, s))) return rc;
-  return launch_gemm_tc(a_hi, a_lo, b_hi, b_lo, M, N, K, kp, C, N, precision, 0, s);
+  if ((rc = launch_split_bf16(A, a_rows, a_cols, a_cols, a_hi, a_lo, pad8(a_cols), s))) return rc;
+  if ((rc = launch_split_bf16(B, b_rows, b_cols, b_cols, b_hi, b_lo, pad8(b_cols), s))) return rc;
+  if (k_splits > 1) {
+    cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
+    CLASR_CHECK_ARG(e == cudaSuccess, "gemm: memset failed");
+  }
+  return launch_gemm_tc(a_hi, a_lo, pad8(a_cols), a_trans, b_hi, b_lo, pad8(b_cols), b_trans, M, N, K, C, N, precision,
+                        k_splits > 1, k_splits, s, nullptr, nullptr);
+}
+
+extern "C" int clasr_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int precision,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  return clasr_gemm_ex(A, B, C, M, N, K, 0, 0, 1, precision, workspace, workspace_bytes, stream);
 }

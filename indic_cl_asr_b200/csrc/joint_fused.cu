@@ -58,6 +58,16 @@ struct JointFwdParams {
   int B, T, U1, H, Vp, blank, activation;
   LatticeWs w;
   float* sumsq;        // [B,T,U1] sum_v z^2 (MAS), or nullptr
+  // ---- pass 2 (kMode == 1): recompute the logits tile and emit the softmax-fused gradient as GEMM operands
+  const float* grad_out;      // [B] upstream gradient of each cost (may be nullptr == 1)
+  float fastemit_lambda, clamp;
+  __nv_bfloat16* dz_hi;       // [rows_pad, ldz]  dZ split hi/lo, compact tile-row order
+  __nv_bfloat16* dz_lo;
+  int ldz;                    // multiple of 8, >= Vp
+  __nv_bfloat16* hid_hi;      // [rows_pad, ldh]  act(f+g) split hi/lo; column H holds 1.0 (bias-gradient trick)
+  __nv_bfloat16* hid_lo;
+  int ldh;                    // H + 8
+  int* rows_pad_dev;          // [1] total_tiles * 128 (written by the tile-offset kernel)
 };
 
 __device__ __forceinline__ float joint_act(float x, int act) {
@@ -71,7 +81,7 @@ __device__ __forceinline__ float joint_act(float x, int act) {
 }
 
 __global__ void joint_tile_offsets_kernel(const int64_t* __restrict__ act_lens, const int64_t* __restrict__ label_lens,
-                                          int B, int* __restrict__ tile_offsets) {
+                                          int B, int* __restrict__ tile_offsets, int* __restrict__ rows_pad_dev) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int acc = 0;
     tile_offsets[0] = 0;
@@ -81,6 +91,7 @@ __global__ void joint_tile_offsets_kernel(const int64_t* __restrict__ act_lens, 
       acc += (int)((cells + kJM - 1) / kJM);
       tile_offsets[b + 1] = acc;
     }
+    rows_pad_dev[0] = acc * kJM;
   }
 }
 
@@ -93,7 +104,7 @@ __device__ __forceinline__ int find_utterance(const int* __restrict__ offs, int 
   return lo;
 }
 
-template <int kTerms>
+template <int kTerms, int kMode>
 __global__ void __launch_bounds__(kJThreads, 1)
 joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                  JointFwdParams p) {
@@ -202,7 +213,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ============================ epilogue: online log-sum-exp + gather ============================
+    // ============================ epilogue ============================
+    // kMode 0: online log-sum-exp + gather of logit[blank] / logit[label]  (pass 1)
+    // kMode 1: softmax-fused gradient dZ = clamp(exp(logp + occupancy) - blank/label terms) * grad_out, split into
+    //          bf16 hi/lo and written in tile-row order as the operand of the two backward GEMMs (pass 2)
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int acc_it = 0;
@@ -214,45 +228,105 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       const int t = valid ? r / Ub1 : 0;
       const int u = valid ? r - t * Ub1 : 0;
       const int label = (valid && u < Ub1 - 1) ? (int)p.labels[(int64_t)b * (p.U1 - 1) + u] : -1;
+      const int64_t idx = ((int64_t)b * p.w.ND + t + u) * p.U1 + u;
       float m = -INFINITY, s = 0.f, zb = 0.f, zl = 0.f, ssq = 0.f;
+      // pass-2 per-row scalars (same algebra as rnnt_grad_kernel, gpu_rnnt_kernel.py:351-396)
+      float base = 0.f, fe_base = 0.f, blank_sub = 0.f, label_sub = 0.f, go = 0.f, dn = 0.f;
+      bool fe = false;
+      if (kMode == 1 && valid) {
+        const double a = p.w.alpha[idx], bt = p.w.beta[idx], ll = p.w.ll_fwd[b];
+        dn = p.w.denom[idx];
+        const float2 lpair = p.w.lp[idx];
+        go = p.grad_out ? p.grad_out[b] : 1.f;
+        const bool has_label = u < Ub1 - 1;
+        const double beta_t1 = (t < Tb - 1) ? p.w.beta[idx + p.U1] : 0.0;
+        const double beta_u1 = has_label ? p.w.beta[idx + p.U1 + 1] : 0.0;
+        base = (float)(a + bt - ll) + dn;
+        fe = p.fastemit_lambda > 0.f && has_label;
+        fe_base = fe ? (float)(a + beta_u1 - ll + (double)lpair.y) + dn : 0.f;
+        if (t == Tb - 1 && u == Ub1 - 1) blank_sub += expf((float)(a - ll + (double)lpair.x));
+        if (t < Tb - 1) blank_sub += expf((float)(a + beta_t1 - ll + (double)lpair.x));
+        label_sub = has_label ? expf(log1pf(p.fastemit_lambda) + (float)(a + beta_u1 - ll + (double)lpair.y)) : 0.f;
+      }
+      const int64_t grow = (int64_t)tile * kJM + row;  // compact tile-row index of this thread's row
       for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
         const int acc = acc_it & 1;
         const uint32_t acc_phase = (acc_it >> 1) & 1;
         tc::mbar_wait(&tmem_full[acc], acc_phase);
         tc::tc_fence_after();
-        const int ncols = (nt == n_tiles - 1) ? (p.Vp - nt * C::kBN) : C::kBN;
+        // columns this N tile must cover: up to Vp (stats) or up to the padded operand width ldz (gradient)
+        const int width = (kMode == 1 ? p.ldz : p.Vp);
+        const int ncols = (nt == n_tiles - 1) ? (width - nt * C::kBN) : C::kBN;
 #pragma unroll 1
         for (int c = 0; c * 32 < ncols; ++c) {
           uint32_t rr[32];
           tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN + c * 32, rr);
           tc::tmem_ld_wait();
           const int col0 = nt * C::kBN + c * 32;
-          float z[32];
-          float cm = -INFINITY;
+          if (kMode == 0) {
+            float z[32];
+            float cm = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            const bool in = col < p.Vp;
-            z[j] = in ? __uint_as_float(rr[j]) + __ldg(p.bias + (in ? col : 0)) : -INFINITY;
-            cm = fmaxf(cm, z[j]);
-            if (col == p.blank) zb = z[j];
-            if (col == label) zl = z[j];
-            if (in) ssq = fmaf(z[j], z[j], ssq);
-          }
-          if (cm > m) {
-            s *= __expf(m - cm);
-            m = cm;
-          }
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              const bool in = col < p.Vp;
+              z[j] = in ? __uint_as_float(rr[j]) + __ldg(p.bias + (in ? col : 0)) : -INFINITY;
+              cm = fmaxf(cm, z[j]);
+              if (col == p.blank) zb = z[j];
+              if (col == label) zl = z[j];
+              if (in) ssq = fmaf(z[j], z[j], ssq);
+            }
+            if (cm > m) {
+              s *= __expf(m - cm);
+              m = cm;
+            }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += __expf(z[j] - m);
+            for (int j = 0; j < 32; ++j) s += __expf(z[j] - m);
+          } else {
+            __nv_bfloat16* dh = p.dz_hi + grow * p.ldz + col0;
+            __nv_bfloat16* dl = p.dz_lo + grow * p.ldz + col0;
+#pragma unroll
+            for (int j8 = 0; j8 < 32; j8 += 8) {
+              if (col0 + j8 < p.ldz) {  // ldz is a multiple of 8: whole 16-byte groups
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int j2 = 0; j2 < 8; j2 += 2) {
+                  float gv[2];
+#pragma unroll
+                  for (int e = 0; e < 2; ++e) {
+                    const int j = j8 + j2 + e;
+                    const int col = col0 + j;
+                    float gr = 0.f;
+                    if (valid && col < p.Vp) {
+                      const float z = __uint_as_float(rr[j]) + __ldg(p.bias + col);
+                      gr = expf(z + base);
+                      if (fe) gr += p.fastemit_lambda * expf(z + fe_base);
+                      if (col == p.blank) gr -= blank_sub;
+                      if (col == label) gr -= label_sub;
+                      if (p.clamp > 0.f) gr = fmaxf(fminf(gr, p.clamp), -p.clamp);
+                      gr *= go;
+                    }
+                    gv[e] = gr;
+                  }
+                  __nv_bfloat16 h0, l0, h1, l1;
+                  tc::split_bf16(gv[0], h0, l0);
+                  tc::split_bf16(gv[1], h1, l1);
+                  __nv_bfloat162 hh = __halves2bfloat162(h0, h1), llo = __halves2bfloat162(l0, l1);
+                  ph[j2 >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                  pl[j2 >> 1] = *reinterpret_cast<uint32_t*>(&llo);
+                }
+                *reinterpret_cast<uint4*>(dh + j8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                if (kTerms > 1) *reinterpret_cast<uint4*>(dl + j8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              }
+            }
+          }
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
       }
-      if (valid) {
+      if (kMode == 0 && valid) {
         const float lse = m + logf(s);
-        const int64_t idx = ((int64_t)b * p.w.ND + t + u) * p.U1 + u;
         p.w.denom[idx] = -lse;
         p.w.lp[idx] = make_float2(zb - lse, label >= 0 ? zl - lse : -INFINITY);
         if (p.sumsq) p.sumsq[((int64_t)b * p.T + t) * p.U1 + u] = ssq;
@@ -303,6 +377,19 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           const uint32_t off = tc::sw128_offset(row, 2 * lane);
           *reinterpret_cast<__nv_bfloat162*>(ablk + off) = __halves2bfloat162(hi0, hi1);
           if (kTerms > 1) *reinterpret_cast<__nv_bfloat162*>(staging + off) = __halves2bfloat162(lo0, lo1);
+          if (kMode == 1) {  // the dW GEMM consumes the hidden activations as an operand: keep a bf16 hi/lo copy
+            const int64_t go_ = ((int64_t)tile * kJM + row) * p.ldh;
+            *reinterpret_cast<__nv_bfloat162*>(p.hid_hi + go_ + k) = __halves2bfloat162(hi0, hi1);
+            if (kTerms > 1) *reinterpret_cast<__nv_bfloat162*>(p.hid_lo + go_ + k) = __halves2bfloat162(lo0, lo1);
+            if (kb == 0 && lane < 4) {  // columns [H, H+8): a column of ones (valid rows) then zeros
+              const float one = (frow[i] && lane == 0) ? 1.f : 0.f;
+              *reinterpret_cast<__nv_bfloat162*>(p.hid_hi + go_ + p.H + 2 * lane) =
+                  __halves2bfloat162(__float2bfloat16_rn(one), __float2bfloat16_rn(0.f));
+              if (kTerms > 1)
+                *reinterpret_cast<__nv_bfloat162*>(p.hid_lo + go_ + p.H + 2 * lane) =
+                    __halves2bfloat162(__float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f));
+            }
+          }
         }
         if (kTerms > 1) {
           // staging (row-major, swizzled) -> tensor memory (lane = row): thread owns row q*32+lane, half of the block
@@ -341,16 +428,115 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pass-2 tail: d_pre = dHid * act'(f+g), reduced over u (-> d_f) and over t (-> d_g).
+// dHid is in compact tile-row order: row(b,t,u) = tile_offsets[b]*128 + t*U_b1 + u.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float joint_act_grad(float pre, int act) {
+  if (act == CLASR_ACT_RELU) return pre > 0.f ? 1.f : 0.f;
+  if (act == CLASR_ACT_SIGMOID) {
+    const float sg = __fdividef(1.f, 1.f + __expf(-pre));
+    return sg * (1.f - sg);
+  }
+  const float h = joint_act(pre, CLASR_ACT_TANH);
+  return 1.f - h * h;
+}
+
+// mode 0: grid (T, B) -> d_f[b,t,:] = sum_u ;  mode 1: grid (U1, B) -> d_g[b,u,:] = sum_t
+__global__ void __launch_bounds__(256) joint_dfg_kernel(const float* __restrict__ dhid, const float* __restrict__ f,
+                                                        const float* __restrict__ g,
+                                                        const int64_t* __restrict__ act_lens,
+                                                        const int64_t* __restrict__ label_lens,
+                                                        const int* __restrict__ tile_offsets, int T, int U1, int H,
+                                                        int activation, int mode, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x;  // t (mode 0) or u (mode 1)
+  const int Tb = (int)act_lens[b], Ub1 = (int)label_lens[b] + 1;
+  const int64_t row0 = (int64_t)tile_offsets[b] * kJM;
+  float* __restrict__ o = out + ((int64_t)b * (mode == 0 ? T : U1) + i) * H;
+  const bool live = mode == 0 ? (i < Tb) : (i < Ub1 && Tb > 0);
+  for (int k = threadIdx.x * 4; k < H; k += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      if (mode == 0) {
+        const float4 fv = *reinterpret_cast<const float4*>(f + ((int64_t)b * T + i) * H + k);
+        for (int u = 0; u < Ub1; ++u) {
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(g + ((int64_t)b * U1 + u) * H + k));
+          const float4 d = __ldg(reinterpret_cast<const float4*>(dhid + (row0 + (int64_t)i * Ub1 + u) * H + k));
+          acc.x = fmaf(d.x, joint_act_grad(fv.x + gv.x, activation), acc.x);
+          acc.y = fmaf(d.y, joint_act_grad(fv.y + gv.y, activation), acc.y);
+          acc.z = fmaf(d.z, joint_act_grad(fv.z + gv.z, activation), acc.z);
+          acc.w = fmaf(d.w, joint_act_grad(fv.w + gv.w, activation), acc.w);
+        }
+      } else {
+        const float4 gv = *reinterpret_cast<const float4*>(g + ((int64_t)b * U1 + i) * H + k);
+        for (int t = 0; t < Tb; ++t) {
+          const float4 fv = __ldg(reinterpret_cast<const float4*>(f + ((int64_t)b * T + t) * H + k));
+          const float4 d = __ldg(reinterpret_cast<const float4*>(dhid + (row0 + (int64_t)t * Ub1 + i) * H + k));
+          acc.x = fmaf(d.x, joint_act_grad(fv.x + gv.x, activation), acc.x);
+          acc.y = fmaf(d.y, joint_act_grad(fv.y + gv.y, activation), acc.y);
+          acc.z = fmaf(d.z, joint_act_grad(fv.z + gv.z, activation), acc.z);
+          acc.w = fmaf(d.w, joint_act_grad(fv.w + gv.w, activation), acc.w);
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(o + k) = acc;
+  }
+}
+
+// dW_ext [Vp, H+8] -> d_w [Vp, H], d_b [Vp] (column H of dW_ext = dZ^T . 1)
+__global__ void joint_dw_finish_kernel(const float* __restrict__ dw_ext, int Vp, int H, int ld,
+                                       float* __restrict__ d_w, float* __restrict__ d_b) {
+  const int v = blockIdx.x;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) d_w[(int64_t)v * H + k] = dw_ext[(int64_t)v * ld + k];
+  if (threadIdx.x == 0) d_b[v] = dw_ext[(int64_t)v * ld + H];
+}
+
+int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
+                   int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
+                   int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev);
+
+// ------------------------------------------------------------------------------------------------
 // workspace layout of the fused path
 // ------------------------------------------------------------------------------------------------
 struct JointWs {
   void* lattice;
   void* w_hi;
   void* w_lo;
-  int* tile_offsets;
+  int* tile_offsets;   // [B+1], then [1] rows_pad
   int vp_pad;
   size_t total;
 };
+
+// Scratch of the backward pass (caller-allocated, reusable across steps).  Sized for the worst case (no ragged
+// savings); the kernels only touch the first rows_pad rows, a count that stays on the device.
+struct JointBwdScratch {
+  void* dz_hi; void* dz_lo;     // [rows_cap, ldz] bf16
+  void* hid_hi; void* hid_lo;   // [rows_cap, ldh] bf16
+  float* dhid;                  // [rows_cap, H]
+  float* dw_ext;                // [Vp, ldh]
+  int64_t rows_cap;
+  int ldz, ldh;
+  size_t total;
+};
+
+static inline JointBwdScratch joint_bwd_scratch_carve(void* base, int B, int T, int U1, int H, int Vp, int precision) {
+  JointBwdScratch sc;
+  const bool x3 = precision == CLASR_PREC_BF16X3;
+  sc.rows_cap = (int64_t)B * ((((int64_t)T * U1) + kJM - 1) / kJM) * kJM;
+  sc.ldz = (Vp + 7) / 8 * 8;
+  sc.ldh = H + 8;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* r = p + off; off += (bytes + 255) / 256 * 256; return r; };
+  sc.dz_hi = take((size_t)sc.rows_cap * sc.ldz * 2);
+  sc.dz_lo = x3 ? take((size_t)sc.rows_cap * sc.ldz * 2) : sc.dz_hi;
+  sc.hid_hi = take((size_t)sc.rows_cap * sc.ldh * 2);
+  sc.hid_lo = x3 ? take((size_t)sc.rows_cap * sc.ldh * 2) : sc.hid_hi;
+  sc.dhid = (float*)take((size_t)sc.rows_cap * H * 4);
+  sc.dw_ext = (float*)take((size_t)Vp * sc.ldh * 4);
+  sc.total = off;
+  return sc;
+}
 
 static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, int Vp, int precision) {
   JointWs j;
@@ -363,7 +549,7 @@ static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, in
   j.w_hi = p + off; off += wbytes;
   j.w_lo = p + off; off += (precision == CLASR_PREC_BF16X3) ? wbytes : 0;
   j.tile_offsets = (int*)(p + off);
-  off += ((size_t)(B + 1) * sizeof(int) + 255) / 256 * 256;
+  off += ((size_t)(B + 2) * sizeof(int) + 255) / 256 * 256;
   j.total = off;
   return j;
 }
@@ -410,10 +596,10 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   const bool x3 = precision == CLASR_PREC_BF16X3;
   // W_out [Vp,H] fp32 -> bf16 hi[,lo] (rows beyond Vp are never read: TMA zero-fills out-of-bounds rows)
   if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s))) return rc;
-  joint_tile_offsets_kernel<<<1, 32, 0, s>>>(act_lens, label_lens, B, jw.tile_offsets);
+  joint_tile_offsets_kernel<<<1, 32, 0, s>>>(act_lens, label_lens, B, jw.tile_offsets, jw.tile_offsets + B + 1);
   CLASR_CHECK_LAUNCH("joint_tile_offsets");
 
-  JointFwdParams p;
+  JointFwdParams p = {};
   p.f = f; p.g = g; p.bias = b_out; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
   p.tile_offsets = jw.tile_offsets;
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank; p.activation = activation;
@@ -429,20 +615,95 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   }
   if (x3) {
     const int smem = JointCfg<3>::smem_bytes(H);
-    cudaFuncSetAttribute(joint_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    joint_fwd_kernel<3><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
+    cudaFuncSetAttribute(joint_fwd_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    joint_fwd_kernel<3, 0><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
   } else {
     const int smem = JointCfg<1>::smem_bytes(H);
-    cudaFuncSetAttribute(joint_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    joint_fwd_kernel<1><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
+    cudaFuncSetAttribute(joint_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    joint_fwd_kernel<1, 0><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
   }
   CLASR_CHECK_LAUNCH("joint_fwd");
   return launch_rnnt_lattice(p.w, act_lens, label_lens, B, T, U1, fastemit_lambda, costs, s);
 }
 
-extern "C" int clasr_joint_rnnt_bwd(const float*, const float*, const float*, const float*, const int64_t*,
-                                    const int64_t*, const int64_t*, int, int, int, int, int, int, int, int, float,
-                                    float, const float*, float*, float*, float*, float*, void*, size_t, void*) {
-  set_error("joint_rnnt_bwd: not implemented yet");
-  return CLASR_STATUS_INVALID_VALUE;
+extern "C" size_t clasr_joint_bwd_scratch_bytes(int B, int T, int U1, int H, int Vp, int precision) {
+  if (B <= 0 || T <= 0 || U1 <= 0 || H <= 0 || Vp <= 0) return 0;
+  return joint_bwd_scratch_carve(nullptr, B, T, U1, H, Vp, precision).total;
+}
+
+extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
+                                    const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
+                                    int T, int U1, int H, int Vp, int blank, int activation, int precision,
+                                    float fastemit_lambda, float clamp, const float* grad_out, float* d_f, float* d_g,
+                                    float* d_w_out, float* d_b_out, void* workspace, size_t workspace_bytes,
+                                    void* scratch, size_t scratch_bytes, void* stream) {
+  int rc = check_joint_args("joint_rnnt_bwd", f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank,
+                            activation, precision, workspace, workspace_bytes);
+  if (rc) return rc;
+  CLASR_CHECK_ARG(d_f && d_g && d_w_out && d_b_out && scratch, "joint_rnnt_bwd: null output / scratch");
+  CLASR_CHECK_ARG(clamp >= 0.f, "joint_rnnt_bwd: `clamp` must be 0.0 or positive");
+  CLASR_CHECK_ARG(scratch_bytes >= clasr_joint_bwd_scratch_bytes(B, T, U1, H, Vp, precision),
+                  "joint_rnnt_bwd: scratch too small");
+  CLASR_CHECK_ARG((((uintptr_t)scratch) & 255) == 0, "joint_rnnt_bwd: scratch must be 256-byte aligned");
+  CLASR_CHECK_ARG((H & 3) == 0, "joint_rnnt_bwd: H must be a multiple of 4");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool x3 = precision == CLASR_PREC_BF16X3;
+  JointWs jw = joint_ws_carve(workspace, B, T, U1, H, Vp, precision);   // filled by the forward call
+  JointBwdScratch sc = joint_bwd_scratch_carve(scratch, B, T, U1, H, Vp, precision);
+  CLASR_CHECK_ARG(sc.rows_cap < 2147483647LL, "joint_rnnt_bwd: too many lattice cells");
+  int* rows_pad_dev = jw.tile_offsets + B + 1;
+
+  // ---- pass 2a: recompute logits tile-wise, emit dZ (bf16 hi/lo) and the hidden activations as GEMM operands
+  JointFwdParams p = {};
+  p.f = f; p.g = g; p.bias = b_out; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
+  p.tile_offsets = jw.tile_offsets;
+  p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank; p.activation = activation;
+  p.w = lattice_ws_carve(jw.lattice, B, T, U1);
+  p.grad_out = grad_out; p.fastemit_lambda = fastemit_lambda; p.clamp = clamp;
+  p.dz_hi = (__nv_bfloat16*)sc.dz_hi; p.dz_lo = (__nv_bfloat16*)sc.dz_lo; p.ldz = sc.ldz;
+  p.hid_hi = (__nv_bfloat16*)sc.hid_hi; p.hid_lo = (__nv_bfloat16*)sc.hid_lo; p.ldh = sc.ldh;
+  p.rows_pad_dev = rows_pad_dev;
+  CUtensorMap tw_hi, tw_lo;
+  const int bn = x3 ? JointCfg<3>::kBN : JointCfg<1>::kBN;
+  if ((rc = make_tmap_bf16_2d(&tw_hi, jw.w_hi, Vp, H, H, bn, kJK))) return rc;
+  if (x3) {
+    if ((rc = make_tmap_bf16_2d(&tw_lo, jw.w_lo, Vp, H, H, bn, kJK))) return rc;
+  } else {
+    tw_lo = tw_hi;
+  }
+  if (x3) {
+    const int smem = JointCfg<3>::smem_bytes(H);
+    cudaFuncSetAttribute(joint_fwd_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    joint_fwd_kernel<3, 1><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
+  } else {
+    const int smem = JointCfg<1>::smem_bytes(H);
+    cudaFuncSetAttribute(joint_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    joint_fwd_kernel<1, 1><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
+  }
+  CLASR_CHECK_LAUNCH("joint_bwd_dz");
+
+  // ---- pass 2b: dHid[rows, H] = dZ[rows, Vp] . W[Vp, H]      (A K-major, B = W consumed MN-major: no transpose)
+  if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 0, jw.w_hi, jw.w_lo, H, 1, (int)sc.rows_cap, H, Vp, sc.dhid, H,
+                           precision, 0, 1, s, rows_pad_dev, nullptr)))
+    return rc;
+  // ---- pass 2c: dW_ext[Vp, H+8] = dZ^T . [Hid | 1 | 0]       (both operands MN-major, split-K over the rows)
+  cudaError_t e = cudaMemsetAsync(sc.dw_ext, 0, (size_t)Vp * sc.ldh * sizeof(float), s);
+  CLASR_CHECK_ARG(e == cudaSuccess, "joint_rnnt_bwd: memset failed");
+  {
+    const int mn_tiles = ((Vp + 127) / 128) * ((sc.ldh + 255) / 256);
+    int splits = (2 * kNumSMs + mn_tiles - 1) / mn_tiles;
+    if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, sc.hid_hi, sc.hid_lo, sc.ldh, 1, Vp, sc.ldh,
+                             (int)sc.rows_cap, sc.dw_ext, sc.ldh, precision, 1, splits, s, nullptr, rows_pad_dev)))
+      return rc;
+  }
+  joint_dw_finish_kernel<<<Vp, 128, 0, s>>>(sc.dw_ext, Vp, H, sc.ldh, d_w_out, d_b_out);
+  CLASR_CHECK_LAUNCH("joint_dw_finish");
+  // ---- pass 2d: through the activation and the broadcast add
+  joint_dfg_kernel<<<dim3(T, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
+                                             activation, 0, d_f);
+  CLASR_CHECK_LAUNCH("joint_df");
+  joint_dfg_kernel<<<dim3(U1, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
+                                              activation, 1, d_g);
+  CLASR_CHECK_LAUNCH("joint_dg");
+  return CLASR_STATUS_SUCCESS;
 }

@@ -148,11 +148,24 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major operand, 128-byte swizzle: the tile is stored as [K rows][64 MN elements = 128 B]; 8 K-rows form a
+// 1024-byte swizzle atom (SBO = 1024 between K groups of 8), consecutive 64-element MN blocks are `lbo_bytes`
+// apart (canonical layout ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in elements, cute::UMMA make_umma_desc<MN>).
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major
 // (cute::UMMA::InstrDescriptor): c_format [4,6)=1 (F32), a_format [7,10)=1 (BF16), b_format [10,13)=1,
 // a_major [15]=0, b_major [16]=0, n_dim [17,23)=N>>3, m_dim [24,29)=M>>4.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_mn_major & 1) << 15) | ((uint32_t)(b_mn_major & 1) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // Byte offset of element (row, k) inside a K-major SWIZZLE_128B tile whose rows are 64 bf16 (128 B) wide and

@@ -75,12 +75,14 @@ class _FusedJointRNNT(torch.autograd.Function):
         d_w = torch.empty_like(weight)
         d_b = torch.empty_like(bias)
         L = _lib.lib()
+        sbytes = L.clasr_joint_bwd_scratch_bytes(B, T, U1, H, Vp, prec)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=f.device)
         with torch.cuda.device(f.device):
             st = L.clasr_joint_rnnt_bwd(
                 f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
                 act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, blank, act, prec, fastemit_lambda, clamp,
                 go.data_ptr(), d_f.data_ptr(), d_g.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ws.data_ptr(), nbytes,
-                _lib.stream_ptr(f.device))
+                scratch.data_ptr(), sbytes, _lib.stream_ptr(f.device))
         _lib.check(st, "joint_rnnt_bwd")
         return (d_f, d_g, d_w, d_b) + (None,) * 9
 

@@ -35,3 +35,31 @@ def test_gemm_nt(M, N, K, precision, tol):
     assert torch.isfinite(C).all()
     err = (C - ref).abs().max().item() / ref.abs().max().item()
     assert err <= tol, err
+
+
+def gemm_ex(A, B, M, N, K, a_trans, b_trans, k_splits, precision):
+    L = _lib.lib()
+    prec = _lib.PREC[precision]
+    nbytes = L.clasr_gemm_workspace_bytes(M, N, K, prec)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    C = torch.full((M, N), float("nan"), device=DEV)
+    _lib.check(L.clasr_gemm_ex(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, int(a_trans), int(b_trans), k_splits,
+                               prec, ws.data_ptr(), nbytes, _lib.stream_ptr()), "gemm_ex")
+    torch.cuda.synchronize()
+    return C
+
+
+@pytest.mark.parametrize("a_trans,b_trans", [(0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,splits", [(128, 256, 64, 1), (200, 300, 500, 1), (1025, 648, 4000, 7), (640, 1025, 256, 1)])
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("bf16x3", 2e-5)])
+def test_gemm_transposed_operands_and_split_k(M, N, K, splits, a_trans, b_trans, precision, tol):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g) / K ** 0.5
+    Ain = (A.t().contiguous() if a_trans else A).to(DEV)
+    Bin = (B.t().contiguous() if b_trans else B).to(DEV)
+    C = gemm_ex(Ain, Bin, M, N, K, a_trans, b_trans, splits, precision).cpu().double()
+    ref = A.double() @ B.double().t()
+    assert torch.isfinite(C).all()
+    err = (C - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= tol, err
