@@ -50,6 +50,12 @@ CLASR_API int clasr_version(void);
 CLASR_API const char* clasr_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
 CLASR_API int64_t clasr_launch_count(void);
+/* Optional per-kernel timing for the roofline numbers: when on, the library brackets its major kernels with CUDA
+ * events on the launch stream ("joint_fwd", "joint_bwd_dz", "gemm_dhid", "gemm_dw", "rnnt_lattice", "rnnt_lse",
+ * "rnnt_grad", "ctc_lattice", "ctc_grad", "cl_penalty_grad", ...).  clasr_profile_ms synchronises on the events. */
+CLASR_API void clasr_set_profiling(int on);
+CLASR_API void clasr_profile_reset(void);
+CLASR_API float clasr_profile_ms(const char* name, int* count);
 
 /* ------------------------------------------------------------------------------------------
  * 1. Continual-learning regulariser sweeps over FLAT fp32 parameter buffers.

@@ -29,6 +29,9 @@ _PROTOS: Dict[str, Tuple[object, List[object]]] = {
     "clasr_version": (_i, []),
     "clasr_last_error": (C.c_char_p, []),
     "clasr_launch_count": (_i64, []),
+    "clasr_set_profiling": (None, [_i]),
+    "clasr_profile_reset": (None, []),
+    "clasr_profile_ms": (C.c_float, [C.c_char_p, _vp]),
     "clasr_cl_penalty_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _i, _vp, _vp]),
     "clasr_cl_penalty_avg": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "clasr_cl_fisher_accum": (_i, [_vp, _vp, _i64, _vp, _vp]),
@@ -107,3 +110,8 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
 
 def launch_count() -> int:
     return int(lib().clasr_launch_count())
+
+
+def profile_ms(name: str) -> float:
+    """Mean ms of the library kernel recorded under `name` since the last reset (-1 if none)."""
+    return float(lib().clasr_profile_ms(name.encode(), None))

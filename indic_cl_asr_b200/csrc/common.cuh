@@ -13,6 +13,8 @@ constexpr int kNumSMs = 148;  // B200
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end(const char* name, cudaStream_t s);
 
 #define CLASR_CHECK_ARG(cond, ...)              \
   do {                                          \

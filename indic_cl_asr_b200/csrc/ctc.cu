@@ -270,8 +270,10 @@ extern "C" int clasr_ctc_loss_fwd(const float* log_probs, const int64_t* targets
     cudaError_t e = cudaFuncSetAttribute(ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     CLASR_CHECK_ARG(e == cudaSuccess, "ctc_loss_fwd: target too long for shared memory (%zu bytes)", smem);
   }
+  prof_begin("ctc_lattice", (cudaStream_t)stream);
   ctc_lattice_kernel<<<dim3(B, need_beta ? 2 : 1), threads, smem, (cudaStream_t)stream>>>(
       log_probs, targets, target_stride, input_lens, target_lens, T, Vp, blank, zero_infinity, w, nll);
+  prof_end("ctc_lattice", (cudaStream_t)stream);
   CLASR_CHECK_LAUNCH("ctc_lattice");
   return CLASR_STATUS_SUCCESS;
 }
@@ -291,9 +293,11 @@ extern "C" int clasr_ctc_loss_bwd(const float* log_probs, const int64_t* targets
     cudaError_t e = cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     CLASR_CHECK_ARG(e == cudaSuccess, "ctc_loss_bwd: vocabulary too large for shared memory (%zu bytes)", smem);
   }
+  prof_begin("ctc_grad", (cudaStream_t)stream);
   ctc_grad_kernel<<<dim3(T, B), 256, smem, (cudaStream_t)stream>>>(log_probs, targets, target_stride, input_lens,
                                                                   target_lens, T, Vp, blank, zero_infinity, grad_out,
                                                                   grad, w);
+  prof_end("ctc_grad", (cudaStream_t)stream);
   CLASR_CHECK_LAUNCH("ctc_grad");
   return CLASR_STATUS_SUCCESS;
 }

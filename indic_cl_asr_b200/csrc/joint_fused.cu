@@ -613,6 +613,7 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   } else {
     tw_lo = tw_hi;
   }
+  prof_begin("joint_fwd", s);
   if (x3) {
     const int smem = JointCfg<3>::smem_bytes(H);
     cudaFuncSetAttribute(joint_fwd_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -622,6 +623,7 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
     cudaFuncSetAttribute(joint_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     joint_fwd_kernel<1, 0><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
   }
+  prof_end("joint_fwd", s);
   CLASR_CHECK_LAUNCH("joint_fwd");
   return launch_rnnt_lattice(p.w, act_lens, label_lens, B, T, U1, fastemit_lambda, costs, s);
 }
@@ -671,6 +673,7 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
   } else {
     tw_lo = tw_hi;
   }
+  prof_begin("joint_bwd_dz", s);
   if (x3) {
     const int smem = JointCfg<3>::smem_bytes(H);
     cudaFuncSetAttribute(joint_fwd_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -680,30 +683,37 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
     cudaFuncSetAttribute(joint_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     joint_fwd_kernel<1, 1><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
   }
+  prof_end("joint_bwd_dz", s);
   CLASR_CHECK_LAUNCH("joint_bwd_dz");
 
   // ---- pass 2b: dHid[rows, H] = dZ[rows, Vp] . W[Vp, H]      (A K-major, B = W consumed MN-major: no transpose)
+  prof_begin("gemm_dhid", s);
   if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 0, jw.w_hi, jw.w_lo, H, 1, (int)sc.rows_cap, H, Vp, sc.dhid, H,
                            precision, 0, 1, s, rows_pad_dev, nullptr)))
     return rc;
+  prof_end("gemm_dhid", s);
   // ---- pass 2c: dW_ext[Vp, H+8] = dZ^T . [Hid | 1 | 0]       (both operands MN-major, split-K over the rows)
   cudaError_t e = cudaMemsetAsync(sc.dw_ext, 0, (size_t)Vp * sc.ldh * sizeof(float), s);
   CLASR_CHECK_ARG(e == cudaSuccess, "joint_rnnt_bwd: memset failed");
   {
     const int mn_tiles = ((Vp + 127) / 128) * ((sc.ldh + 255) / 256);
     int splits = (2 * kNumSMs + mn_tiles - 1) / mn_tiles;
+    prof_begin("gemm_dw", s);
     if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, sc.hid_hi, sc.hid_lo, sc.ldh, 1, Vp, sc.ldh,
                              (int)sc.rows_cap, sc.dw_ext, sc.ldh, precision, 1, splits, s, nullptr, rows_pad_dev)))
       return rc;
+    prof_end("gemm_dw", s);
   }
   joint_dw_finish_kernel<<<Vp, 128, 0, s>>>(sc.dw_ext, Vp, H, sc.ldh, d_w_out, d_b_out);
   CLASR_CHECK_LAUNCH("joint_dw_finish");
   // ---- pass 2d: through the activation and the broadcast add
+  prof_begin("joint_dfg", s);
   joint_dfg_kernel<<<dim3(T, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
                                              activation, 0, d_f);
   CLASR_CHECK_LAUNCH("joint_df");
   joint_dfg_kernel<<<dim3(U1, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
                                               activation, 1, d_g);
+  prof_end("joint_dfg", s);
   CLASR_CHECK_LAUNCH("joint_dg");
   return CLASR_STATUS_SUCCESS;
 }

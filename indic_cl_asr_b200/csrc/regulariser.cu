@@ -257,6 +257,7 @@ extern "C" int clasr_cl_penalty_grad(const float* theta, const float* theta_star
                   "cl_penalty_grad: buffers must be 16-byte aligned");
   if (n_items == 0) return CLASR_STATUS_SUCCESS;
   cudaStream_t s = (cudaStream_t)stream;
+  prof_begin("cl_penalty_grad", s);
   int grid = (int)(n_items < (int64_t)kNumSMs * 4 ? n_items : (int64_t)kNumSMs * 4);  // >= 2 resident CTAs per SM, 2 rounds
   if (accumulate) {
     if (seg_abs_sum)
@@ -269,6 +270,7 @@ extern "C" int clasr_cl_penalty_grad(const float* theta, const float* theta_star
     else
       penalty_grad_kernel<false, false><<<grid, kSweepThreads, 0, s>>>(theta, theta_star, fisher, grad_out, items, n_items, coef, nullptr);
   }
+  prof_end("cl_penalty_grad", s);
   CLASR_CHECK_LAUNCH("cl_penalty_grad");
   return CLASR_STATUS_SUCCESS;
 }
@@ -288,8 +290,10 @@ extern "C" int clasr_cl_fisher_accum(float* fisher, const float* grad, int64_t n
   if (n == 0) return CLASR_STATUS_SUCCESS;
   int64_t nvec = n >> 2;
   FisherOp op{weight_dev};
+  prof_begin("cl_fisher_accum", (cudaStream_t)stream);
   accum_kernel<FisherOp><<<sweep_grid((nvec + kSweepThreads * 4 - 1) / (kSweepThreads * 4)), kSweepThreads, 0,
                            (cudaStream_t)stream>>>(fisher, grad, nvec, n, op);
+  prof_end("cl_fisher_accum", (cudaStream_t)stream);
   CLASR_CHECK_LAUNCH("cl_fisher_accum");
   return CLASR_STATUS_SUCCESS;
 }

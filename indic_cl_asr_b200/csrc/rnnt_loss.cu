@@ -212,8 +212,10 @@ int launch_rnnt_lattice(const LatticeWs& w, const int64_t* act_lens, const int64
       return CLASR_STATUS_INVALID_VALUE;
     }
   }
+  prof_begin("rnnt_lattice", stream);
   rnnt_lattice_kernel<<<dim3(B, 2), threads, smem, stream>>>(w, act_lens, label_lens, T, U1, dch, fastemit_lambda,
                                                             costs);
+  prof_end("rnnt_lattice", stream);
   CLASR_CHECK_LAUNCH("rnnt_lattice");
   return CLASR_STATUS_SUCCESS;
 }
@@ -337,8 +339,10 @@ extern "C" int clasr_rnnt_loss_fwd(const float* logits, const int64_t* labels, c
   const int64_t rows = (int64_t)B * T * U1;
   const int64_t grid = (rows + kRowWarps - 1) / kRowWarps;
   CLASR_CHECK_ARG(grid < 2147483647LL, "rnnt_loss_fwd: too many rows");
+  prof_begin("rnnt_lse", s);
   rnnt_lse_gather_kernel<<<(unsigned)grid, kRowWarps * 32, 0, s>>>(logits, labels, act_lens, label_lens, B, T, U1, Vp,
                                                                   blank, w);
+  prof_end("rnnt_lse", s);
   CLASR_CHECK_LAUNCH("rnnt_lse_gather");
   return launch_rnnt_lattice(w, act_lens, label_lens, B, T, U1, fastemit_lambda, costs, s);
 }
@@ -356,8 +360,10 @@ extern "C" int clasr_rnnt_loss_bwd(const float* logits, const int64_t* labels, c
   const int64_t rows = (int64_t)B * T * U1;
   const int64_t grid = (rows + kRowWarps - 1) / kRowWarps;
   CLASR_CHECK_ARG(grid < 2147483647LL, "rnnt_loss_bwd: too many rows");
+  prof_begin("rnnt_grad", (cudaStream_t)stream);
   rnnt_grad_kernel<<<(unsigned)grid, kRowWarps * 32, 0, (cudaStream_t)stream>>>(
       logits, labels, act_lens, label_lens, B, T, U1, Vp, blank, fastemit_lambda, clamp, grad_out, grads, w);
+  prof_end("rnnt_grad", (cudaStream_t)stream);
   CLASR_CHECK_LAUNCH("rnnt_grad");
   return CLASR_STATUS_SUCCESS;
 }
