@@ -121,10 +121,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tmem_empty = bars + 2 * S::kStages + 2; // [2]
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * S::kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = tc::warp_idx_uniform();
   const int lane = threadIdx.x & 31;
-  const int Mdyn = p.m_dev ? min(p.M, *p.m_dev) : p.M;
-  const int Kdyn = p.k_dev ? min(p.K, *p.k_dev) : p.K;
+  const int Mdyn = (int)tc::uniform_u32((uint32_t)(p.m_dev ? min(p.M, *p.m_dev) : p.M));
+  const int Kdyn = (int)tc::uniform_u32((uint32_t)(p.k_dev ? min(p.K, *p.k_dev) : p.K));
   const int m_tiles = (Mdyn + kBM - 1) / kBM;
   const int n_tiles = (p.N + kBN - 1) / kBN;
   const int mn_tiles = m_tiles * n_tiles;
@@ -133,12 +133,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int k_splits = max(1, (kb_total + kb_per_split - 1) / kb_per_split);  // no empty slice
   const int num_tiles = mn_tiles * k_splits;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && tc::elect_one()) {
     tc::prefetch_tmap(&tmA_hi);
     tc::prefetch_tmap(&tmB_hi);
     if (kTerms > 1) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); }
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 1 && tc::elect_one()) {
     for (int i = 0; i < S::kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 4); }
     tc::fence_barrier_init();
@@ -147,22 +147,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tmem_base = tc::uniform_u32(*tmem_base_slot);
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
-        const int m0 = (mn / n_tiles) * kBM;
-        const int n0 = (mn % n_tiles) * kBN;
-        const int kb_begin = ks * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          tc::mbar_wait(&empty[stage], phase ^ 1);
+    // ================= TMA producer (whole warp loops, one elected lane issues) =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+      const int m0 = (mn / n_tiles) * kBM;
+      const int n0 = (mn % n_tiles) * kBN;
+      const int kb_begin = ks * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        if (tc::elect_one()) {
           uint8_t* st = smem + stage * S::kStageBytes;
           tc::mbar_expect_tx(&full[stage], S::kStageBytes);
+#pragma unroll
           for (int part = 0; part < S::kParts; ++part) {
             const CUtensorMap* ta = part == 0 ? &tmA_hi : &tmA_lo;
             const CUtensorMap* tb = part == 0 ? &tmB_hi : &tmB_lo;
@@ -171,37 +172,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (!p.a_mn) {
               tc::tma_load_2d(sa, ta, &full[stage], kb * kBK, m0);
             } else {  // [K rows][64 M] boxes, one per 64-wide M block
+#pragma unroll
               for (int j = 0; j < kBM / 64; ++j) tc::tma_load_2d(sa + j * 8192, ta, &full[stage], m0 + 64 * j, kb * kBK);
             }
             if (!p.b_mn) {
               tc::tma_load_2d(sb, tb, &full[stage], kb * kBK, n0);
             } else {
+#pragma unroll
               for (int j = 0; j < kBN / 64; ++j) tc::tma_load_2d(sb + j * 8192, tb, &full[stage], n0 + 64 * j, kb * kBK);
             }
           }
-          if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (single thread) =================
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16(kBM, kBN, p.a_mn, p.b_mn);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        const int ks = tile / mn_tiles;
-        const int kb_begin = ks * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
-        tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ================= MMA issuer (whole warp loops, one elected lane issues) =================
+    const uint32_t idesc = tc::make_idesc_bf16(kBM, kBN, p.a_mn, p.b_mn);
+    const uint32_t smem_base = tc::smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int ks = tile / mn_tiles;
+      const int kb_begin = ks * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+      tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kBN;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kBN;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          tc::mbar_wait(&full[stage], phase);
-          tc::tc_fence_after();
-          const uint32_t a_hi = tc::smem_u32(smem + stage * S::kStageBytes);
+        if (tc::elect_one()) {
+          const uint32_t a_hi = smem_base + stage * S::kStageBytes;
           const uint32_t a_lo = a_hi + S::kABytes;
           const uint32_t b_hi = a_hi + S::kParts * S::kABytes;
           const uint32_t b_lo = b_hi + S::kBBytes;
@@ -225,10 +230,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
           tc::umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
       }
+      if (tc::elect_one()) tc::umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> global =================

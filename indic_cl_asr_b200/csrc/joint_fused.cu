@@ -32,6 +32,7 @@ constexpr int kJMaxH = 640;         // A tile (128 x H bf16) must stay resident 
 constexpr int kJThreads = 512;      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue, 8-15 A producers
 constexpr int kJProducerWarps = 8;
 constexpr int kJStages = 2;
+constexpr float kJExpClamp = 43.f;  // |pre-activation| clamp of the exp factorisation: exp(2*43) is finite in fp32
 
 template <int kTerms>
 struct JointCfg {
@@ -41,21 +42,22 @@ struct JointCfg {
   static constexpr int kAloCol = kAccCols;                    // BF16X3: A_lo lives in TMEM columns [192, 192+H/2)
   static constexpr int kABlockBytes = kJM * kJK * 2;          // 16 KB per K block of A
   static constexpr int kBStageBytes = kParts * kBN * kJK * 2; // W ring stage
-  static constexpr int kStagingBytes = kTerms == 1 ? 0 : kABlockBytes;  // A_lo staging (row-major -> lane-major)
+  static constexpr int kStagingBytes = kTerms == 1 ? 0 : kJProducerWarps * 2048;  // warp-private 32x32 bf16 lo tiles
+  static constexpr int kRowTabBytes = 4 * 32 * 8;             // (f offset, g offset) of the tile's 128 rows
   static constexpr int smem_bytes(int H) {
-    return (H / kJK) * kABlockBytes + kStagingBytes + kJStages * kBStageBytes + 1024 + 512;
+    return (H / kJK) * kABlockBytes + kStagingBytes + kJStages * kBStageBytes + kRowTabBytes + 256 + 1024;
   }
 };
 
 struct JointFwdParams {
-  const float* f;      // [B,T,H]
-  const float* g;      // [B,U1,H]
+  const float* ef;     // [B,T,H]   activation factor of f (relu: f itself; tanh: exp(2f); sigmoid: exp(-f))
+  const float* eg;     // [B,U1,H]  same for g
   const float* bias;   // [Vp]
   const int64_t* labels;
   const int64_t* act_lens;
   const int64_t* label_lens;
   const int* tile_offsets;  // [B+1] prefix sums of per-utterance tile counts
-  int B, T, U1, H, Vp, blank, activation;
+  int B, T, U1, H, Vp, blank;
   LatticeWs w;
   float* sumsq;        // [B,T,U1] sum_v z^2 (MAS), or nullptr
   // ---- pass 2 (kMode == 1): recompute the logits tile and emit the softmax-fused gradient as GEMM operands
@@ -78,6 +80,32 @@ __device__ __forceinline__ float joint_act(float x, int act) {
   const float e = __expf(2.f * ax);
   const float r = 1.f - __fdividef(2.f, e + 1.f);
   return copysignf(r, x);
+}
+
+// The A operand act(f[t,k] + g[u,k]) is needed for every lattice cell (t,u): 81 920 activations per 128-row tile.
+// exp factorises over the sum, so the transcendental is hoisted out of the T x U product space:
+//   tanh(a+b)    = 1 - 2 / (1 + e^{2a} e^{2b})        sigmoid(a+b) = 1 / (1 + e^{-a} e^{-b})
+// joint_prep_kernel evaluates the factors once per (t,k) and (u,k) with full-precision expf (7 M instead of 517 M
+// exponentials at B=32,T=250,U=100,H=640); the producers then spend one FMA + one MUFU.RCP (+1 FMA) per element.
+// Pre-activations are clamped to +-43 so that the factors stay finite (tanh/sigmoid are saturated to < 1e-37 there).
+__global__ void joint_prep_kernel(const float* __restrict__ x, float* __restrict__ e, int64_t n4, int act) {
+  const float s = act == CLASR_ACT_TANH ? 2.f : -1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    v.x = expf(s * fminf(fmaxf(v.x, -kJExpClamp), kJExpClamp));
+    v.y = expf(s * fminf(fmaxf(v.y, -kJExpClamp), kJExpClamp));
+    v.z = expf(s * fminf(fmaxf(v.z, -kJExpClamp), kJExpClamp));
+    v.w = expf(s * fminf(fmaxf(v.w, -kJExpClamp), kJExpClamp));
+    reinterpret_cast<float4*>(e)[i] = v;
+  }
+}
+
+template <int kAct>
+__device__ __forceinline__ float joint_combine(float a, float b) {
+  if (kAct == CLASR_ACT_RELU) return fmaxf(a + b, 0.f);
+  const float r = __fdividef(1.f, fmaf(a, b, 1.f));  // MUFU.RCP; 0 for a*b >= 2^126 (saturated)
+  if (kAct == CLASR_ACT_SIGMOID) return r;
+  return fmaf(-2.f, r, 1.f);
 }
 
 __global__ void joint_tile_offsets_kernel(const int64_t* __restrict__ act_lens, const int64_t* __restrict__ label_lens,
@@ -104,7 +132,7 @@ __device__ __forceinline__ int find_utterance(const int* __restrict__ offs, int 
   return lo;
 }
 
-template <int kTerms, int kMode>
+template <int kTerms, int kMode, int kAct>
 __global__ void __launch_bounds__(kJThreads, 1)
 joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                  JointFwdParams p) {
@@ -113,82 +141,86 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   const int kblocks = p.H / kJK;
   uint8_t* a_smem = smem;                                          // [kblocks][128 x 64 bf16], SW128 K-major
-  uint8_t* staging = a_smem + kblocks * C::kABlockBytes;            // BF16X3 only
+  uint8_t* staging = a_smem + kblocks * C::kABlockBytes;            // BF16X3 only: 8 warps x [32 rows x 32 k] bf16
   uint8_t* b_ring = staging + C::kStagingBytes;                     // [stages][parts][BN x 64 bf16]
-  uint64_t* bars = (uint64_t*)(b_ring + kJStages * C::kBStageBytes);
+  uint8_t* rowtab = b_ring + kJStages * C::kBStageBytes;            // int2[4][32]
+  uint64_t* bars = (uint64_t*)(rowtab + C::kRowTabBytes);
   uint64_t* full = bars;                 // [kJStages]  W stage landed
   uint64_t* empty = full + kJStages;     // [kJStages]  W stage consumed
   uint64_t* tmem_full = empty + kJStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
   uint64_t* a_ready = tmem_empty + 2;       // [kblocks <= 10] A K-block written
-  uint64_t* a_free = a_ready + 10;          // [1] all MMAs of the tile retired -> A may be overwritten
-  uint32_t* tmem_base_slot = (uint32_t*)(a_free + 1);
+  uint64_t* a_free = a_ready + 10;          // [kblocks <= 10] last MMA reading A K-block retired
+  uint32_t* tmem_base_slot = (uint32_t*)(a_free + 10);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = tc::warp_idx_uniform();
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tile_offsets[p.B];
+  const int total_tiles = (int)tc::uniform_u32((uint32_t)p.tile_offsets[p.B]);
   const int n_tiles = (p.Vp + C::kBN - 1) / C::kBN;
   const int n_last = ((p.Vp - (n_tiles - 1) * C::kBN) + 15) / 16 * 16;  // width of the last N tile (multiple of 16)
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && tc::elect_one()) {
     tc::prefetch_tmap(&tmW_hi);
     if (kTerms > 1) tc::prefetch_tmap(&tmW_lo);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 1 && tc::elect_one()) {
     for (int i = 0; i < kJStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 4); }
-    for (int i = 0; i < 10; ++i) tc::mbar_init(&a_ready[i], kJProducerWarps);
-    tc::mbar_init(a_free, 1);
+    for (int i = 0; i < 10; ++i) { tc::mbar_init(&a_ready[i], kJProducerWarps); tc::mbar_init(&a_free[i], 1); }
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_base_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tmem_base = tc::uniform_u32(*tmem_base_slot);
 
   if (warp == 0) {
-    // ============================ TMA producer: W ring ============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int nt = 0; nt < n_tiles; ++nt) {
-          for (int kb = 0; kb < kblocks; ++kb) {
-            tc::mbar_wait(&empty[stage], phase ^ 1);
+    // ============================ TMA producer: W ring (whole warp loops, one elected lane issues) ===========
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int nt = 0; nt < n_tiles; ++nt) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          if (tc::elect_one()) {
             uint8_t* st = b_ring + stage * C::kBStageBytes;
             tc::mbar_expect_tx(&full[stage], C::kBStageBytes);
             tc::tma_load_2d(st, &tmW_hi, &full[stage], kb * kJK, nt * C::kBN);
             if (kTerms > 1) tc::tma_load_2d(st + C::kBN * kJK * 2, &tmW_lo, &full[stage], kb * kJK, nt * C::kBN);
-            if (++stage == kJStages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == kJStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    if (lane == 0) {
-      const uint32_t idesc_full = tc::make_idesc_bf16(kJM, C::kBN);
-      const uint32_t idesc_last = tc::make_idesc_bf16(kJM, n_last);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc_it = 0;
-      int tile_it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
-        const uint32_t tile_phase = tile_it & 1;
-        for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
-          const int acc = acc_it & 1;
-          const uint32_t acc_phase = (acc_it >> 1) & 1;
-          const uint32_t idesc = (nt == n_tiles - 1) ? idesc_last : idesc_full;
-          tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ============================ MMA issuer (whole warp loops, one elected lane issues) ======================
+    const uint32_t idesc_full = tc::make_idesc_bf16(kJM, C::kBN);
+    const uint32_t idesc_last = tc::make_idesc_bf16(kJM, n_last);
+    const uint32_t a_base = tc::smem_u32(a_smem);
+    const uint32_t b_base = tc::smem_u32(b_ring);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc_it = 0;
+    int tile_it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+      const uint32_t tile_phase = tile_it & 1;
+      for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
+        const int acc = acc_it & 1;
+        const uint32_t acc_phase = (acc_it >> 1) & 1;
+        const bool last_nt = nt == n_tiles - 1;
+        const uint32_t idesc = last_nt ? idesc_last : idesc_full;
+        tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * C::kBN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          if (nt == 0) tc::mbar_wait(&a_ready[kb], tile_phase);
+          tc::mbar_wait(&full[stage], phase);
           tc::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * C::kBN;
-          for (int kb = 0; kb < kblocks; ++kb) {
-            if (nt == 0) tc::mbar_wait(&a_ready[kb], tile_phase);
-            tc::mbar_wait(&full[stage], phase);
-            tc::tc_fence_after();
-            const uint32_t a_hi = tc::smem_u32(a_smem + kb * C::kABlockBytes);
-            const uint32_t b_hi = tc::smem_u32(b_ring + stage * C::kBStageBytes);
+          if (tc::elect_one()) {
+            const uint32_t a_hi = a_base + kb * C::kABlockBytes;
+            const uint32_t b_hi = b_base + stage * C::kBStageBytes;
             const uint32_t b_lo = b_hi + C::kBN * kJK * 2;
 #pragma unroll
             for (int kk = 0; kk < kJK / 16; ++kk) {
@@ -205,11 +237,15 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               }
             }
             tc::umma_commit(&empty[stage]);
-            if (++stage == kJStages) { stage = 0; phase ^= 1; }
+            // last N tile: this K block of A (smem hi + TMEM lo) is dead once these MMAs retire -> the producers
+            // may already write the next row tile's block while the remaining K blocks are still being consumed
+            if (last_nt) tc::umma_commit(&a_free[kb]);
           }
-          tc::umma_commit(&tmem_full[acc]);
+          __syncwarp();
+          if (++stage == kJStages) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(a_free);  // every MMA reading this tile's A has retired
+        if (tc::elect_one()) tc::umma_commit(&tmem_full[acc]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -334,87 +370,126 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     }
   } else if (warp >= 8) {
     // ============================ A producers: act(f + g) -> bf16 UMMA tiles ============================
+    // Warp pw owns the 32 rows [32q, 32q+32) of the tile (q = pw & 3: the TMEM lane quarter it may write) and the
+    // 32-wide K half `half = pw >> 2` of every 64-wide K block.  Compute mapping: half-warp hs handles one row at a
+    // time (16 lanes x 2 consecutive k = 128 contiguous bytes of ef / eg per row), 16 row pairs per K block.  The lo
+    // halves are transposed through a warp-private smem tile (no block-level barrier) into the warp's TMEM lanes.
     const int pw = warp - 8;
+    const int q = pw & 3, half = pw >> 2;
+    const int hs = lane >> 4, c = lane & 15;
+    const uint32_t a_base = tc::smem_u32(a_smem);
+    const uint32_t tab = tc::smem_u32(rowtab) + q * 256;
+    const uint32_t stg = tc::smem_u32(staging) + pw * 2048;
+    // hi: byte offset of (row = 32q + rl, k = 32*half + 2c) in the SW128 K-major block, rl = (i&3) + 8(i>>2) + 4hs
+    uint32_t aoff[4], soff[4];
+#pragma unroll
+    for (int mth = 0; mth < 4; ++mth) {
+      const int r7 = mth + 4 * hs;  // (row & 7)
+      aoff[mth] = (uint32_t)((q * 32 + 4 * hs) * 128 + (((half * 4 + (c >> 2)) ^ r7) * 16) + (c & 3) * 4);
+      // staging: physical row = rl ^ hs (rows rl, rl+4 of the two half-warps land in different bank halves),
+      // 16-byte chunk XORed with (rl >> 1) & 3 so that the row-per-lane read-back is conflict-free
+      soff[mth] = (uint32_t)((((mth ^ hs) + 4 * hs) * 64) + ((((c >> 2) ^ ((mth >> 1) | (hs << 1))) & 3) * 16) +
+                             (c & 3) * 4);
+    }
     int tile_it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
       const int b = find_utterance(p.tile_offsets, p.B, tile);
       const int Tb = (int)p.act_lens[b], Ub1 = (int)p.label_lens[b] + 1;
       const int r0 = (tile - p.tile_offsets[b]) * kJM;
       const int cells = Tb * Ub1;
-      // this warp's 16 rows: row = pw + 8*i ; (t,u) computed once per tile
-      const float* frow[kJM / kJProducerWarps];
-      const float* grow[kJM / kJProducerWarps];
-#pragma unroll
-      for (int i = 0; i < kJM / kJProducerWarps; ++i) {
-        const int r = r0 + pw + kJProducerWarps * i;
+      {  // row table: lane l <-> row 32q + l (both K-half warps of a quarter write identical values)
+        const int r = r0 + q * 32 + lane;
+        int fo = -1, go_ = -1;
         if (r < cells) {
           const int t = r / Ub1, u = r - t * Ub1;
-          frow[i] = p.f + ((int64_t)b * p.T + t) * p.H;
-          grow[i] = p.g + ((int64_t)b * p.U1 + u) * p.H;
-        } else {
-          frow[i] = nullptr;
-          grow[i] = nullptr;
+          fo = (b * p.T + t) * p.H;
+          go_ = (b * p.U1 + u) * p.H;
         }
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tab + lane * 8), "r"(fo), "r"(go_) : "memory");
       }
-      if (tile_it > 0) tc::mbar_wait(a_free, (tile_it - 1) & 1);  // previous tile's MMAs are done with A
-      tc::tc_fence_after();
-      for (int kb = 0; kb < kblocks; ++kb) {
-        uint8_t* ablk = a_smem + kb * C::kABlockBytes;
-        const int k = kb * kJK + 2 * lane;
+      __syncwarp();
+      float2 fa[8], ga[8], fb[8], gb[8];
+      uint32_t oka = 0, okb = 0;
+      auto load_batch = [&](int kb, int batch, float2 (&fo)[8], float2 (&go_)[8], uint32_t& ok) {
+        const int kcol = kb * kJK + half * 32 + 2 * c;
+        ok = 0;
 #pragma unroll
-        for (int i = 0; i < kJM / kJProducerWarps; ++i) {
-          const int row = pw + kJProducerWarps * i;
-          float h0 = 0.f, h1 = 0.f;
-          if (frow[i]) {
-            const float2 fv = __ldg(reinterpret_cast<const float2*>(frow[i] + k));
-            const float2 gv = __ldg(reinterpret_cast<const float2*>(grow[i] + k));
-            h0 = joint_act(fv.x + gv.x, p.activation);
-            h1 = joint_act(fv.y + gv.y, p.activation);
+        for (int j = 0; j < 8; ++j) {
+          const int i = batch * 8 + j;
+          const int rl = (i & 3) + 8 * (i >> 2) + 4 * hs;
+          const int2 o = tc::ld_shared_i2(tab + rl * 8);
+          if (o.x >= 0) {
+            fo[j] = __ldg(reinterpret_cast<const float2*>(p.ef + o.x + kcol));
+            go_[j] = __ldg(reinterpret_cast<const float2*>(p.eg + o.y + kcol));
+            ok |= 1u << j;
+          } else {  // padding row of the utterance's last tile: A row = 0
+            fo[j] = make_float2(0.f, 0.f);
+            go_[j] = make_float2(0.f, 0.f);
           }
-          __nv_bfloat16 hi0, lo0, hi1, lo1;
-          tc::split_bf16(h0, hi0, lo0);
-          tc::split_bf16(h1, hi1, lo1);
-          const uint32_t off = tc::sw128_offset(row, 2 * lane);
-          *reinterpret_cast<__nv_bfloat162*>(ablk + off) = __halves2bfloat162(hi0, hi1);
-          if (kTerms > 1) *reinterpret_cast<__nv_bfloat162*>(staging + off) = __halves2bfloat162(lo0, lo1);
+        }
+      };
+      auto compute_batch = [&](int kb, int batch, const float2 (&fi)[8], const float2 (&gi)[8], uint32_t okm) {
+        const uint32_t ablk = a_base + kb * C::kABlockBytes;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = batch * 8 + j;
+          const bool ok = (okm >> j) & 1u;
+          const float h0 = joint_combine<kAct>(fi[j].x, gi[j].x);
+          const float h1 = joint_combine<kAct>(fi[j].y, gi[j].y);
+          __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
+          __nv_bfloat162 ll = __floats2bfloat162_rn(h0 - __low2float(hh), h1 - __high2float(hh));
+          const uint32_t hw = ok ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
+          const uint32_t lw = ok ? *reinterpret_cast<uint32_t*>(&ll) : 0u;
+          const int rimm = (i & 3) + 8 * (i >> 2);  // compile-time part of the row index
+          tc::st_shared_u32(ablk + aoff[i & 3] + rimm * 128, hw);
+          if (kTerms > 1) tc::st_shared_u32(stg + soff[i & 3] + 8 * (i >> 2) * 64, lw);
           if (kMode == 1) {  // the dW GEMM consumes the hidden activations as an operand: keep a bf16 hi/lo copy
-            const int64_t go_ = ((int64_t)tile * kJM + row) * p.ldh;
-            *reinterpret_cast<__nv_bfloat162*>(p.hid_hi + go_ + k) = __halves2bfloat162(hi0, hi1);
-            if (kTerms > 1) *reinterpret_cast<__nv_bfloat162*>(p.hid_lo + go_ + k) = __halves2bfloat162(lo0, lo1);
-            if (kb == 0 && lane < 4) {  // columns [H, H+8): a column of ones (valid rows) then zeros
-              const float one = (frow[i] && lane == 0) ? 1.f : 0.f;
-              *reinterpret_cast<__nv_bfloat162*>(p.hid_hi + go_ + p.H + 2 * lane) =
-                  __halves2bfloat162(__float2bfloat16_rn(one), __float2bfloat16_rn(0.f));
-              if (kTerms > 1)
-                *reinterpret_cast<__nv_bfloat162*>(p.hid_lo + go_ + p.H + 2 * lane) =
-                    __halves2bfloat162(__float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f));
+            const int64_t go2 = ((int64_t)tile * kJM + q * 32 + rimm + 4 * hs) * p.ldh;
+            const int k = kb * kJK + half * 32 + 2 * c;
+            *reinterpret_cast<uint32_t*>(p.hid_hi + go2 + k) = hw;
+            if (kTerms > 1) *reinterpret_cast<uint32_t*>(p.hid_lo + go2 + k) = lw;
+            if (kb == 0 && half == 0 && c < 4) {  // columns [H, H+8): a column of ones (valid rows) then zeros
+              const uint32_t one = (ok && c == 0) ? 0x00003f80u : 0u;  // bf16(1.0) in the low half
+              *reinterpret_cast<uint32_t*>(p.hid_hi + go2 + p.H + 2 * c) = one;
+              if (kTerms > 1) *reinterpret_cast<uint32_t*>(p.hid_lo + go2 + p.H + 2 * c) = 0u;
             }
           }
         }
+      };
+      load_batch(0, 0, fa, ga, oka);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        load_batch(kb, 1, fb, gb, okb);
+        if (tile_it > 0) {  // the previous row tile's last MMAs on this K block have retired
+          tc::mbar_wait(&a_free[kb], (tile_it - 1) & 1);
+          tc::tc_fence_after();
+        }
+        compute_batch(kb, 0, fa, ga, oka);
+        if (kb + 1 < kblocks) load_batch(kb + 1, 0, fa, ga, oka);
+        compute_batch(kb, 1, fb, gb, okb);
         if (kTerms > 1) {
-          // staging (row-major, swizzled) -> tensor memory (lane = row): thread owns row q*32+lane, half of the block
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const int q = pw & 3, half = pw >> 2;
-          const int row = q * 32 + lane;
-          uint32_t v[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int chunk = (half * 4 + j) ^ (row & 7);
-            const uint4 x = *reinterpret_cast<const uint4*>(staging + row * 128 + chunk * 16);
-            v[4 * j + 0] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+          // warp-private staging (row-major, swizzled) -> tensor memory: lane l owns row 32q + l of the tile
+          __syncwarp();
+          const uint32_t rbase = stg + (uint32_t)((lane ^ ((lane >> 2) & 1)) * 64);
+          const int sw = (lane >> 1) & 3;
+          uint32_t v0[8], v1[8];
+          {
+            const uint4 x0 = tc::ld_shared_v4(rbase + ((0 ^ sw) * 16));
+            const uint4 x1 = tc::ld_shared_v4(rbase + ((1 ^ sw) * 16));
+            const uint4 x2 = tc::ld_shared_v4(rbase + ((2 ^ sw) * 16));
+            const uint4 x3 = tc::ld_shared_v4(rbase + ((3 ^ sw) * 16));
+            v0[0] = x0.x; v0[1] = x0.y; v0[2] = x0.z; v0[3] = x0.w;
+            v0[4] = x1.x; v0[5] = x1.y; v0[6] = x1.z; v0[7] = x1.w;
+            v1[0] = x2.x; v1[1] = x2.y; v1[2] = x2.z; v1[3] = x2.w;
+            v1[4] = x3.x; v1[5] = x3.y; v1[6] = x3.z; v1[7] = x3.w;
           }
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::kAloCol + kb * (kJK / 2) + half * 16;
-          uint32_t v0[8], v1[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { v0[j] = v[j]; v1[j] = v[8 + j]; }
           tc::tmem_st8(taddr, v0);
           tc::tmem_st8(taddr + 8, v1);
           tc::tmem_st_wait();
           tc::tc_fence_before();
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // staging may be overwritten by the next K block
         }
         tc::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the UMMA (async proxy) reads
-        __syncwarp();
+        __syncwarp();                  // also: staging reads done before the next K block's writes
         if (lane == 0) tc::mbar_arrive(&a_ready[kb]);
       }
     }
@@ -503,6 +578,8 @@ struct JointWs {
   void* w_hi;
   void* w_lo;
   int* tile_offsets;   // [B+1], then [1] rows_pad
+  float* ef;           // [B,T,H]  exp factor of f (tanh / sigmoid; relu reads f directly)
+  float* eg;           // [B,U1,H]
   int vp_pad;
   size_t total;
 };
@@ -550,8 +627,47 @@ static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, in
   j.w_lo = p + off; off += (precision == CLASR_PREC_BF16X3) ? wbytes : 0;
   j.tile_offsets = (int*)(p + off);
   off += ((size_t)(B + 2) * sizeof(int) + 255) / 256 * 256;
+  j.ef = (float*)(p + off);
+  off += ((size_t)B * T * H * sizeof(float) + 255) / 256 * 256;
+  j.eg = (float*)(p + off);
+  off += ((size_t)B * U1 * H * sizeof(float) + 255) / 256 * 256;
   j.total = off;
   return j;
+}
+
+template <int kTerms, int kMode>
+static int launch_joint_kernel(int activation, int H, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
+                               const JointFwdParams& p, cudaStream_t s) {
+  const int smem = JointCfg<kTerms>::smem_bytes(H);
+#define CLASR_LAUNCH_JOINT(ACT)                                                                                   \
+  do {                                                                                                            \
+    cudaFuncSetAttribute(joint_fwd_kernel<kTerms, kMode, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    joint_fwd_kernel<kTerms, kMode, ACT><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);                       \
+  } while (0)
+  if (activation == CLASR_ACT_RELU) CLASR_LAUNCH_JOINT(CLASR_ACT_RELU);
+  else if (activation == CLASR_ACT_SIGMOID) CLASR_LAUNCH_JOINT(CLASR_ACT_SIGMOID);
+  else CLASR_LAUNCH_JOINT(CLASR_ACT_TANH);
+#undef CLASR_LAUNCH_JOINT
+  return CLASR_STATUS_SUCCESS;
+}
+
+// exp factors of the activation (see joint_prep_kernel); relu needs none
+static int launch_joint_prep(const float* f, const float* g, int B, int T, int U1, int H, int activation,
+                             const JointWs& jw, const float** ef, const float** eg, cudaStream_t s) {
+  if (activation == CLASR_ACT_RELU) {
+    *ef = f;
+    *eg = g;
+    return CLASR_STATUS_SUCCESS;
+  }
+  const int64_t nf4 = (int64_t)B * T * H / 4, ng4 = (int64_t)B * U1 * H / 4;
+  auto grid = [](int64_t n4) { int64_t gsz = (n4 + 255) / 256; return (unsigned)(gsz < 1 ? 1 : (gsz > kNumSMs * 8 ? kNumSMs * 8 : gsz)); };
+  joint_prep_kernel<<<grid(nf4), 256, 0, s>>>(f, jw.ef, nf4, activation);
+  CLASR_CHECK_LAUNCH("joint_prep_f");
+  joint_prep_kernel<<<grid(ng4), 256, 0, s>>>(g, jw.eg, ng4, activation);
+  CLASR_CHECK_LAUNCH("joint_prep_g");
+  *ef = jw.ef;
+  *eg = jw.eg;
+  return CLASR_STATUS_SUCCESS;
 }
 
 }  // namespace clasr
@@ -578,7 +694,7 @@ static int check_joint_args(const char* who, const void* f, const void* g, const
                   precision);
   CLASR_CHECK_ARG(ws_bytes >= clasr_joint_workspace_bytes(B, T, U1, H, Vp, precision), "%s: workspace too small", who);
   CLASR_CHECK_ARG((((uintptr_t)ws) & 255) == 0, "%s: workspace must be 256-byte aligned", who);
-  CLASR_CHECK_ARG((((uintptr_t)f) & 7) == 0 && (((uintptr_t)g) & 7) == 0, "%s: f/g must be 8-byte aligned", who);
+  CLASR_CHECK_ARG((((uintptr_t)f) & 15) == 0 && (((uintptr_t)g) & 15) == 0, "%s: f/g must be 16-byte aligned", who);
   return CLASR_STATUS_SUCCESS;
 }
 
@@ -600,9 +716,10 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   CLASR_CHECK_LAUNCH("joint_tile_offsets");
 
   JointFwdParams p = {};
-  p.f = f; p.g = g; p.bias = b_out; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
+  if ((rc = launch_joint_prep(f, g, B, T, U1, H, activation, jw, &p.ef, &p.eg, s))) return rc;
+  p.bias = b_out; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
   p.tile_offsets = jw.tile_offsets;
-  p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank; p.activation = activation;
+  p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.sumsq = sumsq;
   CUtensorMap tw_hi, tw_lo;
@@ -614,15 +731,8 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
     tw_lo = tw_hi;
   }
   prof_begin("joint_fwd", s);
-  if (x3) {
-    const int smem = JointCfg<3>::smem_bytes(H);
-    cudaFuncSetAttribute(joint_fwd_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    joint_fwd_kernel<3, 0><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
-  } else {
-    const int smem = JointCfg<1>::smem_bytes(H);
-    cudaFuncSetAttribute(joint_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    joint_fwd_kernel<1, 0><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
-  }
+  if (x3) launch_joint_kernel<3, 0>(activation, H, tw_hi, tw_lo, p, s);
+  else launch_joint_kernel<1, 0>(activation, H, tw_hi, tw_lo, p, s);
   prof_end("joint_fwd", s);
   CLASR_CHECK_LAUNCH("joint_fwd");
   return launch_rnnt_lattice(p.w, act_lens, label_lens, B, T, U1, fastemit_lambda, costs, s);
@@ -657,9 +767,12 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
 
   // ---- pass 2a: recompute logits tile-wise, emit dZ (bf16 hi/lo) and the hidden activations as GEMM operands
   JointFwdParams p = {};
-  p.f = f; p.g = g; p.bias = b_out; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
+  // the exp factors were written into the workspace by the forward call (relu: f / g themselves)
+  p.ef = activation == CLASR_ACT_RELU ? f : jw.ef;
+  p.eg = activation == CLASR_ACT_RELU ? g : jw.eg;
+  p.bias = b_out; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
   p.tile_offsets = jw.tile_offsets;
-  p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank; p.activation = activation;
+  p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.grad_out = grad_out; p.fastemit_lambda = fastemit_lambda; p.clamp = clamp;
   p.dz_hi = (__nv_bfloat16*)sc.dz_hi; p.dz_lo = (__nv_bfloat16*)sc.dz_lo; p.ldz = sc.ldz;
@@ -674,15 +787,8 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
     tw_lo = tw_hi;
   }
   prof_begin("joint_bwd_dz", s);
-  if (x3) {
-    const int smem = JointCfg<3>::smem_bytes(H);
-    cudaFuncSetAttribute(joint_fwd_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    joint_fwd_kernel<3, 1><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
-  } else {
-    const int smem = JointCfg<1>::smem_bytes(H);
-    cudaFuncSetAttribute(joint_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    joint_fwd_kernel<1, 1><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);
-  }
+  if (x3) launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, p, s);
+  else launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, p, s);
   prof_end("joint_bwd_dz", s);
   CLASR_CHECK_LAUNCH("joint_bwd_dz");
 

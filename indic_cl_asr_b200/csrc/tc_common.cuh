@@ -21,6 +21,27 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Warp index as a value the compiler can prove warp-uniform (shfl broadcast): role dispatch on it is branch-
+// divergence-free, and tcgen05 / TMA instructions issued under elect_one() inside such a region get their
+// operands in uniform registers directly (issued from an `if (lane == 0)` region instead, every UTCHMMA is wrapped
+// in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop costing ~80 cycles: profiles/r01a_ncu_joint_fwd_first_fused.md).
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ int2 ld_shared_i2(uint32_t addr) {
+  int2 r;
+  asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+  return r;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
