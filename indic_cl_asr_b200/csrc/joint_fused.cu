@@ -53,6 +53,7 @@ struct JointFwdParams {
   const float* ef;     // [B,T,H]   activation factor of f (relu: f itself; tanh: exp(2f); sigmoid: exp(-f))
   const float* eg;     // [B,U1,H]  same for g
   const float* bias;   // [Vp]
+  const float* bias_pad;  // [round_up(Vp, 32) + 32] zero-padded copy of bias (vector loads in the pass-2 epilogue)
   const int64_t* labels;
   const int64_t* act_lens;
   const int64_t* label_lens;
@@ -109,7 +110,10 @@ __device__ __forceinline__ float joint_combine(float a, float b) {
 }
 
 __global__ void joint_tile_offsets_kernel(const int64_t* __restrict__ act_lens, const int64_t* __restrict__ label_lens,
-                                          int B, int* __restrict__ tile_offsets, int* __restrict__ rows_pad_dev) {
+                                          int B, int* __restrict__ tile_offsets, int* __restrict__ rows_pad_dev,
+                                          const float* __restrict__ bias, int Vp, float* __restrict__ bias_pad) {
+  const int n_pad = (Vp + 31) / 32 * 32 + 32;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) bias_pad[i] = i < Vp ? bias[i] : 0.f;
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int acc = 0;
     tile_offsets[0] = 0;
@@ -266,20 +270,23 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       const int label = (valid && u < Ub1 - 1) ? (int)p.labels[(int64_t)b * (p.U1 - 1) + u] : -1;
       const int64_t idx = ((int64_t)b * p.w.ND + t + u) * p.U1 + u;
       float m = -INFINITY, s = 0.f, zb = 0.f, zl = 0.f, ssq = 0.f;
-      // pass-2 per-row scalars (same algebra as rnnt_grad_kernel, gpu_rnnt_kernel.py:351-396)
-      float base = 0.f, fe_base = 0.f, blank_sub = 0.f, label_sub = 0.f, go = 0.f, dn = 0.f;
-      bool fe = false;
+      // pass-2 per-row scalars (same algebra as rnnt_grad_kernel, gpu_rnnt_kernel.py:351-396), exponents pre-scaled
+      // by log2(e) so that each logit costs one FFMA + one MUFU.EX2.  Padding rows: base2 = -inf, go = 0 -> dZ = 0.
+      constexpr float kLog2e = 1.4426950408889634f;
+      float base2 = -INFINITY, fe_base2 = -INFINITY, fe_coef = 0.f, blank_sub = 0.f, label_sub = 0.f, go = 0.f;
       if (kMode == 1 && valid) {
         const double a = p.w.alpha[idx], bt = p.w.beta[idx], ll = p.w.ll_fwd[b];
-        dn = p.w.denom[idx];
+        const float dn = p.w.denom[idx];
         const float2 lpair = p.w.lp[idx];
         go = p.grad_out ? p.grad_out[b] : 1.f;
         const bool has_label = u < Ub1 - 1;
         const double beta_t1 = (t < Tb - 1) ? p.w.beta[idx + p.U1] : 0.0;
         const double beta_u1 = has_label ? p.w.beta[idx + p.U1 + 1] : 0.0;
-        base = (float)(a + bt - ll) + dn;
-        fe = p.fastemit_lambda > 0.f && has_label;
-        fe_base = fe ? (float)(a + beta_u1 - ll + (double)lpair.y) + dn : 0.f;
+        base2 = ((float)(a + bt - ll) + dn) * kLog2e;
+        if (p.fastemit_lambda > 0.f && has_label) {
+          fe_coef = p.fastemit_lambda;
+          fe_base2 = ((float)(a + beta_u1 - ll + (double)lpair.y) + dn) * kLog2e;
+        }
         if (t == Tb - 1 && u == Ub1 - 1) blank_sub += expf((float)(a - ll + (double)lpair.x));
         if (t < Tb - 1) blank_sub += expf((float)(a + beta_t1 - ll + (double)lpair.x));
         label_sub = has_label ? expf(log1pf(p.fastemit_lambda) + (float)(a + beta_u1 - ll + (double)lpair.y)) : 0.f;
@@ -319,6 +326,46 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) s += __expf(z[j] - m);
           } else {
+            // branch-free per element; every special case is a warp-uniform branch around a whole 32-column chunk
+            float gr[32];
+            const float4* bias4 = reinterpret_cast<const float4*>(p.bias_pad + col0);  // zero-padded copy
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bv = __ldg(bias4 + j4);
+              gr[4 * j4 + 0] = __uint_as_float(rr[4 * j4 + 0]) + bv.x;
+              gr[4 * j4 + 1] = __uint_as_float(rr[4 * j4 + 1]) + bv.y;
+              gr[4 * j4 + 2] = __uint_as_float(rr[4 * j4 + 2]) + bv.z;
+              gr[4 * j4 + 3] = __uint_as_float(rr[4 * j4 + 3]) + bv.w;
+            }
+            if (p.fastemit_lambda > 0.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                gr[j] = fmaf(fe_coef, tc::ex2_approx(fmaf(gr[j], kLog2e, fe_base2)),
+                             tc::ex2_approx(fmaf(gr[j], kLog2e, base2)));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) gr[j] = tc::ex2_approx(fmaf(gr[j], kLog2e, base2));
+            }
+            if (col0 + 32 > p.Vp) {  // padded tail columns of the operand
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j >= p.Vp) gr[j] = 0.f;
+            }
+            if (p.blank >= col0 && p.blank < col0 + 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j == p.blank) gr[j] -= blank_sub;
+            }
+            if (__any_sync(0xffffffffu, label >= col0 && label < col0 + 32)) {
+              const int jl = label - col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j == jl) gr[j] -= label_sub;
+            }
+            if (p.clamp > 0.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) gr[j] = fmaxf(fminf(gr[j], p.clamp), -p.clamp);
+            }
             __nv_bfloat16* dh = p.dz_hi + grow * p.ldz + col0;
             __nv_bfloat16* dl = p.dz_lo + grow * p.ldz + col0;
 #pragma unroll
@@ -326,30 +373,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               if (col0 + j8 < p.ldz) {  // ldz is a multiple of 8: whole 16-byte groups
                 uint32_t ph[4], pl[4];
 #pragma unroll
-                for (int j2 = 0; j2 < 8; j2 += 2) {
-                  float gv[2];
-#pragma unroll
-                  for (int e = 0; e < 2; ++e) {
-                    const int j = j8 + j2 + e;
-                    const int col = col0 + j;
-                    float gr = 0.f;
-                    if (valid && col < p.Vp) {
-                      const float z = __uint_as_float(rr[j]) + __ldg(p.bias + col);
-                      gr = expf(z + base);
-                      if (fe) gr += p.fastemit_lambda * expf(z + fe_base);
-                      if (col == p.blank) gr -= blank_sub;
-                      if (col == label) gr -= label_sub;
-                      if (p.clamp > 0.f) gr = fmaxf(fminf(gr, p.clamp), -p.clamp);
-                      gr *= go;
-                    }
-                    gv[e] = gr;
-                  }
-                  __nv_bfloat16 h0, l0, h1, l1;
-                  tc::split_bf16(gv[0], h0, l0);
-                  tc::split_bf16(gv[1], h1, l1);
-                  __nv_bfloat162 hh = __halves2bfloat162(h0, h1), llo = __halves2bfloat162(l0, l1);
-                  ph[j2 >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-                  pl[j2 >> 1] = *reinterpret_cast<uint32_t*>(&llo);
+                for (int j2 = 0; j2 < 4; ++j2) {
+                  const float g0 = gr[j8 + 2 * j2] * go, g1 = gr[j8 + 2 * j2 + 1] * go;
+                  __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
+                  __nv_bfloat162 ll = __floats2bfloat162_rn(g0 - __low2float(hh), g1 - __high2float(hh));
+                  ph[j2] = *reinterpret_cast<uint32_t*>(&hh);
+                  pl[j2] = *reinterpret_cast<uint32_t*>(&ll);
                 }
                 *reinterpret_cast<uint4*>(dh + j8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                 if (kTerms > 1) *reinterpret_cast<uint4*>(dl + j8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -578,6 +607,7 @@ struct JointWs {
   void* w_hi;
   void* w_lo;
   int* tile_offsets;   // [B+1], then [1] rows_pad
+  float* bias_pad;     // [round_up(Vp,32)+32]
   float* ef;           // [B,T,H]  exp factor of f (tanh / sigmoid; relu reads f directly)
   float* eg;           // [B,U1,H]
   int vp_pad;
@@ -627,6 +657,8 @@ static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, in
   j.w_lo = p + off; off += (precision == CLASR_PREC_BF16X3) ? wbytes : 0;
   j.tile_offsets = (int*)(p + off);
   off += ((size_t)(B + 2) * sizeof(int) + 255) / 256 * 256;
+  j.bias_pad = (float*)(p + off);
+  off += ((size_t)((Vp + 31) / 32 * 32 + 32) * sizeof(float) + 255) / 256 * 256;
   j.ef = (float*)(p + off);
   off += ((size_t)B * T * H * sizeof(float) + 255) / 256 * 256;
   j.eg = (float*)(p + off);
@@ -712,12 +744,13 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   const bool x3 = precision == CLASR_PREC_BF16X3;
   // W_out [Vp,H] fp32 -> bf16 hi[,lo] (rows beyond Vp are never read: TMA zero-fills out-of-bounds rows)
   if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s))) return rc;
-  joint_tile_offsets_kernel<<<1, 32, 0, s>>>(act_lens, label_lens, B, jw.tile_offsets, jw.tile_offsets + B + 1);
+  joint_tile_offsets_kernel<<<1, 256, 0, s>>>(act_lens, label_lens, B, jw.tile_offsets, jw.tile_offsets + B + 1,
+                                              b_out, Vp, jw.bias_pad);
   CLASR_CHECK_LAUNCH("joint_tile_offsets");
 
   JointFwdParams p = {};
   if ((rc = launch_joint_prep(f, g, B, T, U1, H, activation, jw, &p.ef, &p.eg, s))) return rc;
-  p.bias = b_out; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
+  p.bias = b_out; p.bias_pad = jw.bias_pad; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
   p.tile_offsets = jw.tile_offsets;
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
@@ -770,7 +803,7 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
   // the exp factors were written into the workspace by the forward call (relu: f / g themselves)
   p.ef = activation == CLASR_ACT_RELU ? f : jw.ef;
   p.eg = activation == CLASR_ACT_RELU ? g : jw.eg;
-  p.bias = b_out; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
+  p.bias = b_out; p.bias_pad = jw.bias_pad; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
   p.tile_offsets = jw.tile_offsets;
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
