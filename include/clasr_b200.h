@@ -181,6 +181,17 @@ CLASR_API int clasr_gemm_nt(const float* A, const float* B, float* C, int M, int
 CLASR_API int clasr_gemm_ex(const float* A, const float* B, float* C, int M, int N, int K, int a_trans, int b_trans,
                             int k_splits, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Linear layer on the tcgen05 GEMM: y[M,N] = x[M,K] . w[N,K]^T + bias[N]  (bias may be NULL), and its backward
+ *   dx[M,K] = dy . w,  dw[N,K] = dy^T . x,  db[N] = column sums of dy   (each output may be NULL).
+ * Replaces nn.Linear for the joint's enc / pred projections (modules/rnnt.py:1563-1585, built :1679-1680) and the
+ * kernel-size-1 Conv1d of the CTC head (modules/conv_asr.py:444-446, 467-469).  The backward call reuses the
+ * operand splits the forward call left in the same workspace. */
+CLASR_API size_t clasr_linear_workspace_bytes(int M, int N, int K, int precision);
+CLASR_API int clasr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
+                               int precision, void* workspace, size_t workspace_bytes, void* stream);
+CLASR_API int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db, int M, int N, int K, int precision,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * 4. Fused joint + transducer loss — replaces the fused branch of RNNTJoint.forward
  *    (modules/rnnt.py:1403-1561): joint_after_projection (:1587-1665) + RNNTLoss, without ever

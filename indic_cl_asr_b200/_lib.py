@@ -51,6 +51,9 @@ _PROTOS: Dict[str, Tuple[object, List[object]]] = {
     "clasr_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "clasr_gemm_nt": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "clasr_gemm_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "clasr_linear_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "clasr_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "clasr_linear_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "clasr_joint_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "clasr_joint_rnnt_fwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, _vp, _vp, _vp, _sz, _vp]),
     "clasr_joint_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),

@@ -105,6 +105,7 @@ struct GemmParams {
   int b_mn;        // 0: B given as [N,K] (K contiguous) ; 1: B given as [K,N] (N contiguous)
   const int* m_dev;  // optional device-side M (<= M): lets a ragged row count stay on the device (no host sync)
   const int* k_dev;  // optional device-side K (<= K)
+  const float* bias; // optional [N]: C = acc + bias[n] (non-atomic epilogue only)
 };
 
 template <int kTerms>
@@ -267,11 +268,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int j = 0; j < 32; j += 4) {
               float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                      __uint_as_float(r[j + 3]));
+              if (p.bias) {
+                v.x += __ldg(p.bias + col0 + j);     v.y += __ldg(p.bias + col0 + j + 1);
+                v.z += __ldg(p.bias + col0 + j + 2); v.w += __ldg(p.bias + col0 + j + 3);
+              }
               *reinterpret_cast<float4*>(crow + col0 + j) = v;
             }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]);
+              if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
           }
         }
       }
@@ -294,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // lda / ldb in elements (multiples of 8).  k_splits > 1 requires atomic_add and a zero-initialised C.
 int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
                    int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
-                   int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev) {
+                   int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias) {
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   const bool x3 = precision == CLASR_PREC_BF16X3;
@@ -320,7 +325,7 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
     set_error("gemm_tc: split-K needs atomic accumulation");
     return CLASR_STATUS_INVALID_VALUE;
   }
-  GemmParams p{M, N, K, C, ldc, atomic_add, k_splits, a_mn, b_mn, m_dev, k_dev};
+  GemmParams p{M, N, K, C, ldc, atomic_add, k_splits, a_mn, b_mn, m_dev, k_dev, atomic_add ? nullptr : bias};
   const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN) * k_splits;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (x3) {
@@ -375,10 +380,128 @@ extern "C" int clasr_gemm_ex(const float* A, const float* B, float* C, int M, in
     CLASR_CHECK_ARG(e == cudaSuccess, "gemm: memset failed");
   }
   return launch_gemm_tc(a_hi, a_lo, pad8(a_cols), a_trans, b_hi, b_lo, pad8(b_cols), b_trans, M, N, K, C, N, precision,
-                        k_splits > 1, k_splits, s, nullptr, nullptr);
+                        k_splits > 1, k_splits, s, nullptr, nullptr, nullptr);
 }
 
 extern "C" int clasr_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int precision,
                              void* workspace, size_t workspace_bytes, void* stream) {
   return clasr_gemm_ex(A, B, C, M, N, K, 0, 0, 1, precision, workspace, workspace_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Linear layer y = x . W^T + b and its backward on the tcgen05 GEMM (bf16 hi/lo split, fp32-grade results).
+// Replaces nn.Linear for the joint's enc / pred projections (reference modules/rnnt.py:1563-1585, 1679-1680) and
+// the k=1 Conv1d of the CTC head (modules/conv_asr.py:444-446, 467-469), which torch runs as SIMT sgemm / cuDNN
+// convolutions when TF32 is off.
+// ------------------------------------------------------------------------------------------------
+namespace clasr {
+__global__ void colsum_kernel(const float* __restrict__ dy, int64_t M, int N, int64_t rows_per_block,
+                              float* __restrict__ db) {
+  // block = 32 columns x 8 row lanes; grid = (ceil(N/32), row slices)
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float acc = 0.f;
+  if (col < N)
+    for (int64_t r = r0 + ry; r < r1; r += 8) acc += dy[r * N + col];
+  __shared__ float sm[8][33];
+  sm[ry][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ry == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
+    atomicAdd(db + col, t);
+  }
+}
+}  // namespace clasr
+
+static size_t linear_ws_bytes(int M, int N, int K, int precision) {
+  // operands of the three GEMMs are split one pair at a time: max over (x,w), (dy,w), (dy,x)
+  const size_t parts = precision == CLASR_PREC_BF16X3 ? 2 : 1;
+  auto sz = [&](int64_t r, int64_t c) { return ((size_t)pad8((int)r) * pad8((int)c) * 2 + 255) / 256 * 256; };
+  const size_t x = sz(M, K), w = sz(N, K), dy = sz(M, N);
+  return parts * (x + w + dy);
+}
+
+extern "C" size_t clasr_linear_workspace_bytes(int M, int N, int K, int precision) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return linear_ws_bytes(M, N, K, precision);
+}
+
+struct LinearWs { void *x_hi, *x_lo, *w_hi, *w_lo, *dy_hi, *dy_lo; };
+static LinearWs linear_ws_carve(void* base, int M, int N, int K, int precision) {
+  const bool x3 = precision == CLASR_PREC_BF16X3;
+  auto sz = [&](int64_t r, int64_t c) { return ((size_t)pad8((int)r) * pad8((int)c) * 2 + 255) / 256 * 256; };
+  char* p = (char*)base;
+  LinearWs w;
+  w.x_hi = p; p += sz(M, K); w.x_lo = x3 ? p : nullptr; if (x3) p += sz(M, K);
+  w.w_hi = p; p += sz(N, K); w.w_lo = x3 ? p : nullptr; if (x3) p += sz(N, K);
+  w.dy_hi = p; p += sz(M, N); w.dy_lo = x3 ? p : nullptr;
+  return w;
+}
+
+extern "C" int clasr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
+                                int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  CLASR_CHECK_ARG(x && w && y && workspace, "linear_fwd: null pointer");
+  CLASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear_fwd: non-positive dimension");
+  CLASR_CHECK_ARG(precision == CLASR_PREC_BF16 || precision == CLASR_PREC_BF16X3, "linear_fwd: bad precision");
+  CLASR_CHECK_ARG(workspace_bytes >= linear_ws_bytes(M, N, K, precision), "linear_fwd: workspace too small");
+  CLASR_CHECK_ARG((((uintptr_t)workspace) & 255) == 0, "linear_fwd: workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  LinearWs ws = linear_ws_carve(workspace, M, N, K, precision);
+  int rc;
+  if ((rc = launch_split_bf16(x, M, K, K, ws.x_hi, ws.x_lo, pad8(K), s))) return rc;
+  if ((rc = launch_split_bf16(w, N, K, K, ws.w_hi, ws.w_lo, pad8(K), s))) return rc;
+  prof_begin("linear_fwd", s);
+  rc = launch_gemm_tc(ws.x_hi, ws.x_lo, pad8(K), 0, ws.w_hi, ws.w_lo, pad8(K), 0, M, N, K, y, N, precision, 0, 1, s,
+                      nullptr, nullptr, bias);
+  prof_end("linear_fwd", s);
+  return rc;
+}
+
+// dx [M,K] = dy . W ; dw [N,K] = dy^T . x ; db [N] = column sums of dy.  Any of dx / dw / db may be NULL.
+// The workspace must be the one clasr_linear_fwd filled (x and w splits are reused).
+extern "C" int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db, int M, int N, int K, int precision,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  CLASR_CHECK_ARG(dy && workspace, "linear_bwd: null pointer");
+  CLASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear_bwd: non-positive dimension");
+  CLASR_CHECK_ARG(precision == CLASR_PREC_BF16 || precision == CLASR_PREC_BF16X3, "linear_bwd: bad precision");
+  CLASR_CHECK_ARG(workspace_bytes >= linear_ws_bytes(M, N, K, precision), "linear_bwd: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  LinearWs ws = linear_ws_carve(workspace, M, N, K, precision);
+  int rc;
+  if (dx || dw)
+    if ((rc = launch_split_bf16(dy, M, N, N, ws.dy_hi, ws.dy_lo, pad8(N), s))) return rc;
+  prof_begin("linear_bwd", s);
+  if (dx) {  // A = dy [M, N] K-major (K_gemm = N); B = W given as [K_gemm = N rows, N_gemm = K cols] (MN-major)
+    if ((rc = launch_gemm_tc(ws.dy_hi, ws.dy_lo, pad8(N), 0, ws.w_hi, ws.w_lo, pad8(K), 1, M, K, N, dx, K, precision, 0, 1,
+                             s, nullptr, nullptr, nullptr)))
+      return rc;
+  }
+  if (dw) {  // A = dy given as [K_gemm = M rows, M_gemm = N cols]; B = x given as [K_gemm = M rows, N_gemm = K cols]
+    const int mn_tiles = ((N + 127) / 128) * ((K + 255) / 256);
+    int splits = (kNumSMs + mn_tiles - 1) / mn_tiles;
+    const int kb_total = (M + 63) / 64;
+    if (splits > kb_total) splits = kb_total;
+    if (splits < 1) splits = 1;
+    if (splits > 1) {
+      cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), s);
+      CLASR_CHECK_ARG(e == cudaSuccess, "linear_bwd: memset failed");
+    }
+    if ((rc = launch_gemm_tc(ws.dy_hi, ws.dy_lo, pad8(N), 1, ws.x_hi, ws.x_lo, pad8(K), 1, N, K, M, dw, K, precision,
+                             splits > 1, splits, s, nullptr, nullptr, nullptr)))
+      return rc;
+  }
+  if (db) {
+    cudaError_t e = cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), s);
+    CLASR_CHECK_ARG(e == cudaSuccess, "linear_bwd: memset failed");
+    const int64_t rows_per_block = 256;
+    dim3 grid((N + 31) / 32, (unsigned)((M + rows_per_block - 1) / rows_per_block));
+    colsum_kernel<<<grid, 256, 0, s>>>(dy, M, N, rows_per_block, db);
+    CLASR_CHECK_LAUNCH("linear_colsum");
+  }
+  prof_end("linear_bwd", s);
+  return CLASR_STATUS_SUCCESS;
 }

@@ -597,7 +597,7 @@ __global__ void joint_dw_finish_kernel(const float* __restrict__ dw_ext, int Vp,
 
 int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
                    int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
-                   int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev);
+                   int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias = nullptr);
 
 // ------------------------------------------------------------------------------------------------
 // workspace layout of the fused path

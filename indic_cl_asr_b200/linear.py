@@ -1,0 +1,60 @@
+"""Linear layer y = x W^T + b on the tcgen05 GEMM (C ABI: clasr_linear_fwd / clasr_linear_bwd).
+
+Used for the joint's enc / pred projections (reference NeMo modules/rnnt.py:1563-1585; layers built :1679-1680) and
+for the kernel-size-1 Conv1d of the CTC head (modules/conv_asr.py:444-446, 467-469).  Operands are split into bf16
+hi + lo and multiplied as hi.hi + hi.lo + lo.hi with fp32 accumulation in tensor memory ("bf16x3": ~2^-17 relative
+per product, fp32-grade) — with TF32 disabled, torch runs the same layers as SIMT sgemm / cuDNN convolutions.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+__all__ = ["linear_x3"]
+
+
+class _LinearX3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, precision):
+        _lib.require_cuda(x, "x")
+        lead = x.shape[:-1]
+        K = x.shape[-1]
+        N = weight.shape[0]
+        if weight.shape[1] != K:
+            raise ValueError(f"linear: weight {tuple(weight.shape)} does not match input features {K}")
+        x2 = x.reshape(-1, K).contiguous().float()
+        w = weight.contiguous().float()
+        b = None if bias is None else bias.contiguous().float()
+        M = x2.shape[0]
+        prec = _lib.PREC[precision]
+        L = _lib.lib()
+        nbytes = L.clasr_linear_workspace_bytes(M, N, K, prec)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.clasr_linear_fwd(x2.data_ptr(), w.data_ptr(), _lib.ptr(b), y.data_ptr(), M, N, K, prec,
+                                          ws.data_ptr(), nbytes, _lib.stream_ptr(x.device)), "linear_fwd")
+        ctx.save_for_backward(ws)
+        ctx.dims = (M, N, K, prec, nbytes, tuple(x.shape), bias is not None)
+        return y.view(*lead, N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ws,) = ctx.saved_tensors
+        M, N, K, prec, nbytes, xshape, has_bias = ctx.dims
+        dy2 = dy.reshape(M, N).contiguous().float()
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
+        dx = torch.empty(M, K, dtype=torch.float32, device=dy.device) if need_x else None
+        dw = torch.empty(N, K, dtype=torch.float32, device=dy.device) if need_w else None
+        db = torch.empty(N, dtype=torch.float32, device=dy.device) if need_b else None
+        L = _lib.lib()
+        with torch.cuda.device(dy.device):
+            _lib.check(L.clasr_linear_bwd(dy2.data_ptr(), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), M, N, K, prec,
+                                          ws.data_ptr(), nbytes, _lib.stream_ptr(dy.device)), "linear_bwd")
+        return (dx.view(xshape) if need_x else None), dw, db, None
+
+
+def linear_x3(x: torch.Tensor, weight: torch.Tensor, bias=None, precision: str = "bf16x3") -> torch.Tensor:
+    """``torch.nn.functional.linear(x, weight, bias)`` on the tcgen05 tensor cores (CUDA tensors only)."""
+    return _LinearX3.apply(x, weight, bias, precision)

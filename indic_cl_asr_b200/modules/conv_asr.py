@@ -98,17 +98,29 @@ class ConvASRDecoder(torch.nn.Module):
 
     @kwargs_only
     def forward(self, encoder_output, language_ids=None):
-        out = self.decoder_layers(encoder_output).transpose(1, 2)  # [B,T,C]
-        if self.temperature != 1.0:
-            out = out / self.temperature
-        if language_ids is not None:
-            if len(set(language_ids)) == 1:
-                out = out.index_select(-1, self._columns(language_ids[0], out.device))
-            else:  # mixed-language batch: per-sample select (all languages have equal width)
+        """Conv1d(k=1) -> per-language column select -> log_softmax (reference modules/conv_asr.py:458-490).
+
+        A kernel-size-1 convolution over [B,D,T] is the GEMM [B*T,D] x [C,D]^T: it runs on the tcgen05 GEMM
+        (``linear_x3``) and lands directly in the [B,T,C] layout the reference reaches by transposing.  With one
+        language per batch (what the drivers pass, cl_baseline_ewc.py:225) only that language's rows of the weight
+        are multiplied (device-resident column index instead of the reference's per-call host-built bool mask and
+        the [B,T,n_lang*256+1] intermediate, conv_asr.py:471-484); gradients scatter back into the full weight."""
+        from ..linear import linear_x3
+        if not encoder_output.is_cuda:
+            raise RuntimeError("ConvASRDecoder: CUDA tensors only (no CPU path in indic_cl_asr_b200)")
+        conv = self.decoder_layers[0]
+        weight, bias = conv.weight.squeeze(-1), conv.bias  # [C,D], [C]
+        x = encoder_output.transpose(1, 2)                   # [B,T,D]
+        if language_ids is not None and len(set(language_ids)) == 1:
+            cols = self._columns(language_ids[0], x.device)
+            out = linear_x3(x, weight.index_select(0, cols), bias.index_select(0, cols))
+        else:
+            out = linear_x3(x, weight, bias)
+            if language_ids is not None:  # mixed-language batch: per-sample select (all languages have equal width)
                 out = torch.stack([o.index_select(-1, self._columns(l, out.device))
                                    for o, l in zip(out, language_ids)])
+        if self.temperature != 1.0:
+            out = out / self.temperature
         if self.return_logits_:
             self.decoder_logits = out.clone()
-        if not out.is_cuda:
-            raise RuntimeError("ConvASRDecoder: CUDA tensors only (no CPU path in indic_cl_asr_b200)")
         return log_softmax_rows(out)

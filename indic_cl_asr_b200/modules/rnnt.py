@@ -166,11 +166,22 @@ class RNNTJoint(torch.nn.Module):
         self._fused_batch_size = fused_batch_size
 
     # ------------------------------------------------------------------ joint maths (:1563-1665)
+    def _project(self, lin: torch.nn.Linear, x: torch.Tensor) -> torch.Tensor:
+        """enc / pred Linear (reference modules/rnnt.py:1563-1585); parameters stay ``enc.*`` / ``pred.*``.
+
+        tanh / sigmoid joints run the projection on the tcgen05 GEMM (bf16 hi+lo split, ~2^-17 relative per product).
+        A ReLU joint keeps torch's true-fp32 GEMM: the pre-activation feeds a kink, and a 1e-5 perturbation of
+        f+g flips relu' for ~80x more elements than fp32 rounding does, which alone costs 3e-4 of gradient parity."""
+        if x.is_cuda and str(self.activation).lower() != "relu":
+            from ..linear import linear_x3
+            return linear_x3(x, lin.weight, lin.bias, self.precision)
+        return lin(x)
+
     def project_encoder(self, encoder_output: torch.Tensor) -> torch.Tensor:
-        return self.enc(encoder_output)
+        return self._project(self.enc, encoder_output)
 
     def project_prednet(self, prednet_output: torch.Tensor) -> torch.Tensor:
-        return self.pred(prednet_output)
+        return self._project(self.pred, prednet_output)
 
     def joint(self, f: torch.Tensor, g: torch.Tensor, language_ids=None) -> torch.Tensor:
         return self.joint_after_projection(self.project_encoder(f), self.project_prednet(g), language_ids)
@@ -335,7 +346,7 @@ class RNNTJoint(torch.nn.Module):
         from ..fused import fused_joint_rnnt_loss
 
         lin = self._final_linear(language_ids)
-        f = self.project_encoder(enc)   # [B,T,H]  (small cuBLAS GEMM)
+        f = self.project_encoder(enc)   # [B,T,H]  (tcgen05 GEMM)
         g = self.project_prednet(dec)   # [B,U1,H]
         loss_mod = self.loss
         per_sample = fused_joint_rnnt_loss(
