@@ -15,6 +15,7 @@
 //   warps 4-7 epilogue     tcgen05.ld (32 lanes x 32 columns) -> 128-byte row segments -> global
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace clasr {
 
@@ -293,6 +294,219 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a 2-CTA cluster computes a 256 x 256 tile; each CTA loads its own 128 rows of A
+// and HALF of the B tile (128 of the 256 N) — half the L2->smem traffic for B per CTA and half its smem footprint,
+// i.e. the arithmetic intensity of a 256 x 256 tile at the smem cost of 128 x 128.  The 1-CTA kernel above moves
+// 64 B/clk/SM at full MMA rate in BF16X3 (measured: L2-bound at ~10.8 TB/s); this one 42.7 B/clk/SM.
+// ------------------------------------------------------------------------------------------------
+template <int kTerms>
+struct Gemm2Smem {
+  static constexpr int kParts = kTerms == 1 ? 1 : 2;
+  static constexpr int kABytes = kBM * kBK * 2;          // own 128 rows of A: 16 KB
+  static constexpr int kBBytes = (kBN / 2) * kBK * 2;    // half of B: 16 KB
+  static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
+  static constexpr int kStages = kTerms == 1 ? 6 : 3;
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static constexpr int kTotalBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int kTerms>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, GemmParams p) {
+  using S = Gemm2Smem<kTerms>;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + S::kRingBytes);
+  uint64_t* full = bars;                            // [kStages]  (the leader's copy is the one in use)
+  uint64_t* empty = bars + S::kStages;              // [kStages]  per CTA: both ring slots of the pair consumed
+  uint64_t* tmem_full = bars + 2 * S::kStages;      // [2]  per CTA
+  uint64_t* tmem_empty = bars + 2 * S::kStages + 2; // [2]  leader's copy: 8 epilogue warps of the pair
+  uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * S::kStages + 4);
+
+  const int warp = tc::warp_idx_uniform();
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = tc::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int Mdyn = (int)tc::uniform_u32((uint32_t)(p.m_dev ? min(p.M, *p.m_dev) : p.M));
+  const int Kdyn = (int)tc::uniform_u32((uint32_t)(p.k_dev ? min(p.K, *p.k_dev) : p.K));
+  constexpr int kPM = 2 * kBM;  // rows per pair tile
+  const int m_tiles = (Mdyn + kPM - 1) / kPM;
+  const int n_tiles = (p.N + kBN - 1) / kBN;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int kb_total = (Kdyn + kBK - 1) / kBK;
+  const int kb_per_split = max(1, (kb_total + p.k_splits - 1) / p.k_splits);
+  const int k_splits = max(1, (kb_total + kb_per_split - 1) / kb_per_split);
+  const int num_tiles = mn_tiles * k_splits;
+
+  if (warp == 0 && tc::elect_one()) {
+    tc::prefetch_tmap(&tmA_hi);
+    tc::prefetch_tmap(&tmB_hi);
+    if (kTerms > 1) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); }
+  }
+  if (warp == 1 && tc::elect_one()) {
+    for (int i = 0; i < S::kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 8); }
+    tc::fence_barrier_init();
+  }
+  tc::cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / multicast commit
+  if (warp == 2) tc::tmem_alloc_2sm(tmem_base_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tc::uniform_u32(*tmem_base_slot);
+
+  // width of N tile `nt` (multiple of 128 so that each CTA's half is a whole number of 64-wide swizzle atoms)
+  auto n_width = [&](int n0) { return min(kBN, (p.N - n0 + 127) / 128 * 128); };
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs: own A rows, own half of B; bytes land on the leader's barrier) ====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+      const int m0 = (mn / n_tiles) * kPM + (int)cta_rank * kBM;
+      const int nbase = (mn % n_tiles) * kBN;
+      const int n0 = nbase + (int)cta_rank * (n_width(nbase) / 2);
+      const int kb_begin = ks * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        if (tc::elect_one()) {
+          uint8_t* st = smem + stage * S::kStageBytes;
+          if (leader) tc::mbar_expect_tx(&full[stage], 2 * S::kStageBytes);
+#pragma unroll
+          for (int part = 0; part < S::kParts; ++part) {
+            const CUtensorMap* ta = part == 0 ? &tmA_hi : &tmA_lo;
+            const CUtensorMap* tb = part == 0 ? &tmB_hi : &tmB_lo;
+            uint8_t* sa = st + part * S::kABytes;
+            uint8_t* sb = st + S::kParts * S::kABytes + part * S::kBBytes;
+            if (!p.a_mn) {
+              tc::tma_load_2d_2sm(sa, ta, &full[stage], kb * kBK, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < kBM / 64; ++j)
+                tc::tma_load_2d_2sm(sa + j * 8192, ta, &full[stage], m0 + 64 * j, kb * kBK);
+            }
+            if (!p.b_mn) {
+              tc::tma_load_2d_2sm(sb, tb, &full[stage], kb * kBK, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < kBN / 128; ++j)
+                tc::tma_load_2d_2sm(sb + j * 8192, tb, &full[stage], n0 + 64 * j, kb * kBK);
+            }
+          }
+        }
+        __syncwarp();
+        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ================= MMA issuer (leader CTA; one elected lane issues for the pair) =================
+    const uint32_t smem_base = tc::smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+      const int nw = n_width((mn % n_tiles) * kBN);
+      const uint32_t idesc = tc::make_idesc_bf16(kPM, nw, p.a_mn, p.b_mn);
+      const int kb_begin = ks * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+      tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kBN;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        tc::mbar_wait(&full[stage], phase);
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          const uint32_t a_hi = smem_base + stage * S::kStageBytes;
+          const uint32_t a_lo = a_hi + S::kABytes;
+          const uint32_t b_hi = a_hi + S::kParts * S::kABytes;
+          const uint32_t b_lo = b_hi + S::kBBytes;
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk) {
+            const uint32_t aoff = p.a_mn ? kk * 2048 : kk * 32;
+            const uint32_t boff = p.b_mn ? kk * 2048 : kk * 32;
+            auto adesc = [&](uint32_t base) {
+              return p.a_mn ? tc::make_desc_mnmajor_sw128(base + aoff, 8192) : tc::make_desc_kmajor_sw128(base + aoff);
+            };
+            auto bdesc = [&](uint32_t base) {
+              return p.b_mn ? tc::make_desc_mnmajor_sw128(base + boff, 8192) : tc::make_desc_kmajor_sw128(base + boff);
+            };
+            const uint32_t first = (kb == kb_begin && kk == 0) ? 0u : 1u;
+            tc::umma_ss_2sm(d_tmem, adesc(a_hi), bdesc(b_hi), idesc, first);
+            if (kTerms > 1) {
+              tc::umma_ss_2sm(d_tmem, adesc(a_hi), bdesc(b_lo), idesc, 1u);
+              tc::umma_ss_2sm(d_tmem, adesc(a_lo), bdesc(b_hi), idesc, 1u);
+            }
+          }
+          tc::umma_commit_2sm(&empty[stage], 0b11);  // both CTAs' ring slots are reusable once these MMAs retire
+        }
+        __syncwarp();
+        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (tc::elect_one()) tc::umma_commit_2sm(&tmem_full[acc], 0b11);  // accumulators complete in both CTAs
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (both CTAs: own 128 accumulator rows) =================
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int mn = tile % mn_tiles;
+      const int m0 = (mn / n_tiles) * kPM + (int)cta_rank * kBM;
+      const int n0 = (mn % n_tiles) * kBN;
+      const int nw = n_width(n0);
+      tc::mbar_wait(&tmem_full[acc], acc_phase);
+      tc::tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      float* crow = p.C + (int64_t)row * p.ldc;
+      const bool vec_ok = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+#pragma unroll 1
+      for (int c = 0; c < nw / 32; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kBN + c * 32, r);
+        tc::tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < Mdyn && col0 < p.N) {
+          if (p.atomic_add) {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(crow + col0 + j, __uint_as_float(r[j]));
+          } else if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+              if (p.bias) {
+                v.x += __ldg(p.bias + col0 + j);     v.y += __ldg(p.bias + col0 + j + 1);
+                v.z += __ldg(p.bias + col0 + j + 2); v.w += __ldg(p.bias + col0 + j + 3);
+              }
+              *reinterpret_cast<float4*>(crow + col0 + j) = v;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) crow[col0 + j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's MMA warp owns the accumulator hand-off
+    }
+  }
+  tc::tc_fence_before();
+  tc::cluster_sync_all();  // nobody leaves while the peer may still read its smem / signal its barriers
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // C[M,N] (+)= op(A) . op(B)^T from pre-split bf16 operands.
 //   a_mn == 0: A is [M, lda] with K contiguous      a_mn == 1: A is [K, lda] with M contiguous
 //   b_mn == 0: B is [N, ldb] with K contiguous      b_mn == 1: B is [K, ldb] with N contiguous
@@ -303,15 +517,19 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   const bool x3 = precision == CLASR_PREC_BF16X3;
+  // CTA pairs (256-row tiles) pay off once there are enough rows; CLASR_GEMM_PAIR=0/1 forces the choice (tests)
+  static const int force_pair = [] { const char* e = getenv("CLASR_GEMM_PAIR"); return e ? atoi(e) : -1; }();
+  const bool use_pair = force_pair >= 0 ? force_pair != 0 : (M >= 4 * kBM);
+  const int b_box = use_pair ? kBN / 2 : kBN;
   auto mk = [&](CUtensorMap* t, const void* base, int64_t ld, int mn, int rows_mn, int box_mn) -> int {
     if (!mn) return make_tmap_bf16_2d(t, base, rows_mn, K, ld, box_mn, kBK);       // [MN rows, K cols]
     return make_tmap_bf16_2d(t, base, K, rows_mn, ld, kBK, 64);                    // [K rows, MN cols], 64x64 boxes
   };
   if ((rc = mk(&ta_hi, A_hi, lda, a_mn, M, kBM))) return rc;
-  if ((rc = mk(&tb_hi, B_hi, ldb, b_mn, N, kBN))) return rc;
+  if ((rc = mk(&tb_hi, B_hi, ldb, b_mn, N, b_box))) return rc;
   if (x3) {
     if ((rc = mk(&ta_lo, A_lo, lda, a_mn, M, kBM))) return rc;
-    if ((rc = mk(&tb_lo, B_lo, ldb, b_mn, N, kBN))) return rc;
+    if ((rc = mk(&tb_lo, B_lo, ldb, b_mn, N, b_box))) return rc;
   } else {
     ta_lo = ta_hi;
     tb_lo = tb_hi;
@@ -326,6 +544,20 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
     return CLASR_STATUS_INVALID_VALUE;
   }
   GemmParams p{M, N, K, C, ldc, atomic_add, k_splits, a_mn, b_mn, m_dev, k_dev, atomic_add ? nullptr : bias};
+  if (use_pair) {
+    const int tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN) * k_splits;
+    int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+    if (pairs < 1) pairs = 1;
+    if (x3) {
+      cudaFuncSetAttribute(gemm2_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<3>::kTotalBytes);
+      gemm2_tc_kernel<3><<<2 * pairs, kGemmThreads, Gemm2Smem<3>::kTotalBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+    } else {
+      cudaFuncSetAttribute(gemm2_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<1>::kTotalBytes);
+      gemm2_tc_kernel<1><<<2 * pairs, kGemmThreads, Gemm2Smem<1>::kTotalBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+    }
+    CLASR_CHECK_LAUNCH("gemm2_tc");
+    return CLASR_STATUS_SUCCESS;
+  }
   const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN) * k_splits;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (x3) {
