@@ -192,6 +192,10 @@ CLASR_API int clasr_linear_fwd(const float* x, const float* w, const float* bias
 CLASR_API int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db, int M, int N, int K, int precision,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Design tool (not on the product path): cycles per tcgen05.mma M=128 x N x K=16 issued back to back on an otherwise
+ * idle SM.  pattern 0: SS, 1: TS (A from TMEM), 2: SS,SS,TS.  out_dev[0] = cycles, out_dev[1] = MMA count. */
+CLASR_API int clasr_debug_mma_rate(int N, int pattern, int iters, long long* out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * 4. Fused joint + transducer loss — replaces the fused branch of RNNTJoint.forward
  *    (modules/rnnt.py:1403-1561): joint_after_projection (:1587-1665) + RNNTLoss, without ever

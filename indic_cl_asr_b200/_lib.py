@@ -51,6 +51,7 @@ _PROTOS: Dict[str, Tuple[object, List[object]]] = {
     "clasr_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "clasr_gemm_nt": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "clasr_gemm_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "clasr_debug_mma_rate": (_i, [_i, _i, _i, _vp, _vp]),
     "clasr_linear_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "clasr_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "clasr_linear_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),

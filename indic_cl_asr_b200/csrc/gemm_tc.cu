@@ -737,3 +737,68 @@ extern "C" int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db
   prof_end("linear_bwd", s);
   return CLASR_STATUS_SUCCESS;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Micro-benchmark (design tool, not on the product path): cycles per tcgen05.mma M=128 x N x K=16 for a given
+// operand pattern, issued back to back by one thread with nothing else running on the SM.
+//   pattern 0: SS only   1: TS only (A from TMEM)   2: SS,SS,TS (the BF16X3 joint sequence)
+// ------------------------------------------------------------------------------------------------
+namespace clasr {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int pattern, int iters, long long* out) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = tc::warp_idx_uniform();
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  if (warp == 0 && tc::elect_one()) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+  if (warp == 1) tc::tmem_alloc(&slot, 512);
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tc::uniform_u32(slot);
+  if (warp == 0) {
+    const uint32_t idesc = tc::make_idesc_bf16(128, N);
+    const uint32_t a = tc::smem_u32(smem), b = a + 16384;
+    long long t0 = 0, t1 = 0;
+    if (tc::elect_one()) {
+      t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t da = tc::make_desc_kmajor_sw128(a + kk * 32), db = tc::make_desc_kmajor_sw128(b + kk * 32);
+          if (pattern == 0) {
+            tc::umma_ss(tmem_base, da, db, idesc, 1u);
+          } else if (pattern == 1) {
+            tc::umma_ts(tmem_base, tmem_base + 256 + kk * 8, db, idesc, 1u);
+          } else {
+            tc::umma_ss(tmem_base, da, db, idesc, 1u);
+            tc::umma_ss(tmem_base, da, db, idesc, 1u);
+            tc::umma_ts(tmem_base, tmem_base + 256 + kk * 8, db, idesc, 1u);
+          }
+        }
+      }
+      tc::umma_commit(&bar);
+    }
+    __syncwarp();
+    tc::mbar_wait(&bar, 0);
+    if (tc::elect_one()) {
+      t1 = clock64();
+      out[0] = t1 - t0;
+      out[1] = (long long)iters * 4 * (pattern == 2 ? 3 : 1);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+}  // namespace clasr
+
+extern "C" int clasr_debug_mma_rate(int N, int pattern, int iters, long long* out_dev, void* stream) {
+  CLASR_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && out_dev, "debug_mma_rate: bad arguments");
+  cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  mma_rate_kernel<<<1, 128, 64 * 1024, (cudaStream_t)stream>>>(N, pattern, iters, out_dev);
+  CLASR_CHECK_LAUNCH("mma_rate");
+  return CLASR_STATUS_SUCCESS;
+}

@@ -20,6 +20,7 @@
 // The alpha/beta wavefront (rnnt_loss.cu) then runs on those compact buffers.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace clasr {
 
@@ -34,18 +35,24 @@ constexpr int kJProducerWarps = 8;
 constexpr int kJStages = 2;
 constexpr float kJExpClamp = 43.f;  // |pre-activation| clamp of the exp factorisation: exp(2*43) is finite in fp32
 
-template <int kTerms>
+// kPair = 1: two CTAs of a cluster (one TPC) run each tcgen05.mma together (cta_group::2, M = 256 = two 128-row tiles):
+// every CTA keeps its own A tile (smem hi / TMEM lo) and loads only HALF of each W tile, so the W ring holds twice as
+// many stages in the same bytes, the L2->smem traffic per CTA halves, and an SS MMA reads 4 KB (A) + 1.5 KB (B half)
+// of shared memory per 48 clocks instead of 4 + 3 KB (the 1-CTA N = 96 MMA is smem-bandwidth-bound: r01b profile).
+template <int kTerms, int kPair = 0>
 struct JointCfg {
   static constexpr int kBN = kTerms == 1 ? 256 : 96;          // accumulator tile width (TMEM columns)
   static constexpr int kParts = kTerms == 1 ? 1 : 2;          // W parts streamed per stage (hi[,lo])
   static constexpr int kAccCols = 2 * kBN;                    // two accumulator stages
   static constexpr int kAloCol = kAccCols;                    // BF16X3: A_lo lives in TMEM columns [192, 192+H/2)
   static constexpr int kABlockBytes = kJM * kJK * 2;          // 16 KB per K block of A
-  static constexpr int kBStageBytes = kParts * kBN * kJK * 2; // W ring stage
+  static constexpr int kBRows = kBN / (kPair ? 2 : 1);        // W rows this CTA loads per N tile
+  static constexpr int kBStageBytes = kParts * kBRows * kJK * 2; // W ring stage (per CTA)
+  static constexpr int kStages = kPair ? 2 * kJStages : kJStages;
   static constexpr int kStagingBytes = kTerms == 1 ? 0 : kJProducerWarps * 2048;  // warp-private 32x32 bf16 lo tiles
   static constexpr int kRowTabBytes = 4 * 32 * 8;             // (f offset, g offset) of the tile's 128 rows
   static constexpr int smem_bytes(int H) {
-    return (H / kJK) * kABlockBytes + kStagingBytes + kJStages * kBStageBytes + kRowTabBytes + 256 + 1024;
+    return (H / kJK) * kABlockBytes + kStagingBytes + kStages * kBStageBytes + kRowTabBytes + 256 + 1024;
   }
 };
 
@@ -136,30 +143,38 @@ __device__ __forceinline__ int find_utterance(const int* __restrict__ offs, int 
   return lo;
 }
 
-template <int kTerms, int kMode, int kAct>
+template <int kTerms, int kMode, int kAct, int kPair>
 __global__ void __launch_bounds__(kJThreads, 1)
 joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                  JointFwdParams p) {
-  using C = JointCfg<kTerms>;
+  using C = JointCfg<kTerms, kPair>;
+  constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   const int kblocks = p.H / kJK;
   uint8_t* a_smem = smem;                                          // [kblocks][128 x 64 bf16], SW128 K-major
   uint8_t* staging = a_smem + kblocks * C::kABlockBytes;            // BF16X3 only: 8 warps x [32 rows x 32 k] bf16
   uint8_t* b_ring = staging + C::kStagingBytes;                     // [stages][parts][BN x 64 bf16]
-  uint8_t* rowtab = b_ring + kJStages * C::kBStageBytes;            // int2[4][32]
+  uint8_t* rowtab = b_ring + kStages * C::kBStageBytes;             // int2[4][32]
   uint64_t* bars = (uint64_t*)(rowtab + C::kRowTabBytes);
-  uint64_t* full = bars;                 // [kJStages]  W stage landed
-  uint64_t* empty = full + kJStages;     // [kJStages]  W stage consumed
-  uint64_t* tmem_full = empty + kJStages;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;     // [2]
-  uint64_t* a_ready = tmem_empty + 2;       // [kblocks <= 10] A K-block written
+  uint64_t* full = bars;                 // [kStages]  W stage landed            (pair: the leader's copy)
+  uint64_t* empty = full + kStages;      // [kStages]  W stage consumed
+  uint64_t* tmem_full = empty + kStages;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]                                 (pair: the leader's copy)
+  uint64_t* a_ready = tmem_empty + 2;       // [kblocks <= 10] A K-block written   (pair: the leader's copy)
   uint64_t* a_free = a_ready + 10;          // [kblocks <= 10] last MMA reading A K-block retired
   uint32_t* tmem_base_slot = (uint32_t*)(a_free + 10);
 
   const int warp = tc::warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const int total_tiles = (int)tc::uniform_u32((uint32_t)p.tile_offsets[p.B]);
+  // pair mode: the cluster walks PAIRS of consecutive row tiles; this CTA owns tile 2*step + rank (possibly a null
+  // tile past the end, which still takes part in every barrier hand-shake)
+  const uint32_t cta_rank = kPair ? tc::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int tile_first = kPair ? 2 * (int)(blockIdx.x >> 1) + (int)cta_rank : (int)blockIdx.x;
+  const int tile_stride = kPair ? (int)(gridDim.x & ~1u) : (int)gridDim.x;
+  const int tile_end = kPair ? (total_tiles + 1) / 2 * 2 : total_tiles;  // both CTAs run the same number of steps
   const int n_tiles = (p.Vp + C::kBN - 1) / C::kBN;
   const int n_last = ((p.Vp - (n_tiles - 1) * C::kBN) + 15) / 16 * 16;  // width of the last N tile (multiple of 16)
 
@@ -168,12 +183,20 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     if (kTerms > 1) tc::prefetch_tmap(&tmW_lo);
   }
   if (warp == 1 && tc::elect_one()) {
-    for (int i = 0; i < kJStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 4); }
-    for (int i = 0; i < 10; ++i) { tc::mbar_init(&a_ready[i], kJProducerWarps); tc::mbar_init(&a_free[i], 1); }
+    constexpr int kCtas = kPair ? 2 : 1;
+    for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 4 * kCtas); }
+    for (int i = 0; i < 10; ++i) {
+      tc::mbar_init(&a_ready[i], kJProducerWarps * kCtas);
+      tc::mbar_init(&a_free[i], 1);
+    }
     tc::fence_barrier_init();
   }
-  if (warp == 2) tc::tmem_alloc(tmem_base_slot, 512);
+  if (kPair) tc::cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / multicast commit
+  if (warp == 2) {
+    if (kPair) tc::tmem_alloc_2sm(tmem_base_slot, 512);
+    else tc::tmem_alloc(tmem_base_slot, 512);
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -183,32 +206,41 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     // ============================ TMA producer: W ring (whole warp loops, one elected lane issues) ===========
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
       for (int nt = 0; nt < n_tiles; ++nt) {
+        // pair: this CTA loads rows [n0 + rank * width/2, +kBRows) of the W tile (the MMA reads width/2 of them)
+        const int n_cur = (nt == n_tiles - 1) ? n_last : C::kBN;
+        const int n0 = nt * C::kBN + (kPair ? (int)cta_rank * (n_cur / 2) : 0);
         for (int kb = 0; kb < kblocks; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
           if (tc::elect_one()) {
             uint8_t* st = b_ring + stage * C::kBStageBytes;
-            tc::mbar_expect_tx(&full[stage], C::kBStageBytes);
-            tc::tma_load_2d(st, &tmW_hi, &full[stage], kb * kJK, nt * C::kBN);
-            if (kTerms > 1) tc::tma_load_2d(st + C::kBN * kJK * 2, &tmW_lo, &full[stage], kb * kJK, nt * C::kBN);
+            if (kPair) {
+              if (leader) tc::mbar_expect_tx(&full[stage], 2 * C::kBStageBytes);
+              tc::tma_load_2d_2sm(st, &tmW_hi, &full[stage], kb * kJK, n0);
+              if (kTerms > 1) tc::tma_load_2d_2sm(st + C::kBRows * kJK * 2, &tmW_lo, &full[stage], kb * kJK, n0);
+            } else {
+              tc::mbar_expect_tx(&full[stage], C::kBStageBytes);
+              tc::tma_load_2d(st, &tmW_hi, &full[stage], kb * kJK, n0);
+              if (kTerms > 1) tc::tma_load_2d(st + C::kBRows * kJK * 2, &tmW_lo, &full[stage], kb * kJK, n0);
+            }
           }
           __syncwarp();
-          if (++stage == kJStages) { stage = 0; phase ^= 1; }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ============================ MMA issuer (whole warp loops, one elected lane issues) ======================
-    const uint32_t idesc_full = tc::make_idesc_bf16(kJM, C::kBN);
-    const uint32_t idesc_last = tc::make_idesc_bf16(kJM, n_last);
+  } else if (warp == 1 && leader) {
+    // ============================ MMA issuer (whole warp loops, one elected lane issues; pair: leader CTA) ====
+    const uint32_t idesc_full = tc::make_idesc_bf16(kPair ? 2 * kJM : kJM, C::kBN);
+    const uint32_t idesc_last = tc::make_idesc_bf16(kPair ? 2 * kJM : kJM, n_last);
     const uint32_t a_base = tc::smem_u32(a_smem);
     const uint32_t b_base = tc::smem_u32(b_ring);
     int stage = 0;
     uint32_t phase = 0;
     int acc_it = 0;
     int tile_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++tile_it) {
       const uint32_t tile_phase = tile_it & 1;
       for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
         const int acc = acc_it & 1;
@@ -225,30 +257,47 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           if (tc::elect_one()) {
             const uint32_t a_hi = a_base + kb * C::kABlockBytes;
             const uint32_t b_hi = b_base + stage * C::kBStageBytes;
-            const uint32_t b_lo = b_hi + C::kBN * kJK * 2;
+            const uint32_t b_lo = b_hi + C::kBRows * kJK * 2;
 #pragma unroll
             for (int kk = 0; kk < kJK / 16; ++kk) {
               const uint32_t koff = kk * 32;
               const uint32_t accum = (kb == 0 && kk == 0) ? 0u : 1u;
-              tc::umma_ss(d_tmem, tc::make_desc_kmajor_sw128(a_hi + koff), tc::make_desc_kmajor_sw128(b_hi + koff),
-                          idesc, accum);
-              if (kTerms > 1) {
-                tc::umma_ss(d_tmem, tc::make_desc_kmajor_sw128(a_hi + koff), tc::make_desc_kmajor_sw128(b_lo + koff),
-                            idesc, 1u);
-                // A_lo from tensor memory: 16 bf16 of K = 8 packed 32-bit columns
-                tc::umma_ts(d_tmem, tmem_base + C::kAloCol + kb * (kJK / 2) + kk * 8,
-                            tc::make_desc_kmajor_sw128(b_hi + koff), idesc, 1u);
+              const uint64_t da = tc::make_desc_kmajor_sw128(a_hi + koff);
+              const uint64_t dbh = tc::make_desc_kmajor_sw128(b_hi + koff);
+              const uint64_t dbl = tc::make_desc_kmajor_sw128(b_lo + koff);
+              // A_lo from tensor memory: 16 bf16 of K = 8 packed 32-bit columns
+              const uint32_t a_lo_t = tmem_base + C::kAloCol + kb * (kJK / 2) + kk * 8;
+              if (kPair) {
+                tc::umma_ss_2sm(d_tmem, da, dbh, idesc, accum);
+                if (kTerms > 1) {
+                  tc::umma_ss_2sm(d_tmem, da, dbl, idesc, 1u);
+                  tc::umma_ts_2sm(d_tmem, a_lo_t, dbh, idesc, 1u);
+                }
+              } else {
+                tc::umma_ss(d_tmem, da, dbh, idesc, accum);
+                if (kTerms > 1) {
+                  tc::umma_ss(d_tmem, da, dbl, idesc, 1u);
+                  tc::umma_ts(d_tmem, a_lo_t, dbh, idesc, 1u);
+                }
               }
             }
-            tc::umma_commit(&empty[stage]);
             // last N tile: this K block of A (smem hi + TMEM lo) is dead once these MMAs retire -> the producers
             // may already write the next row tile's block while the remaining K blocks are still being consumed
-            if (last_nt) tc::umma_commit(&a_free[kb]);
+            if (kPair) {
+              tc::umma_commit_2sm(&empty[stage], 0b11);
+              if (last_nt) tc::umma_commit_2sm(&a_free[kb], 0b11);
+            } else {
+              tc::umma_commit(&empty[stage]);
+              if (last_nt) tc::umma_commit(&a_free[kb]);
+            }
           }
           __syncwarp();
-          if (++stage == kJStages) { stage = 0; phase ^= 1; }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (tc::elect_one()) tc::umma_commit(&tmem_full[acc]);
+        if (tc::elect_one()) {
+          if (kPair) tc::umma_commit_2sm(&tmem_full[acc], 0b11);
+          else tc::umma_commit(&tmem_full[acc]);
+        }
         __syncwarp();
       }
     }
@@ -260,11 +309,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int acc_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int b = find_utterance(p.tile_offsets, p.B, tile);
+    for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
+      const bool tile_ok = tile < total_tiles;  // pair mode: a null tile past the end only does the hand-shakes
+      const int b = find_utterance(p.tile_offsets, p.B, tile_ok ? tile : 0);
       const int Tb = (int)p.act_lens[b], Ub1 = (int)p.label_lens[b] + 1;
       const int r = (tile - p.tile_offsets[b]) * kJM + row;  // cell index inside the utterance (t-major)
-      const bool valid = r < Tb * Ub1;
+      const bool valid = tile_ok && r < Tb * Ub1;
       const int t = valid ? r / Ub1 : 0;
       const int u = valid ? r - t * Ub1 : 0;
       const int label = (valid && u < Ub1 - 1) ? (int)p.labels[(int64_t)b * (p.U1 - 1) + u] : -1;
@@ -301,7 +351,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         const int width = (kMode == 1 ? p.ldz : p.Vp);
         const int ncols = (nt == n_tiles - 1) ? (width - nt * C::kBN) : C::kBN;
 #pragma unroll 1
-        for (int c = 0; c * 32 < ncols; ++c) {
+        for (int c = 0; tile_ok && c * 32 < ncols; ++c) {
           uint32_t rr[32];
           tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN + c * 32, rr);
           tc::tmem_ld_wait();
@@ -388,7 +438,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         }
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's MMA warp owns the hand-off
+          else tc::mbar_arrive(&tmem_empty[acc]);
+        }
       }
       if (kMode == 0 && valid) {
         const float lse = m + logf(s);
@@ -421,11 +474,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
                              (c & 3) * 4);
     }
     int tile_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
-      const int b = find_utterance(p.tile_offsets, p.B, tile);
+    for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++tile_it) {
+      const bool tile_ok = tile < total_tiles;
+      const int b = find_utterance(p.tile_offsets, p.B, tile_ok ? tile : 0);
       const int Tb = (int)p.act_lens[b], Ub1 = (int)p.label_lens[b] + 1;
       const int r0 = (tile - p.tile_offsets[b]) * kJM;
-      const int cells = Tb * Ub1;
+      const int cells = tile_ok ? Tb * Ub1 : 0;  // null tile: every row is padding (A = 0)
       {  // row table: lane l <-> row 32q + l (both K-half warps of a quarter write identical values)
         const int r = r0 + q * 32 + lane;
         int fo = -1, go_ = -1;
@@ -472,7 +526,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           const int rimm = (i & 3) + 8 * (i >> 2);  // compile-time part of the row index
           tc::st_shared_u32(ablk + aoff[i & 3] + rimm * 128, hw);
           if (kTerms > 1) tc::st_shared_u32(stg + soff[i & 3] + 8 * (i >> 2) * 64, lw);
-          if (kMode == 1) {  // the dW GEMM consumes the hidden activations as an operand: keep a bf16 hi/lo copy
+          if (kMode == 1 && tile_ok) {  // the dW GEMM consumes the hidden activations: keep a bf16 hi/lo copy
             const int64_t go2 = ((int64_t)tile * kJM + q * 32 + rimm + 4 * hs) * p.ldh;
             const int k = kb * kJK + half * 32 + 2 * c;
             *reinterpret_cast<uint32_t*>(p.hid_hi + go2 + k) = hw;
@@ -519,15 +573,20 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         }
         tc::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the UMMA (async proxy) reads
         __syncwarp();                  // also: staging reads done before the next K block's writes
-        if (lane == 0) tc::mbar_arrive(&a_ready[kb]);
+        if (lane == 0) {
+          if (kPair) tc::mbar_arrive_cluster(&a_ready[kb], 0);  // the leader's MMA warp waits for both CTAs' A blocks
+          else tc::mbar_arrive(&a_ready[kb]);
+        }
       }
     }
   }
   tc::tc_fence_before();
-  __syncthreads();
+  if (kPair) tc::cluster_sync_all();  // nobody leaves while the peer may still read its smem / signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 512);
+    if (kPair) tc::tmem_dealloc_2sm(tmem_base, 512);
+    else tc::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -667,20 +726,48 @@ static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, in
   return j;
 }
 
+// CLASR_JOINT_PAIR=0/1 selects the 1-CTA / CTA-pair variant (default: pairs)
+static bool joint_use_pair() {
+  const char* e = getenv("CLASR_JOINT_PAIR");  // read per call: the tests toggle it
+  return e ? atoi(e) != 0 : true;
+}
+
+template <int kTerms, int kMode, int kAct, int kPair>
+static int launch_joint_variant(int H, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo, const JointFwdParams& p,
+                                cudaStream_t s) {
+  const int smem = JointCfg<kTerms, kPair>::smem_bytes(H);
+  auto kern = joint_fwd_kernel<kTerms, kMode, kAct, kPair>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kNumSMs & ~1);
+  cfg.blockDim = dim3(kJThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tw_hi, tw_lo, p);
+  if (e != cudaSuccess) {
+    set_error("joint kernel launch: %s", cudaGetErrorString(e));
+    return CLASR_STATUS_CUDA_ERROR;
+  }
+  return CLASR_STATUS_SUCCESS;
+}
+
 template <int kTerms, int kMode>
 static int launch_joint_kernel(int activation, int H, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
                                const JointFwdParams& p, cudaStream_t s) {
-  const int smem = JointCfg<kTerms>::smem_bytes(H);
-#define CLASR_LAUNCH_JOINT(ACT)                                                                                   \
-  do {                                                                                                            \
-    cudaFuncSetAttribute(joint_fwd_kernel<kTerms, kMode, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-    joint_fwd_kernel<kTerms, kMode, ACT><<<kNumSMs, kJThreads, smem, s>>>(tw_hi, tw_lo, p);                       \
-  } while (0)
-  if (activation == CLASR_ACT_RELU) CLASR_LAUNCH_JOINT(CLASR_ACT_RELU);
-  else if (activation == CLASR_ACT_SIGMOID) CLASR_LAUNCH_JOINT(CLASR_ACT_SIGMOID);
-  else CLASR_LAUNCH_JOINT(CLASR_ACT_TANH);
+#define CLASR_LAUNCH_JOINT(ACT)                                                                  \
+  (joint_use_pair() ? launch_joint_variant<kTerms, kMode, ACT, 1>(H, tw_hi, tw_lo, p, s)         \
+                    : launch_joint_variant<kTerms, kMode, ACT, 0>(H, tw_hi, tw_lo, p, s))
+  if (activation == CLASR_ACT_RELU) return CLASR_LAUNCH_JOINT(CLASR_ACT_RELU);
+  if (activation == CLASR_ACT_SIGMOID) return CLASR_LAUNCH_JOINT(CLASR_ACT_SIGMOID);
+  return CLASR_LAUNCH_JOINT(CLASR_ACT_TANH);
 #undef CLASR_LAUNCH_JOINT
-  return CLASR_STATUS_SUCCESS;
 }
 
 // exp factors of the activation (see joint_prep_kernel); relu needs none
@@ -756,7 +843,8 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.sumsq = sumsq;
   CUtensorMap tw_hi, tw_lo;
-  const int bn = x3 ? JointCfg<3>::kBN : JointCfg<1>::kBN;
+  const int bn = joint_use_pair() ? (x3 ? JointCfg<3, 1>::kBRows : JointCfg<1, 1>::kBRows)
+                                  : (x3 ? JointCfg<3, 0>::kBRows : JointCfg<1, 0>::kBRows);
   if ((rc = make_tmap_bf16_2d(&tw_hi, jw.w_hi, Vp, H, H, bn, kJK))) return rc;
   if (x3) {
     if ((rc = make_tmap_bf16_2d(&tw_lo, jw.w_lo, Vp, H, H, bn, kJK))) return rc;
@@ -764,8 +852,9 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
     tw_lo = tw_hi;
   }
   prof_begin("joint_fwd", s);
-  if (x3) launch_joint_kernel<3, 0>(activation, H, tw_hi, tw_lo, p, s);
-  else launch_joint_kernel<1, 0>(activation, H, tw_hi, tw_lo, p, s);
+  rc = x3 ? launch_joint_kernel<3, 0>(activation, H, tw_hi, tw_lo, p, s)
+          : launch_joint_kernel<1, 0>(activation, H, tw_hi, tw_lo, p, s);
+  if (rc) return rc;
   prof_end("joint_fwd", s);
   CLASR_CHECK_LAUNCH("joint_fwd");
   return launch_rnnt_lattice(p.w, act_lens, label_lens, B, T, U1, fastemit_lambda, costs, s);
@@ -812,7 +901,8 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
   p.hid_hi = (__nv_bfloat16*)sc.hid_hi; p.hid_lo = (__nv_bfloat16*)sc.hid_lo; p.ldh = sc.ldh;
   p.rows_pad_dev = rows_pad_dev;
   CUtensorMap tw_hi, tw_lo;
-  const int bn = x3 ? JointCfg<3>::kBN : JointCfg<1>::kBN;
+  const int bn = joint_use_pair() ? (x3 ? JointCfg<3, 1>::kBRows : JointCfg<1, 1>::kBRows)
+                                  : (x3 ? JointCfg<3, 0>::kBRows : JointCfg<1, 0>::kBRows);
   if ((rc = make_tmap_bf16_2d(&tw_hi, jw.w_hi, Vp, H, H, bn, kJK))) return rc;
   if (x3) {
     if ((rc = make_tmap_bf16_2d(&tw_lo, jw.w_lo, Vp, H, H, bn, kJK))) return rc;
@@ -820,8 +910,9 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
     tw_lo = tw_hi;
   }
   prof_begin("joint_bwd_dz", s);
-  if (x3) launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, p, s);
-  else launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, p, s);
+  rc = x3 ? launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, p, s)
+          : launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, p, s);
+  if (rc) return rc;
   prof_end("joint_bwd_dz", s);
   CLASR_CHECK_LAUNCH("joint_bwd_dz");
 
