@@ -228,6 +228,18 @@ CLASR_API int clasr_joint_rnnt_bwd(const float* f, const float* g, const float* 
                          float* d_b_out, void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
                          void* stream);
 
+/* Backward of the per-cell sum_v z^2 that clasr_joint_rnnt_fwd writes into `sumsq` — the joint half of the MAS
+ * importance objective (cl_baseline_mas.py:258-265: mean over the stored sub-batch logits of sum_v z^2): dZ = 2 z *
+ * grad_cells[b,t,u], then the same two GEMMs / reductions as the loss backward.  Replaces autograd through the
+ * materialised `store_list` logits (modules/rnnt.py:1480-1496, 1649-1650).  Cells are those selected by act_lens /
+ * label_lens of the forward call (pass the sub-batch maxima to include the reference's padded cells). */
+CLASR_API int clasr_joint_sumsq_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
+                                    const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
+                                    int T, int U1, int H, int Vp, int blank, int activation, int precision,
+                                    const float* grad_cells, float* d_f, float* d_g, float* d_w_out, float* d_b_out,
+                                    void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

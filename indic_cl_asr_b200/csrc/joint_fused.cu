@@ -70,6 +70,7 @@ struct JointFwdParams {
   float* sumsq;        // [B,T,U1] sum_v z^2 (MAS), or nullptr
   // ---- pass 2 (kMode == 1): recompute the logits tile and emit the softmax-fused gradient as GEMM operands
   const float* grad_out;      // [B] upstream gradient of each cost (may be nullptr == 1)
+  const float* grad_cells;    // kMode 2: [B,T,U1] upstream gradient of sum_v z^2 per cell (MAS objective)
   float fastemit_lambda, clamp;
   __nv_bfloat16* dz_hi;       // [rows_pad, ldz]  dZ split hi/lo, compact tile-row order
   __nv_bfloat16* dz_lo;
@@ -324,6 +325,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       // by log2(e) so that each logit costs one FFMA + one MUFU.EX2.  Padding rows: base2 = -inf, go = 0 -> dZ = 0.
       constexpr float kLog2e = 1.4426950408889634f;
       float base2 = -INFINITY, fe_base2 = -INFINITY, fe_coef = 0.f, blank_sub = 0.f, label_sub = 0.f, go = 0.f;
+      if (kMode == 2 && valid) go = 2.f * p.grad_cells[((int64_t)b * p.T + t) * p.U1 + u];  // d(sum z^2)/dz = 2z
       if (kMode == 1 && valid) {
         const double a = p.w.alpha[idx], bt = p.w.beta[idx], ll = p.w.ll_fwd[b];
         const float dn = p.w.denom[idx];
@@ -348,7 +350,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         tc::mbar_wait(&tmem_full[acc], acc_phase);
         tc::tc_fence_after();
         // columns this N tile must cover: up to Vp (stats) or up to the padded operand width ldz (gradient)
-        const int width = (kMode == 1 ? p.ldz : p.Vp);
+        const int width = (kMode >= 1 ? p.ldz : p.Vp);
         const int ncols = (nt == n_tiles - 1) ? (width - nt * C::kBN) : C::kBN;
 #pragma unroll 1
         for (int c = 0; tile_ok && c * 32 < ncols; ++c) {
@@ -387,7 +389,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               gr[4 * j4 + 2] = __uint_as_float(rr[4 * j4 + 2]) + bv.z;
               gr[4 * j4 + 3] = __uint_as_float(rr[4 * j4 + 3]) + bv.w;
             }
-            if (p.fastemit_lambda > 0.f) {
+            if (kMode == 2) {
+              // MAS importance objective: dZ = 2 z * upstream (go); nothing else to do per logit
+            } else if (p.fastemit_lambda > 0.f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 gr[j] = fmaf(fe_coef, tc::ex2_approx(fmaf(gr[j], kLog2e, fe_base2)),
@@ -401,18 +405,18 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               for (int j = 0; j < 32; ++j)
                 if (col0 + j >= p.Vp) gr[j] = 0.f;
             }
-            if (p.blank >= col0 && p.blank < col0 + 32) {
+            if (kMode == 1 && p.blank >= col0 && p.blank < col0 + 32) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j == p.blank) gr[j] -= blank_sub;
             }
-            if (__any_sync(0xffffffffu, label >= col0 && label < col0 + 32)) {
+            if (kMode == 1 && __any_sync(0xffffffffu, label >= col0 && label < col0 + 32)) {
               const int jl = label - col0;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (j == jl) gr[j] -= label_sub;
             }
-            if (p.clamp > 0.f) {
+            if (kMode == 1 && p.clamp > 0.f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) gr[j] = fmaxf(fminf(gr[j], p.clamp), -p.clamp);
             }
@@ -526,7 +530,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           const int rimm = (i & 3) + 8 * (i >> 2);  // compile-time part of the row index
           tc::st_shared_u32(ablk + aoff[i & 3] + rimm * 128, hw);
           if (kTerms > 1) tc::st_shared_u32(stg + soff[i & 3] + 8 * (i >> 2) * 64, lw);
-          if (kMode == 1 && tile_ok) {  // the dW GEMM consumes the hidden activations: keep a bf16 hi/lo copy
+          if (kMode >= 1 && tile_ok) {  // the dW GEMM consumes the hidden activations: keep a bf16 hi/lo copy
             const int64_t go2 = ((int64_t)tile * kJM + q * 32 + rimm + 4 * hs) * p.ldh;
             const int k = kb * kJK + half * 32 + 2 * c;
             *reinterpret_cast<uint32_t*>(p.hid_hi + go2 + k) = hw;
@@ -865,12 +869,13 @@ extern "C" size_t clasr_joint_bwd_scratch_bytes(int B, int T, int U1, int H, int
   return joint_bwd_scratch_carve(nullptr, B, T, U1, H, Vp, precision).total;
 }
 
-extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
-                                    const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
-                                    int T, int U1, int H, int Vp, int blank, int activation, int precision,
-                                    float fastemit_lambda, float clamp, const float* grad_out, float* d_f, float* d_g,
-                                    float* d_w_out, float* d_b_out, void* workspace, size_t workspace_bytes,
-                                    void* scratch, size_t scratch_bytes, void* stream) {
+// mode 1: transducer-loss backward (grad_out [B]);  mode 2: backward of sum_v z^2 per cell (grad_cells [B,T,U1])
+static int joint_bwd_impl(int mode, const float* f, const float* g, const float* w_out, const float* b_out,
+                          const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B, int T, int U1,
+                          int H, int Vp, int blank, int activation, int precision, float fastemit_lambda, float clamp,
+                          const float* grad_out, const float* grad_cells, float* d_f, float* d_g, float* d_w_out,
+                          float* d_b_out, void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                          void* stream) {
   int rc = check_joint_args("joint_rnnt_bwd", f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank,
                             activation, precision, workspace, workspace_bytes);
   if (rc) return rc;
@@ -896,7 +901,7 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
   p.tile_offsets = jw.tile_offsets;
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
-  p.grad_out = grad_out; p.fastemit_lambda = fastemit_lambda; p.clamp = clamp;
+  p.grad_out = grad_out; p.grad_cells = grad_cells; p.fastemit_lambda = fastemit_lambda; p.clamp = clamp;
   p.dz_hi = (__nv_bfloat16*)sc.dz_hi; p.dz_lo = (__nv_bfloat16*)sc.dz_lo; p.ldz = sc.ldz;
   p.hid_hi = (__nv_bfloat16*)sc.hid_hi; p.hid_lo = (__nv_bfloat16*)sc.hid_lo; p.ldh = sc.ldh;
   p.rows_pad_dev = rows_pad_dev;
@@ -910,8 +915,12 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
     tw_lo = tw_hi;
   }
   prof_begin("joint_bwd_dz", s);
-  rc = x3 ? launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, p, s)
-          : launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, p, s);
+  if (mode == 1)
+    rc = x3 ? launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, p, s)
+            : launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, p, s);
+  else
+    rc = x3 ? launch_joint_kernel<3, 2>(activation, H, tw_hi, tw_lo, p, s)
+            : launch_joint_kernel<1, 2>(activation, H, tw_hi, tw_lo, p, s);
   if (rc) return rc;
   prof_end("joint_bwd_dz", s);
   CLASR_CHECK_LAUNCH("joint_bwd_dz");
@@ -946,4 +955,27 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
   prof_end("joint_dfg", s);
   CLASR_CHECK_LAUNCH("joint_dg");
   return CLASR_STATUS_SUCCESS;
+}
+
+extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
+                                    const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
+                                    int T, int U1, int H, int Vp, int blank, int activation, int precision,
+                                    float fastemit_lambda, float clamp, const float* grad_out, float* d_f, float* d_g,
+                                    float* d_w_out, float* d_b_out, void* workspace, size_t workspace_bytes,
+                                    void* scratch, size_t scratch_bytes, void* stream) {
+  return joint_bwd_impl(1, f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank, activation,
+                        precision, fastemit_lambda, clamp, grad_out, nullptr, d_f, d_g, d_w_out, d_b_out, workspace,
+                        workspace_bytes, scratch, scratch_bytes, stream);
+}
+
+extern "C" int clasr_joint_sumsq_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
+                                     const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
+                                     int T, int U1, int H, int Vp, int blank, int activation, int precision,
+                                     const float* grad_cells, float* d_f, float* d_g, float* d_w_out, float* d_b_out,
+                                     void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                                     void* stream) {
+  CLASR_CHECK_ARG(grad_cells, "joint_sumsq_bwd: null grad_cells");
+  return joint_bwd_impl(2, f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank, activation,
+                        precision, 0.f, 0.f, nullptr, grad_cells, d_f, d_g, d_w_out, d_b_out, workspace, workspace_bytes,
+                        scratch, scratch_bytes, stream);
 }

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["fused_joint_rnnt_loss", "fused_joint_forward_stats"]
+__all__ = ["fused_joint_rnnt_loss", "fused_joint_forward_stats", "fused_joint_sumsq", "LazySubLogits"]
 
 
 def _ws(f, B, T, U1, H, Vp, prec):
@@ -99,3 +99,110 @@ def fused_joint_forward_stats(f, g, weight, bias, labels, act_lens, label_lens, 
     """(costs [B], sum_v z^2 [B,T,U+1]) — the second is what MAS needs from the joint logits."""
     return _FusedJointRNNT.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision, 0.0,
                                  0.0, True)
+
+
+class _FusedJointSumsq(torch.autograd.Function):
+    """sum_v z[b,t,u,v]^2 for every cell selected by (act_lens, label_lens), differentiable w.r.t. f, g, W, b — the
+    joint half of the MAS importance objective (reference cl_baseline_mas.py:258-265) without the logits tensor."""
+
+    @staticmethod
+    def forward(ctx, f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision):
+        _lib.require_cuda(f, "f")
+        f = f.contiguous().float()
+        g = g.contiguous().float()
+        weight = weight.contiguous().float()
+        bias = bias.contiguous().float()
+        B, T, H = f.shape
+        U1 = g.shape[1]
+        Vp = weight.shape[0]
+        labels = labels[:, : U1 - 1].contiguous().long() if U1 > 1 else labels.contiguous().long()
+        act_lens = act_lens.contiguous().long()
+        label_lens = label_lens.contiguous().long()
+        prec = _lib.PREC[precision]
+        ws, nbytes = _ws(f, B, T, U1, H, Vp, prec)
+        costs = torch.empty(B, dtype=torch.float32, device=f.device)  # by-product of the same pass; not used here
+        sumsq = torch.zeros(B, T, U1, dtype=torch.float32, device=f.device)
+        L = _lib.lib()
+        with torch.cuda.device(f.device):
+            st = L.clasr_joint_rnnt_fwd(
+                f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
+                act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, int(blank), _lib.ACT[activation], prec,
+                0.0, costs.data_ptr(), sumsq.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr(f.device))
+        _lib.check(st, "joint_rnnt_fwd")
+        ctx.save_for_backward(f, g, weight, bias, labels, act_lens, label_lens, ws)
+        ctx.args = (int(blank), _lib.ACT[activation], prec, nbytes)
+        return sumsq
+
+    @staticmethod
+    def backward(ctx, grad_sumsq):
+        f, g, weight, bias, labels, act_lens, label_lens, ws = ctx.saved_tensors
+        blank, act, prec, nbytes = ctx.args
+        B, T, H = f.shape
+        U1 = g.shape[1]
+        Vp = weight.shape[0]
+        gc = grad_sumsq.contiguous().float()
+        d_f, d_g = torch.empty_like(f), torch.empty_like(g)
+        d_w, d_b = torch.empty_like(weight), torch.empty_like(bias)
+        L = _lib.lib()
+        sbytes = L.clasr_joint_bwd_scratch_bytes(B, T, U1, H, Vp, prec)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=f.device)
+        with torch.cuda.device(f.device):
+            st = L.clasr_joint_sumsq_bwd(
+                f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
+                act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, blank, act, prec, gc.data_ptr(),
+                d_f.data_ptr(), d_g.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ws.data_ptr(), nbytes,
+                scratch.data_ptr(), sbytes, _lib.stream_ptr(f.device))
+        _lib.check(st, "joint_sumsq_bwd")
+        return (d_f, d_g, d_w, d_b) + (None,) * 6
+
+
+def fused_joint_sumsq(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh", precision="bf16x3"):
+    """[B,T,U+1] tensor of sum_v z^2 (zero outside the cells selected by the lengths), with autograd."""
+    return _FusedJointSumsq.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision)
+
+
+class LazySubLogits:
+    """Stand-in for one entry of ``RNNTJoint.store_list`` when ``store_sub_logits`` is set on the fused path.
+
+    The only thing the reference's MAS driver does with a stored sub-batch logits tensor is
+    ``(x.flatten(end_dim=-2) ** 2).sum(dim=-1).mean()`` (cl_baseline_mas.py:260-262).  This object answers exactly that
+    chain from the fused kernel's per-cell sum of squares (so the [b,T',U'+1,V+1] tensor never exists) and falls
+    back to materialising the logits for anything else."""
+
+    def __init__(self, sumsq_box: torch.Tensor, vp: int, materialise, squared: bool = False):
+        self._sumsq = sumsq_box          # [b, T', U'+1] (or flattened), autograd-connected
+        self._vp = vp
+        self._materialise = materialise  # () -> logits tensor [b, T', U'+1, V+1]
+        self._squared = squared
+
+    @property
+    def shape(self):
+        return torch.Size(tuple(self._sumsq.shape) + (self._vp,))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def flatten(self, start_dim: int = 0, end_dim: int = -1):
+        if start_dim == 0 and end_dim in (-2, self._sumsq.dim() - 1):
+            return LazySubLogits(self._sumsq.reshape(-1), self._vp, lambda: self._materialise().flatten(end_dim=-2),
+                                 self._squared)
+        return self.materialise().flatten(start_dim, end_dim)
+
+    def __pow__(self, p):
+        if p == 2 and not self._squared:
+            return LazySubLogits(self._sumsq, self._vp, lambda: self._materialise() ** 2, True)
+        return self.materialise() ** p
+
+    def pow(self, p):
+        return self.__pow__(p)
+
+    def sum(self, dim=None, **kw):
+        if self._squared and dim in (-1, self._sumsq.dim()) and not kw:
+            return self._sumsq
+        return self.materialise().sum(dim, **kw) if dim is not None else self.materialise().sum(**kw)
+
+    def materialise(self) -> torch.Tensor:
+        return self._materialise()
+
+    def __getattr__(self, name):  # any other tensor API: pay for the logits
+        return getattr(self.materialise(), name)

@@ -250,7 +250,9 @@ class RNNTJoint(torch.nn.Module):
         if (encoder_lengths is None) or (transcript_lengths is None):
             raise ValueError("`fuse_loss_wer` is set, therefore encoder and target lengths must be provided as well!")
 
-        needs_tensors = self.store_sub_enc or self.store_sub_logits
+        # store_sub_logits alone (the MAS importance pass) stays on the fused path: store_list gets lazy entries that
+        # answer the driver's sum-of-squares objective from the kernel's per-cell sum_v z^2
+        needs_tensors = self.store_sub_enc or (self.store_sub_logits and self.detach_sub_enc)
         use_tcgen05 = (
             self.fused_impl == "tcgen05" and decoder_outputs is not None and not needs_tensors
             and self._tcgen05_supported(language_ids)
@@ -258,6 +260,9 @@ class RNNTJoint(torch.nn.Module):
         if use_tcgen05:
             losses = self._forward_fused_tcgen05(encoder_outputs, decoder_outputs, encoder_lengths, transcripts,
                                                  transcript_lengths, language_ids)
+            if self.store_sub_logits:
+                self.store_list = self._lazy_store_list(encoder_outputs, decoder_outputs, encoder_lengths,
+                                                        transcripts, transcript_lengths, language_ids)
             wer, wer_num, wer_denom = self._wer_pass(encoder_outputs, encoder_lengths, transcripts,
                                                      transcript_lengths, language_ids) if compute_wer else (None,) * 3
             return losses, wer, wer_num, wer_denom
@@ -341,6 +346,39 @@ class RNNTJoint(torch.nn.Module):
         if isinstance(self.joint_net[-1], torch.nn.ModuleDict):
             return language_ids is not None and len(set(language_ids)) == 1
         return True
+
+    def _lazy_store_list(self, enc, dec, enc_lens, transcripts, transcript_lens, language_ids):
+        """``store_list`` for ``store_sub_logits`` on the fused path (reference modules/rnnt.py:1480-1496, 1649-1650).
+
+        One extra fused forward over the PADDED sub-batch boxes (every utterance of a sub-batch takes the sub-batch's
+        max T and max U, exactly the cells the reference's stored ``[b, T', U'+1, V+1]`` tensors hold) yields
+        sum_v z^2 per cell; each sub-batch becomes a LazySubLogits over its slice."""
+        from ..fused import LazySubLogits, fused_joint_sumsq
+
+        lin = self._final_linear(language_ids)
+        B = int(enc.size(0))
+        box_t = torch.empty_like(enc_lens, dtype=torch.long)
+        box_u = torch.empty_like(transcript_lens, dtype=torch.long)
+        boxes = []
+        for begin, end in self._sub_batches(B):
+            mt, mu = int(enc_lens[begin:end].max()), int(transcript_lens[begin:end].max())
+            box_t[begin:end], box_u[begin:end] = mt, mu
+            boxes.append((begin, end, mt, mu))
+        f, g = self.project_encoder(enc), self.project_prednet(dec)
+        sumsq = fused_joint_sumsq(f, g, lin.weight, lin.bias, transcripts, box_t, box_u, blank=self.loss._blank,
+                                  activation=self.activation, precision=self.precision)
+        vp = int(lin.weight.shape[0])
+        out = []
+        for begin, end, mt, mu in boxes:
+            def mat(b0=begin, b1=end, t=mt, u=mu):
+                lang = None if language_ids is None else language_ids[b0:b1]
+                keep, self.store_sub_logits = self.store_sub_logits, False
+                try:
+                    return self.joint(enc[b0:b1, :t], dec[b0:b1, : u + 1], language_ids=lang)
+                finally:
+                    self.store_sub_logits = keep
+            out.append(LazySubLogits(sumsq[begin:end, :mt, : mu + 1], vp, mat))
+        return out
 
     def _forward_fused_tcgen05(self, enc, dec, enc_lens, transcripts, transcript_lens, language_ids):
         from ..fused import fused_joint_rnnt_loss
