@@ -535,7 +535,22 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
     tb_lo = tb_hi;
   }
   const int kb_total = (K + kBK - 1) / kBK;
-  if (k_splits < 1) k_splits = 1;
+  if (k_splits <= 0) {
+    // auto split-K: fill the persistent grid (74 CTA pairs or 148 CTAs) with as little wave-quantisation loss as
+    // possible — 15 output tiles x 11 slices on 74 pairs run 3 rounds at 74 % occupancy, x 24 slices 5 rounds at 97 %
+    const int units = use_pair ? kNumSMs / 2 : kNumSMs;
+    const int mn = use_pair ? ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN)
+                            : ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
+    const int s_max = kb_total / 16 > 1 ? (kb_total / 16 < 64 ? kb_total / 16 : 64) : 1;  // >= 16 K blocks per slice
+    int best = 1;
+    double best_u = 0.0;
+    for (int sp = 1; sp <= s_max; ++sp) {
+      const int items = mn * sp;
+      const double u = (double)items / ((double)((items + units - 1) / units) * units);
+      if (u > best_u + 0.02) { best_u = u; best = sp; }  // prefer fewer slices unless clearly better
+    }
+    k_splits = best;
+  }
   if (k_splits > kb_total) k_splits = kb_total;
   const int per = (kb_total + k_splits - 1) / k_splits;
   k_splits = (kb_total + per - 1) / per;  // no empty slice

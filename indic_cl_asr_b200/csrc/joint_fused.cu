@@ -75,9 +75,10 @@ struct JointFwdParams {
   __nv_bfloat16* dz_hi;       // [rows_pad, ldz]  dZ split hi/lo, compact tile-row order
   __nv_bfloat16* dz_lo;
   int ldz;                    // multiple of 8, >= Vp
-  __nv_bfloat16* hid_hi;      // [rows_pad, ldh]  act(f+g) split hi/lo; column H holds 1.0 (bias-gradient trick)
+  __nv_bfloat16* hid_hi;      // [rows_pad, ldh]  act(f+g) split hi/lo
   __nv_bfloat16* hid_lo;
-  int ldh;                    // H + 8
+  int ldh;                    // H
+  float* db_acc;              // [Vp] bias gradient: column sums of dZ, accumulated by the pass-2 epilogue (zeroed first)
   int* rows_pad_dev;          // [1] total_tiles * 128 (written by the tile-offset kernel)
 };
 
@@ -420,6 +421,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 32; ++j) gr[j] = fmaxf(fminf(gr[j], p.clamp), -p.clamp);
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gr[j] *= go;
             __nv_bfloat16* dh = p.dz_hi + grow * p.ldz + col0;
             __nv_bfloat16* dl = p.dz_lo + grow * p.ldz + col0;
 #pragma unroll
@@ -428,7 +431,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
                 uint32_t ph[4], pl[4];
 #pragma unroll
                 for (int j2 = 0; j2 < 4; ++j2) {
-                  const float g0 = gr[j8 + 2 * j2] * go, g1 = gr[j8 + 2 * j2 + 1] * go;
+                  const float g0 = gr[j8 + 2 * j2], g1 = gr[j8 + 2 * j2 + 1];
                   __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
                   __nv_bfloat162 ll = __floats2bfloat162_rn(g0 - __low2float(hh), g1 - __high2float(hh));
                   ph[j2] = *reinterpret_cast<uint32_t*>(&hh);
@@ -438,6 +441,19 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
                 if (kTerms > 1) *reinterpret_cast<uint4*>(dl + j8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
               }
             }
+            // bias gradient d_b[v] = sum over cells of dZ[., v]: transpose-reduce the warp's 32 rows x 32 columns with
+            // 31 shuffles (lane l ends up with the column-(col0 + l) sum), then one coalesced fp32 RED per warp
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int j = 0; j < off; ++j) {
+                const float send = up ? gr[j] : gr[j + off];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+                gr[j] = (up ? gr[j + off] : gr[j]) + recv;
+              }
+            }
+            if (col0 + lane < p.Vp) atomicAdd(p.db_acc + col0 + lane, gr[0]);
           }
         }
         tc::tc_fence_before();
@@ -535,11 +551,6 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             const int k = kb * kJK + half * 32 + 2 * c;
             *reinterpret_cast<uint32_t*>(p.hid_hi + go2 + k) = hw;
             if (kTerms > 1) *reinterpret_cast<uint32_t*>(p.hid_lo + go2 + k) = lw;
-            if (kb == 0 && half == 0 && c < 4) {  // columns [H, H+8): a column of ones (valid rows) then zeros
-              const uint32_t one = (ok && c == 0) ? 0x00003f80u : 0u;  // bf16(1.0) in the low half
-              *reinterpret_cast<uint32_t*>(p.hid_hi + go2 + p.H + 2 * c) = one;
-              if (kTerms > 1) *reinterpret_cast<uint32_t*>(p.hid_lo + go2 + p.H + 2 * c) = 0u;
-            }
           }
         }
       };
@@ -650,14 +661,6 @@ __global__ void __launch_bounds__(256) joint_dfg_kernel(const float* __restrict_
   }
 }
 
-// dW_ext [Vp, H+8] -> d_w [Vp, H], d_b [Vp] (column H of dW_ext = dZ^T . 1)
-__global__ void joint_dw_finish_kernel(const float* __restrict__ dw_ext, int Vp, int H, int ld,
-                                       float* __restrict__ d_w, float* __restrict__ d_b) {
-  const int v = blockIdx.x;
-  for (int k = threadIdx.x; k < H; k += blockDim.x) d_w[(int64_t)v * H + k] = dw_ext[(int64_t)v * ld + k];
-  if (threadIdx.x == 0) d_b[v] = dw_ext[(int64_t)v * ld + H];
-}
-
 int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
                    int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
                    int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias = nullptr);
@@ -683,7 +686,6 @@ struct JointBwdScratch {
   void* dz_hi; void* dz_lo;     // [rows_cap, ldz] bf16
   void* hid_hi; void* hid_lo;   // [rows_cap, ldh] bf16
   float* dhid;                  // [rows_cap, H]
-  float* dw_ext;                // [Vp, ldh]
   int64_t rows_cap;
   int ldz, ldh;
   size_t total;
@@ -694,7 +696,7 @@ static inline JointBwdScratch joint_bwd_scratch_carve(void* base, int B, int T, 
   const bool x3 = precision == CLASR_PREC_BF16X3;
   sc.rows_cap = (int64_t)B * ((((int64_t)T * U1) + kJM - 1) / kJM) * kJM;
   sc.ldz = (Vp + 7) / 8 * 8;
-  sc.ldh = H + 8;
+  sc.ldh = H;
   char* p = (char*)base;
   size_t off = 0;
   auto take = [&](size_t bytes) { void* r = p + off; off += (bytes + 255) / 256 * 256; return r; };
@@ -703,7 +705,6 @@ static inline JointBwdScratch joint_bwd_scratch_carve(void* base, int B, int T, 
   sc.hid_hi = take((size_t)sc.rows_cap * sc.ldh * 2);
   sc.hid_lo = x3 ? take((size_t)sc.rows_cap * sc.ldh * 2) : sc.hid_hi;
   sc.dhid = (float*)take((size_t)sc.rows_cap * H * 4);
-  sc.dw_ext = (float*)take((size_t)Vp * sc.ldh * 4);
   sc.total = off;
   return sc;
 }
@@ -905,6 +906,12 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   p.dz_hi = (__nv_bfloat16*)sc.dz_hi; p.dz_lo = (__nv_bfloat16*)sc.dz_lo; p.ldz = sc.ldz;
   p.hid_hi = (__nv_bfloat16*)sc.hid_hi; p.hid_lo = (__nv_bfloat16*)sc.hid_lo; p.ldh = sc.ldh;
   p.rows_pad_dev = rows_pad_dev;
+  p.db_acc = d_b_out;
+  {  // d_b accumulates in the pass-2a epilogue, d_W in the split-K GEMM: both start from zero
+    cudaError_t e1 = cudaMemsetAsync(d_b_out, 0, (size_t)Vp * sizeof(float), s);
+    cudaError_t e2 = cudaMemsetAsync(d_w_out, 0, (size_t)Vp * H * sizeof(float), s);
+    CLASR_CHECK_ARG(e1 == cudaSuccess && e2 == cudaSuccess, "joint_rnnt_bwd: memset failed");
+  }
   CUtensorMap tw_hi, tw_lo;
   const int bn = joint_use_pair() ? (x3 ? JointCfg<3, 1>::kBRows : JointCfg<1, 1>::kBRows)
                                   : (x3 ? JointCfg<3, 0>::kBRows : JointCfg<1, 0>::kBRows);
@@ -931,20 +938,12 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
                            precision, 0, 1, s, rows_pad_dev, nullptr)))
     return rc;
   prof_end("gemm_dhid", s);
-  // ---- pass 2c: dW_ext[Vp, H+8] = dZ^T . [Hid | 1 | 0]       (both operands MN-major, split-K over the rows)
-  cudaError_t e = cudaMemsetAsync(sc.dw_ext, 0, (size_t)Vp * sc.ldh * sizeof(float), s);
-  CLASR_CHECK_ARG(e == cudaSuccess, "joint_rnnt_bwd: memset failed");
-  {
-    const int mn_tiles = ((Vp + 127) / 128) * ((sc.ldh + 255) / 256);
-    int splits = (2 * kNumSMs + mn_tiles - 1) / mn_tiles;
-    prof_begin("gemm_dw", s);
-    if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, sc.hid_hi, sc.hid_lo, sc.ldh, 1, Vp, sc.ldh,
-                             (int)sc.rows_cap, sc.dw_ext, sc.ldh, precision, 1, splits, s, nullptr, rows_pad_dev)))
-      return rc;
-    prof_end("gemm_dw", s);
-  }
-  joint_dw_finish_kernel<<<Vp, 128, 0, s>>>(sc.dw_ext, Vp, H, sc.ldh, d_w_out, d_b_out);
-  CLASR_CHECK_LAUNCH("joint_dw_finish");
+  // ---- pass 2c: dW[Vp, H] = dZ^T . Hid       (both operands MN-major, split-K over the rows, fp32 atomics)
+  prof_begin("gemm_dw", s);
+  if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, sc.hid_hi, sc.hid_lo, sc.ldh, 1, Vp, H, (int)sc.rows_cap,
+                           d_w_out, H, precision, 1, /*auto split-K*/ 0, s, nullptr, rows_pad_dev)))
+    return rc;
+  prof_end("gemm_dw", s);
   // ---- pass 2d: through the activation and the broadcast add
   prof_begin("joint_dfg", s);
   joint_dfg_kernel<<<dim3(T, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
