@@ -661,6 +661,75 @@ __global__ void __launch_bounds__(256) joint_dfg_kernel(const float* __restrict_
   }
 }
 
+// Single-pass variant: a block owns (utterance b, 32-wide slice of H, chunk of 32 time steps) and reads each dHid
+// element ONCE (128-byte row segments, 8 loads in flight per warp, 8 blocks per SM): d_f[t] accumulates in registers
+// over the consecutive u rows, d_g[u] in a shared-memory tile via shared atomics (8 warps = 8 different t), flushed
+// with one global RED per element per block (d_g is zeroed first).  act' comes from the exp factors:
+// tanh' = 4 r (1 - r), sigmoid' = r (1 - r) with r = 1 / (1 + e_f e_g); relu' = [f + g > 0].
+constexpr int kDfgTChunk = 32;
+template <int kAct>
+__global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __restrict__ dhid,
+                                                              const float* __restrict__ ef,
+                                                              const float* __restrict__ eg,
+                                                              const int64_t* __restrict__ act_lens,
+                                                              const int64_t* __restrict__ label_lens,
+                                                              const int* __restrict__ tile_offsets, int T, int U1, int H,
+                                                              float* __restrict__ d_f, float* __restrict__ d_g) {
+  extern __shared__ float sm_dfg[];
+  const int b = blockIdx.y, k0 = blockIdx.x * 32, t_begin = blockIdx.z * kDfgTChunk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int Tb = (int)act_lens[b], Ub1 = (int)label_lens[b] + 1;
+  const int t_end = min(T, t_begin + kDfgTChunk);
+  const int64_t row0 = (int64_t)tile_offsets[b] * kJM;
+  float* eg_s = sm_dfg;            // [U1][32]
+  float* dg_s = sm_dfg + U1 * 32;  // [U1][32]
+  const bool live = t_begin < Tb;  // block-uniform
+  if (live) {
+    for (int i = threadIdx.x; i < U1 * 32; i += blockDim.x) {
+      const int u = i >> 5;
+      eg_s[i] = u < Ub1 ? __ldg(eg + ((int64_t)b * U1 + u) * H + k0 + (i & 31)) : 0.f;
+      dg_s[i] = 0.f;
+    }
+    __syncthreads();
+  }
+  auto dact = [](float a, float bb) -> float {
+    if (kAct == CLASR_ACT_RELU) return (a + bb) > 0.f ? 1.f : 0.f;
+    const float r = __fdividef(1.f, fmaf(a, bb, 1.f));
+    const float t1 = fmaf(-r, r, r);
+    return kAct == CLASR_ACT_TANH ? 4.f * t1 : t1;
+  };
+  for (int t = t_begin + warp; t < t_end; t += nw) {
+    float df = 0.f;
+    if (t < Tb) {
+      const float fv = __ldg(ef + ((int64_t)b * T + t) * H + k0 + lane);
+      const float* dp = dhid + (row0 + (int64_t)t * Ub1) * H + k0 + lane;
+      int u = 0;
+      for (; u + 8 <= Ub1; u += 8) {
+        float d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = ld_stream1(dp + (int64_t)(u + j) * H);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pv = d[j] * dact(fv, eg_s[(u + j) * 32 + lane]);
+          df += pv;
+          atomicAdd(dg_s + (u + j) * 32 + lane, pv);
+        }
+      }
+      for (; u < Ub1; ++u) {
+        const float pv = ld_stream1(dp + (int64_t)u * H) * dact(fv, eg_s[u * 32 + lane]);
+        df += pv;
+        atomicAdd(dg_s + u * 32 + lane, pv);
+      }
+    }
+    d_f[((int64_t)b * T + t) * H + k0 + lane] = df;
+  }
+  if (live) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < Ub1 * 32; i += blockDim.x)
+      atomicAdd(d_g + ((int64_t)b * U1 + (i >> 5)) * H + k0 + (i & 31), dg_s[i]);
+  }
+}
+
 int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
                    int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
                    int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias = nullptr);
@@ -944,15 +1013,37 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
                            d_w_out, H, precision, 1, /*auto split-K*/ 0, s, nullptr, rows_pad_dev)))
     return rc;
   prof_end("gemm_dw", s);
-  // ---- pass 2d: through the activation and the broadcast add
+  // ---- pass 2d: through the activation and the broadcast add: d_f = sum_u, d_g = sum_t of dHid * act'(f+g)
   prof_begin("joint_dfg", s);
-  joint_dfg_kernel<<<dim3(T, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
-                                             activation, 0, d_f);
-  CLASR_CHECK_LAUNCH("joint_df");
-  joint_dfg_kernel<<<dim3(U1, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
-                                              activation, 1, d_g);
+  {
+    const size_t smem = (size_t)2 * U1 * 32 * sizeof(float);
+    if (smem <= 200 * 1024 && (H % 32) == 0) {
+      const float* ef_ = activation == CLASR_ACT_RELU ? f : jw.ef;
+      const float* eg_ = activation == CLASR_ACT_RELU ? g : jw.eg;
+      cudaError_t e0 = cudaMemsetAsync(d_g, 0, (size_t)B * U1 * H * sizeof(float), s);
+      CLASR_CHECK_ARG(e0 == cudaSuccess, "joint_rnnt_bwd: memset failed");
+      const dim3 grid(H / 32, B, (T + kDfgTChunk - 1) / kDfgTChunk);
+#define CLASR_LAUNCH_DFG(ACT)                                                                                      \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(joint_dfg_fused_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    joint_dfg_fused_kernel<ACT><<<grid, 256, smem, s>>>(sc.dhid, ef_, eg_, act_lens, label_lens, jw.tile_offsets,  \
+                                                        T, U1, H, d_f, d_g);                                       \
+  } while (0)
+      if (activation == CLASR_ACT_RELU) CLASR_LAUNCH_DFG(CLASR_ACT_RELU);
+      else if (activation == CLASR_ACT_SIGMOID) CLASR_LAUNCH_DFG(CLASR_ACT_SIGMOID);
+      else CLASR_LAUNCH_DFG(CLASR_ACT_TANH);
+#undef CLASR_LAUNCH_DFG
+      CLASR_CHECK_LAUNCH("joint_dfg_fused");
+    } else {  // very long label sequences: the two-pass kernel (reads dHid twice, no shared-memory partials)
+      joint_dfg_kernel<<<dim3(T, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
+                                                 activation, 0, d_f);
+      CLASR_CHECK_LAUNCH("joint_df");
+      joint_dfg_kernel<<<dim3(U1, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
+                                                  activation, 1, d_g);
+      CLASR_CHECK_LAUNCH("joint_dg");
+    }
+  }
   prof_end("joint_dfg", s);
-  CLASR_CHECK_LAUNCH("joint_dg");
   return CLASR_STATUS_SUCCESS;
 }
 
