@@ -107,6 +107,7 @@ struct GemmParams {
   const int* m_dev;  // optional device-side M (<= M): lets a ragged row count stay on the device (no host sync)
   const int* k_dev;  // optional device-side K (<= K)
   const float* bias; // optional [N]: C = acc + bias[n] (non-atomic epilogue only)
+  int group_n;       // pair kernel, no split-K: walk all N tiles of a row block back to back
 };
 
 template <int kTerms>
@@ -340,6 +341,17 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int kb_per_split = max(1, (kb_total + p.k_splits - 1) / p.k_splits);
   const int k_splits = max(1, (kb_total + kb_per_split - 1) / kb_per_split);
   const int num_tiles = mn_tiles * k_splits;
+  // Work order.  Default: tile ids round-robin over the pairs, so the N tiles of one 256-row block run CONCURRENTLY on
+  // neighbouring pairs (the A rows are fetched from HBM once, the other pairs hit under the miss).  group_n = 1 walks
+  // them back to back on ONE pair instead; measured slower (dHid 2.66 vs 2.55 ms: one tile in three pays the full HBM
+  // miss latency that the 3-stage ring cannot hide), kept as a switch (CLASR_GEMM_GROUP=1).
+  const int group = (k_splits == 1 && p.group_n) ? n_tiles : 1;
+  const int num_groups = (num_tiles + group - 1) / group;
+  auto tile_at = [&](int it) -> int {
+    const int g = pair + (it / group) * num_pairs;
+    const int t = g * group + it % group;
+    return (g < num_groups && t < num_tiles) ? t : -1;
+  };
 
   if (warp == 0 && tc::elect_one()) {
     tc::prefetch_tmap(&tmA_hi);
@@ -365,7 +377,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     // ================= TMA producer (both CTAs: own A rows, own half of B; bytes land on the leader's barrier) ====
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    for (int wi = 0, tile; (tile = tile_at(wi)) >= 0; ++wi) {
       const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
       const int m0 = (mn / n_tiles) * kPM + (int)cta_rank * kBM;
       const int nbase = (mn % n_tiles) * kBN;
@@ -408,7 +420,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+    for (int tile; (tile = tile_at(it)) >= 0; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
@@ -455,7 +467,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     // ================= epilogue (both CTAs: own 128 accumulator rows) =================
     const int q = warp & 3;
     int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+    for (int tile; (tile = tile_at(it)) >= 0; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int mn = tile % mn_tiles;
@@ -558,7 +570,9 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
     set_error("gemm_tc: split-K needs atomic accumulation");
     return CLASR_STATUS_INVALID_VALUE;
   }
-  GemmParams p{M, N, K, C, ldc, atomic_add, k_splits, a_mn, b_mn, m_dev, k_dev, atomic_add ? nullptr : bias};
+  const char* ge = getenv("CLASR_GEMM_GROUP");
+  GemmParams p{M, N, K, C, ldc, atomic_add, k_splits, a_mn, b_mn, m_dev, k_dev, atomic_add ? nullptr : bias,
+               ge ? atoi(ge) : 0};
   if (use_pair) {
     const int tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN) * k_splits;
     int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;

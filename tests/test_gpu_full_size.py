@@ -75,3 +75,47 @@ def test_full_size_gradients_and_properties():
     # blank mass: each alignment emits exactly T_b blanks => sum over cells of dZ[., blank] = sum_b w_b (E[#blank] - T_b)
     # with E[#blank] = sum of blank posteriors, which the softmax part reproduces; only sign/finite checks here
     assert torch.isfinite(d_W).all() and d_b[V].item() < 0.0
+
+
+def _generic_costs(f, g, W, b, lab, al, ll, V, act, sub=2):
+    loss = RNNTLossNumba(blank=V, reduction="none")
+    fn = {"tanh": torch.tanh, "relu": torch.relu}[act]
+    out = []
+    for b0 in range(0, f.shape[0], sub):
+        sl = slice(b0, b0 + sub)
+        mt, mu = int(al[sl].max()), int(ll[sl].max())
+        z = torch.nn.functional.linear(fn(f[sl, :mt].unsqueeze(2) + g[sl, : mu + 1].unsqueeze(1)), W, b)
+        out.append(loss(z, lab[sl, :mu].contiguous(), al[sl], ll[sl]))
+    return torch.cat(out)
+
+
+@pytest.mark.parametrize("name,B,T_,U_,V_,act,precision,ltol,gtol", [
+    # configs[2]: IndicConformer-medium shapes (16 s audio -> T'~400, per-language vocabulary 256, ReLU joint)
+    ("config3", 4, 400, 80, 256, "relu", "bf16x3", 1e-5, 1e-4),
+    # configs[4]: V=4096 multilingual tokenizer, T=500, U=200, bf16 joint GEMM (single MMA term: bf16 tolerances)
+    ("config5", 2, 500, 200, 4096, "tanh", "bf16", 2e-3, 3e-2),
+])
+def test_other_config_shapes_fused_vs_materialised(name, B, T_, U_, V_, act, precision, ltol, gtol):
+    g = torch.Generator().manual_seed(17)
+    f = (torch.randn(B, T_, H, generator=g) * 0.7).to(DEV)
+    gg = (torch.randn(B, U_ + 1, H, generator=g) * 0.7).to(DEV)
+    W = ((torch.rand(V_ + 1, H, generator=g) * 2 - 1) / H ** 0.5).to(DEV)
+    b = ((torch.rand(V_ + 1, generator=g) * 2 - 1) / H ** 0.5).to(DEV)
+    lab = torch.randint(0, V_, (B, U_), generator=g).to(DEV)
+    al = torch.randint(T_ // 2, T_ + 1, (B,), generator=g); al[0] = T_
+    ll = torch.randint(U_ // 2, U_ + 1, (B,), generator=g); ll[0] = U_
+    al, ll = al.to(DEV), ll.to(DEV)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        leaves = [x.clone().requires_grad_(True) for x in (f, gg, W, b)]
+        costs = fused_joint_rnnt_loss(*leaves, lab, al, ll, V_, act, precision)
+        costs.sum().backward()
+        ref_leaves = [x.clone().requires_grad_(True) for x in (f, gg, W, b)]
+        ref = _generic_costs(*ref_leaves, lab, al, ll, V_, act)
+        ref.sum().backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert ((costs - ref).abs() <= ltol * ref.abs()).all(), ((costs - ref).abs() / ref.abs()).max().item()
+    for nm, got, rf in zip(["d_f", "d_g", "d_W", "d_b"], leaves, ref_leaves):
+        assert rel_err(got.grad.cpu().numpy(), rf.grad.cpu().numpy()) <= gtol, (name, nm)
