@@ -78,6 +78,7 @@ struct JointFwdParams {
   __nv_bfloat16* hid_hi;      // [rows_pad, ldh]  act(f+g) split hi/lo
   __nv_bfloat16* hid_lo;
   int ldh;                    // H
+  float* dzb;                 // [rows_pad] dZ[., blank] per compact row (feeds the blank row of dW in joint_dfg), or null
   float* db_acc;              // [Vp] bias gradient: column sums of dZ, accumulated by the pass-2 epilogue (zeroed first)
   int* rows_pad_dev;          // [1] total_tiles * 128 (written by the tile-offset kernel)
 };
@@ -423,6 +424,13 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) gr[j] *= go;
+            if (p.dzb && p.blank >= col0 && p.blank < col0 + 32) {
+              float zb_ = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j == p.blank) zb_ = gr[j];
+              p.dzb[grow] = zb_;
+            }
             __nv_bfloat16* dh = p.dz_hi + grow * p.ldz + col0;
             __nv_bfloat16* dl = p.dz_lo + grow * p.ldz + col0;
 #pragma unroll
@@ -674,7 +682,9 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
                                                               const int64_t* __restrict__ act_lens,
                                                               const int64_t* __restrict__ label_lens,
                                                               const int* __restrict__ tile_offsets, int T, int U1, int H,
-                                                              float* __restrict__ d_f, float* __restrict__ d_g) {
+                                                              float* __restrict__ d_f, float* __restrict__ d_g,
+                                                              const float* __restrict__ dzb,
+                                                              float* __restrict__ d_w_blank) {
   extern __shared__ float sm_dfg[];
   const int b = blockIdx.y, k0 = blockIdx.x * 32, t_begin = blockIdx.z * kDfgTChunk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -692,37 +702,59 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
     }
     __syncthreads();
   }
-  auto dact = [](float a, float bb) -> float {
-    if (kAct == CLASR_ACT_RELU) return (a + bb) > 0.f ? 1.f : 0.f;
+  // (hidden activation, its derivative) from the exp factors
+  auto act_pair = [](float a, float bb, float& h, float& dh) {
+    if (kAct == CLASR_ACT_RELU) {
+      const float x = a + bb;
+      h = fmaxf(x, 0.f);
+      dh = x > 0.f ? 1.f : 0.f;
+      return;
+    }
     const float r = __fdividef(1.f, fmaf(a, bb, 1.f));
     const float t1 = fmaf(-r, r, r);
-    return kAct == CLASR_ACT_TANH ? 4.f * t1 : t1;
+    if (kAct == CLASR_ACT_TANH) { h = fmaf(-2.f, r, 1.f); dh = 4.f * t1; }
+    else { h = r; dh = t1; }
   };
+  // dW[blank, k] = sum over cells of dZ[cell, blank] * hid[cell, k]: the blank is the (V+1)-th class, a 1025th GEMM row
+  // that would cost a whole extra 256-row tile in the dW GEMM; here it is one FMA per element on data already in flight
+  float wb = 0.f;
   for (int t = t_begin + warp; t < t_end; t += nw) {
     float df = 0.f;
     if (t < Tb) {
       const float fv = __ldg(ef + ((int64_t)b * T + t) * H + k0 + lane);
-      const float* dp = dhid + (row0 + (int64_t)t * Ub1) * H + k0 + lane;
+      const int64_t r0 = row0 + (int64_t)t * Ub1;
+      const float* dp = dhid + r0 * H + k0 + lane;
       int u = 0;
       for (; u + 8 <= Ub1; u += 8) {
-        float d[8];
+        float d[8], zb[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = ld_stream1(dp + (int64_t)(u + j) * H);
+        if (dzb) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) zb[j] = __ldg(dzb + r0 + u + j);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float pv = d[j] * dact(fv, eg_s[(u + j) * 32 + lane]);
+          float h, dh;
+          act_pair(fv, eg_s[(u + j) * 32 + lane], h, dh);
+          const float pv = d[j] * dh;
           df += pv;
           atomicAdd(dg_s + (u + j) * 32 + lane, pv);
+          if (dzb) wb = fmaf(zb[j], h, wb);
         }
       }
       for (; u < Ub1; ++u) {
-        const float pv = ld_stream1(dp + (int64_t)u * H) * dact(fv, eg_s[u * 32 + lane]);
+        float h, dh;
+        act_pair(fv, eg_s[u * 32 + lane], h, dh);
+        const float pv = ld_stream1(dp + (int64_t)u * H) * dh;
         df += pv;
         atomicAdd(dg_s + u * 32 + lane, pv);
+        if (dzb) wb = fmaf(__ldg(dzb + r0 + u), h, wb);
       }
     }
     d_f[((int64_t)b * T + t) * H + k0 + lane] = df;
   }
+  if (dzb && live) atomicAdd(d_w_blank + k0 + lane, wb);
   if (live) {
     __syncthreads();
     for (int i = threadIdx.x; i < Ub1 * 32; i += blockDim.x)
@@ -755,6 +787,7 @@ struct JointBwdScratch {
   void* dz_hi; void* dz_lo;     // [rows_cap, ldz] bf16
   void* hid_hi; void* hid_lo;   // [rows_cap, ldh] bf16
   float* dhid;                  // [rows_cap, H]
+  float* dzb;                   // [rows_cap]
   int64_t rows_cap;
   int ldz, ldh;
   size_t total;
@@ -774,6 +807,7 @@ static inline JointBwdScratch joint_bwd_scratch_carve(void* base, int B, int T, 
   sc.hid_hi = take((size_t)sc.rows_cap * sc.ldh * 2);
   sc.hid_lo = x3 ? take((size_t)sc.rows_cap * sc.ldh * 2) : sc.hid_hi;
   sc.dhid = (float*)take((size_t)sc.rows_cap * H * 4);
+  sc.dzb = (float*)take((size_t)sc.rows_cap * 4);
   sc.total = off;
   return sc;
 }
@@ -975,6 +1009,10 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   p.dz_hi = (__nv_bfloat16*)sc.dz_hi; p.dz_lo = (__nv_bfloat16*)sc.dz_lo; p.ldz = sc.ldz;
   p.hid_hi = (__nv_bfloat16*)sc.hid_hi; p.hid_lo = (__nv_bfloat16*)sc.hid_lo; p.ldh = sc.ldh;
   p.rows_pad_dev = rows_pad_dev;
+  // blank == last class (NeMo: RNNTLoss._blank = num_classes): its dW row comes from joint_dfg, the GEMM covers V rows
+  const bool blank_split = blank == Vp - 1 && Vp > 1 && (H % 32) == 0 &&
+                           (size_t)2 * U1 * 32 * sizeof(float) <= 200 * 1024;
+  p.dzb = blank_split ? sc.dzb : nullptr;
   p.db_acc = d_b_out;
   {  // d_b accumulates in the pass-2a epilogue, d_W in the split-K GEMM: both start from zero
     cudaError_t e1 = cudaMemsetAsync(d_b_out, 0, (size_t)Vp * sizeof(float), s);
@@ -1009,8 +1047,8 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   prof_end("gemm_dhid", s);
   // ---- pass 2c: dW[Vp, H] = dZ^T . Hid       (both operands MN-major, split-K over the rows, fp32 atomics)
   prof_begin("gemm_dw", s);
-  if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, sc.hid_hi, sc.hid_lo, sc.ldh, 1, Vp, H, (int)sc.rows_cap,
-                           d_w_out, H, precision, 1, /*auto split-K*/ 0, s, nullptr, rows_pad_dev)))
+  if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, sc.hid_hi, sc.hid_lo, sc.ldh, 1, blank_split ? Vp - 1 : Vp, H,
+                           (int)sc.rows_cap, d_w_out, H, precision, 1, /*auto split-K*/ 0, s, nullptr, rows_pad_dev)))
     return rc;
   prof_end("gemm_dw", s);
   // ---- pass 2d: through the activation and the broadcast add: d_f = sum_u, d_g = sum_t of dHid * act'(f+g)
@@ -1027,7 +1065,8 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   do {                                                                                                             \
     cudaFuncSetAttribute(joint_dfg_fused_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     joint_dfg_fused_kernel<ACT><<<grid, 256, smem, s>>>(sc.dhid, ef_, eg_, act_lens, label_lens, jw.tile_offsets,  \
-                                                        T, U1, H, d_f, d_g);                                       \
+                                                        T, U1, H, d_f, d_g, blank_split ? sc.dzb : nullptr,        \
+                                                        d_w_out + (size_t)blank * H);                              \
   } while (0)
       if (activation == CLASR_ACT_RELU) CLASR_LAUNCH_DFG(CLASR_ACT_RELU);
       else if (activation == CLASR_ACT_SIGMOID) CLASR_LAUNCH_DFG(CLASR_ACT_SIGMOID);
