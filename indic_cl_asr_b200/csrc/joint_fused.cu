@@ -33,7 +33,6 @@ constexpr int kJMaxH = 640;         // A tile (128 x H bf16) must stay resident 
 constexpr int kJThreads = 512;      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue, 8-15 A producers
 constexpr int kJProducerWarps = 8;
 constexpr int kJStages = 2;
-constexpr float kJExpClamp = 43.f;  // |pre-activation| clamp of the exp factorisation: exp(2*43) is finite in fp32
 
 // kPair = 1: two CTAs of a cluster (one TPC) run each tcgen05.mma together (cta_group::2, M = 256 = two 128-row tiles):
 // every CTA keeps its own A tile (smem hi / TMEM lo) and loads only HALF of each W tile, so the W ring holds twice as
@@ -57,7 +56,7 @@ struct JointCfg {
 };
 
 struct JointFwdParams {
-  const float* ef;     // [B,T,H]   activation factor of f (relu: f itself; tanh: exp(2f); sigmoid: exp(-f))
+  const float* ef;     // [B,T,H]   scaled pre-activation of f (relu: f itself; tanh: 2 log2e f; sigmoid: -log2e f)
   const float* eg;     // [B,U1,H]  same for g
   const float* bias;   // [Vp]
   const float* bias_pad;  // [round_up(Vp, 32) + 32] zero-padded copy of bias (vector loads in the pass-2 epilogue)
@@ -94,19 +93,17 @@ __device__ __forceinline__ float joint_act(float x, int act) {
 }
 
 // The A operand act(f[t,k] + g[u,k]) is needed for every lattice cell (t,u): 81 920 activations per 128-row tile.
-// exp factorises over the sum, so the transcendental is hoisted out of the T x U product space:
-//   tanh(a+b)    = 1 - 2 / (1 + e^{2a} e^{2b})        sigmoid(a+b) = 1 / (1 + e^{-a} e^{-b})
-// joint_prep_kernel evaluates the factors once per (t,k) and (u,k) with full-precision expf (7 M instead of 517 M
-// exponentials at B=32,T=250,U=100,H=640); the producers then spend one FMA + one MUFU.RCP (+1 FMA) per element.
-// Pre-activations are clamped to +-43 so that the factors stay finite (tanh/sigmoid are saturated to < 1e-37 there).
+// The argument scaling of the exponential is hoisted out of the T x U product space: joint_prep_kernel stores
+//   sf = c f,  sg = c g   with c = 2 log2(e) for tanh, -log2(e) for sigmoid   (relu reads f, g themselves)
+// so that per element   tanh(a+b) = 1 - 2 / (1 + 2^(sf+sg)),   sigmoid(a+b) = 1 / (1 + 2^(sf+sg))
+// costs FADD + MUFU.EX2 + FADD + MUFU.RCP (+ FFMA), with IEEE saturation for any input (2^x -> inf / 0, 1/inf = 0):
+// no clamping, no special cases.  (An earlier version multiplied pre-computed exp factors e^{2f} e^{2g}; that saves one
+// MUFU but needs |f|, |g| clamped to stay finite, which is wrong when a large f meets a large -g.)
 __global__ void joint_prep_kernel(const float* __restrict__ x, float* __restrict__ e, int64_t n4, int act) {
-  const float s = act == CLASR_ACT_TANH ? 2.f : -1.f;
+  const float c = act == CLASR_ACT_TANH ? 2.885390081777927f : -1.4426950408889634f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(x)[i];
-    v.x = expf(s * fminf(fmaxf(v.x, -kJExpClamp), kJExpClamp));
-    v.y = expf(s * fminf(fmaxf(v.y, -kJExpClamp), kJExpClamp));
-    v.z = expf(s * fminf(fmaxf(v.z, -kJExpClamp), kJExpClamp));
-    v.w = expf(s * fminf(fmaxf(v.w, -kJExpClamp), kJExpClamp));
+    v.x *= c; v.y *= c; v.z *= c; v.w *= c;
     reinterpret_cast<float4*>(e)[i] = v;
   }
 }
@@ -114,7 +111,7 @@ __global__ void joint_prep_kernel(const float* __restrict__ x, float* __restrict
 template <int kAct>
 __device__ __forceinline__ float joint_combine(float a, float b) {
   if (kAct == CLASR_ACT_RELU) return fmaxf(a + b, 0.f);
-  const float r = __fdividef(1.f, fmaf(a, b, 1.f));  // MUFU.RCP; 0 for a*b >= 2^126 (saturated)
+  const float r = tc::rcp_approx(1.f + tc::ex2_approx(a + b));  // 1 + 2^x >= 1; +inf -> 0
   if (kAct == CLASR_ACT_SIGMOID) return r;
   return fmaf(-2.f, r, 1.f);
 }
@@ -672,8 +669,8 @@ __global__ void __launch_bounds__(256) joint_dfg_kernel(const float* __restrict_
 // Single-pass variant: a block owns (utterance b, 32-wide slice of H, chunk of 32 time steps) and reads each dHid
 // element ONCE (128-byte row segments, 8 loads in flight per warp, 8 blocks per SM): d_f[t] accumulates in registers
 // over the consecutive u rows, d_g[u] in a shared-memory tile via shared atomics (8 warps = 8 different t), flushed
-// with one global RED per element per block (d_g is zeroed first).  act' comes from the exp factors:
-// tanh' = 4 r (1 - r), sigmoid' = r (1 - r) with r = 1 / (1 + e_f e_g); relu' = [f + g > 0].
+// with one global RED per element per block (d_g is zeroed first).  act' comes from the scaled pre-activations:
+// tanh' = 4 r (1 - r), sigmoid' = r (1 - r) with r = 1 / (1 + 2^(sf+sg)); relu' = [f + g > 0].
 constexpr int kDfgTChunk = 32;
 template <int kAct>
 __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __restrict__ dhid,
@@ -702,7 +699,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
     }
     __syncthreads();
   }
-  // (hidden activation, its derivative) from the exp factors
+  // (hidden activation, its derivative) from the scaled pre-activations
   auto act_pair = [](float a, float bb, float& h, float& dh) {
     if (kAct == CLASR_ACT_RELU) {
       const float x = a + bb;
@@ -710,7 +707,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
       dh = x > 0.f ? 1.f : 0.f;
       return;
     }
-    const float r = __fdividef(1.f, fmaf(a, bb, 1.f));
+    const float r = tc::rcp_approx(1.f + tc::ex2_approx(a + bb));
     const float t1 = fmaf(-r, r, r);
     if (kAct == CLASR_ACT_TANH) { h = fmaf(-2.f, r, 1.f); dh = 4.f * t1; }
     else { h = r; dh = t1; }
@@ -775,7 +772,7 @@ struct JointWs {
   void* w_lo;
   int* tile_offsets;   // [B+1], then [1] rows_pad
   float* bias_pad;     // [round_up(Vp,32)+32]
-  float* ef;           // [B,T,H]  exp factor of f (tanh / sigmoid; relu reads f directly)
+  float* ef;           // [B,T,H]  scaled pre-activation c*f (tanh / sigmoid; relu reads f directly)
   float* eg;           // [B,U1,H]
   int vp_pad;
   size_t total;
@@ -878,7 +875,7 @@ static int launch_joint_kernel(int activation, int H, const CUtensorMap& tw_hi, 
 #undef CLASR_LAUNCH_JOINT
 }
 
-// exp factors of the activation (see joint_prep_kernel); relu needs none
+// scaled pre-activations (see joint_prep_kernel); relu needs none
 static int launch_joint_prep(const float* f, const float* g, int B, int T, int U1, int H, int activation,
                              const JointWs& jw, const float** ef, const float** eg, cudaStream_t s) {
   if (activation == CLASR_ACT_RELU) {
@@ -998,7 +995,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
 
   // ---- pass 2a: recompute logits tile-wise, emit dZ (bf16 hi/lo) and the hidden activations as GEMM operands
   JointFwdParams p = {};
-  // the exp factors were written into the workspace by the forward call (relu: f / g themselves)
+  // the scaled pre-activations were written into the workspace by the forward call (relu: f / g themselves)
   p.ef = activation == CLASR_ACT_RELU ? f : jw.ef;
   p.eg = activation == CLASR_ACT_RELU ? g : jw.eg;
   p.bias = b_out; p.bias_pad = jw.bias_pad; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;

@@ -42,6 +42,12 @@ __device__ __forceinline__ int2 ld_shared_i2(uint32_t addr) {
   return r;
 }
 
+// 1 / x for x >= 1 (no denormal handling needed): a single MUFU.RCP instead of __fdividef's 5-instruction sequence
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

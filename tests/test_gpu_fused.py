@@ -69,3 +69,43 @@ def test_backward(B, T, U, V, H, act, precision):
     (oc * wts.double()).sum().backward()
     for name, got, ref in zip(["d_f", "d_g", "d_W", "d_b"], (fd, gd, Wd, bd), leaves):
         assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy()) <= GRAD_TOL[precision], name
+
+
+@pytest.mark.parametrize("act", ["tanh", "sigmoid", "relu"])
+def test_saturated_preactivations(act):
+    """|f|, |g| far beyond the range where exp() is finite, with opposite signs meeting: the activation must
+    saturate exactly like the fp64 oracle (no clamping of the individual projections)."""
+    B, T, U, V, H = 2, 12, 5, 30, 64
+    f, g, W, b, lab, al, ll = make(B, T, U, V, H, seed=99, ragged=False)
+    f = f * 60.0          # pre-activations up to ~ +-200
+    g = g * 60.0
+    f[0, 0, :8], g[0, 0, :8] = 150.0, -149.0      # tanh(1) after cancellation of two huge terms
+    f[1, 3, 8:16], g[1, 2, 8:16] = -120.0, 121.5
+    fd, gd, Wd, bd = [x.to(DEV).requires_grad_(True) for x in (f, g, W, b)]
+    costs = fused_joint_rnnt_loss(fd, gd, Wd, bd, lab.to(DEV), al.to(DEV), ll.to(DEV), V, act, "bf16x3")
+    costs.sum().backward()
+    oc, _, leaves = oracle(f, g, W, b, lab, al, ll, V, act)
+    oc.sum().backward()
+    assert torch.isfinite(costs).all()
+    assert rel_err(costs.detach().cpu().numpy(), oc.detach().numpy()) <= 1e-5
+    for name, got, ref in zip(["d_f", "d_g", "d_W", "d_b"], (fd, gd, Wd, bd), leaves):
+        assert torch.isfinite(got.grad).all(), name
+        assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy()) <= 1e-4, name
+
+
+def test_degenerate_shapes():
+    """Single cell (T=1, U=0), empty transcripts for the whole batch, and T_b = 1 inside a ragged batch."""
+    for B, T, U, al, ll in [(1, 1, 0, [1], [0]), (3, 7, 0, [7, 3, 1], [0, 0, 0]), (3, 9, 4, [9, 1, 5], [4, 0, 2])]:
+        V, H = 17, 64
+        f, g, W, b, lab, _, _ = make(B, T, max(U, 1), V, H, seed=B * 31 + T, ragged=False)
+        g = g[:, : U + 1].contiguous()
+        lab = lab[:, :U].contiguous()
+        al_t, ll_t = torch.tensor(al), torch.tensor(ll)
+        fd, gd, Wd, bd = [x.to(DEV).requires_grad_(True) for x in (f, g, W, b)]
+        costs = fused_joint_rnnt_loss(fd, gd, Wd, bd, lab.to(DEV), al_t.to(DEV), ll_t.to(DEV), V, "tanh", "bf16x3")
+        costs.sum().backward()
+        oc, _, leaves = oracle(f, g, W, b, lab, al_t, ll_t, V, "tanh")
+        oc.sum().backward()
+        assert rel_err(costs.detach().cpu().numpy(), oc.detach().numpy()) <= 1e-5, (B, T, U)
+        for name, got, ref in zip(["d_f", "d_g", "d_W", "d_b"], (fd, gd, Wd, bd), leaves):
+            assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy()) <= 1e-4, (B, T, U, name)
