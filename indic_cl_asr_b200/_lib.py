@@ -117,6 +117,13 @@ def launch_count() -> int:
     return int(lib().clasr_launch_count())
 
 
+def profile_ms_count(name: str):
+    """(mean ms per launch, number of launches) recorded under `name` since the last reset."""
+    n = C.c_int(0)
+    ms = float(lib().clasr_profile_ms(name.encode(), C.byref(n)))
+    return ms, int(n.value)
+
+
 def profile_ms(name: str) -> float:
     """Mean ms of the library kernel recorded under `name` since the last reset (-1 if none)."""
     return float(lib().clasr_profile_ms(name.encode(), None))
