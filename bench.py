@@ -144,25 +144,55 @@ def run_cpu_baseline(n_utts, activation, steps=1, warmup=0):
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML (10 ms period) when importable, else
+    nvidia-smi (the B200_PROFILING.md clocks line, ~5 samples/s)."""
+
+    _REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                ("sw_power_cap", 0x4))
+
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []   # (sm_mhz, sm_max_mhz, [reasons])
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[index])
+                                                        if os.environ.get("CUDA_VISIBLE_DEVICES") else index)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        self.samples.append((sm, self._max, [name for name, bit in self._REASONS if mask & bit]))
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            p = [x.strip() for x in out.split(",")]
+            names = [nm for nm, _ in self._REASONS]
+            self.samples.append((float(p[0]), float(p[1]),
+                                 [nm for nm, v in zip(names, p[2:6]) if v.lower().startswith("active")]))
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self._nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01 if self._nvml else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -174,19 +204,12 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for s in self.samples:
-            try:
-                sm.append(float(s[0])); mx.append(float(s[1]))
-            except Exception:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        reasons = sorted({r for s in self.samples for r in s[2]})
+        return {"sm_mhz": statistics.median(s[0] for s in self.samples), "sm_max_mhz": max(s[1] for s in self.samples),
+                "reasons": reasons, "samples": len(self.samples),
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------- our arm

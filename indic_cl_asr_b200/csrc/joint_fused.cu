@@ -51,7 +51,7 @@ struct JointCfg {
   static constexpr int kStagingBytes = kTerms == 1 ? 0 : kJProducerWarps * 2048;  // warp-private 32x32 bf16 lo tiles
   static constexpr int kRowTabBytes = 4 * 32 * 8;             // (f offset, g offset) of the tile's 128 rows
   static constexpr int smem_bytes(int H) {
-    return (H / kJK) * kABlockBytes + kStagingBytes + kStages * kBStageBytes + kRowTabBytes + 256 + 1024;
+    return (H / kJK) * kABlockBytes + kStagingBytes + kStages * kBStageBytes + kRowTabBytes + 384 + 1024;
   }
 };
 
@@ -146,7 +146,7 @@ __device__ __forceinline__ int find_utterance(const int* __restrict__ offs, int 
 template <int kTerms, int kMode, int kAct, int kPair>
 __global__ void __launch_bounds__(kJThreads, 1)
 joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                 JointFwdParams p) {
+                 const __grid_constant__ CUtensorMap tmHid, JointFwdParams p) {
   using C = JointCfg<kTerms, kPair>;
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_dyn[];
@@ -162,8 +162,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   uint64_t* tmem_full = empty + kStages;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]                                 (pair: the leader's copy)
   uint64_t* a_ready = tmem_empty + 2;       // [kblocks <= 10] A K-block written   (pair: the leader's copy)
-  uint64_t* a_free = a_ready + 10;          // [kblocks <= 10] last MMA reading A K-block retired
-  uint32_t* tmem_base_slot = (uint32_t*)(a_free + 10);
+  uint64_t* a_free = a_ready + 10;          // [kblocks <= 10] last MMA reading A K-block retired (+ pass 2: its
+                                            //                 TMA store to Hid_hi has read the block)
+  uint64_t* hid_ready = a_free + 10;        // [kblocks <= 10] pass 2: A K-block written (local copy for the store warp)
+  uint32_t* tmem_base_slot = (uint32_t*)(hid_ready + 10);
 
   const int warp = tc::warp_idx_uniform();
   const int lane = threadIdx.x & 31;
@@ -181,6 +183,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   if (warp == 0 && tc::elect_one()) {
     tc::prefetch_tmap(&tmW_hi);
     if (kTerms > 1) tc::prefetch_tmap(&tmW_lo);
+    if (kMode >= 1) tc::prefetch_tmap(&tmHid);
   }
   if (warp == 1 && tc::elect_one()) {
     constexpr int kCtas = kPair ? 2 : 1;
@@ -188,7 +191,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 4 * kCtas); }
     for (int i = 0; i < 10; ++i) {
       tc::mbar_init(&a_ready[i], kJProducerWarps * kCtas);
-      tc::mbar_init(&a_free[i], 1);
+      tc::mbar_init(&a_free[i], kMode >= 1 ? 2 : 1);
+      tc::mbar_init(&hid_ready[i], kJProducerWarps);
     }
     tc::fence_barrier_init();
   }
@@ -301,6 +305,30 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         __syncwarp();
       }
     }
+  } else if (warp == 3 && kMode >= 1) {
+    // ============================ pass 2: Hid_hi store warp ============================
+    // The bf16 hi halves of act(f+g) that the dW GEMM consumes ARE the A tile in shared memory (128-byte-swizzled
+    // [128 rows x 64 k] blocks = exactly a TMA box): one elected lane stores each block with a TMA store as soon as
+    // the producers have written it, and releases the block (second arrival on a_free) once the store has read it.
+    int tile_it = 0;
+    for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++tile_it) {
+      const bool tile_ok = tile < total_tiles;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        tc::mbar_wait(&hid_ready[kb], tile_it & 1);
+        if (tile_ok && tc::elect_one()) {
+          tc::tma_store_2d(&tmHid, a_smem + kb * C::kABlockBytes, kb * kJK, tile * kJM);
+          tc::bulk_commit_group();
+        }
+        __syncwarp();
+      }
+      if (tc::elect_one()) {
+        tc::bulk_wait_group_read0();
+        for (int kb = 0; kb < kblocks; ++kb) tc::mbar_arrive(&a_free[kb]);
+      }
+      __syncwarp();
+    }
+    if (tc::elect_one()) tc::bulk_wait_group0();  // all stores complete before the CTA exits
+    __syncwarp();
   } else if (warp >= 4 && warp < 8) {
     // ============================ epilogue ============================
     // kMode 0: online log-sum-exp + gather of logit[blank] / logit[label]  (pass 1)
@@ -551,12 +579,6 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           const int rimm = (i & 3) + 8 * (i >> 2);  // compile-time part of the row index
           tc::st_shared_u32(ablk + aoff[i & 3] + rimm * 128, hw);
           if (kTerms > 1) tc::st_shared_u32(stg + soff[i & 3] + 8 * (i >> 2) * 64, lw);
-          if (kMode >= 1 && tile_ok) {  // the dW GEMM consumes the hidden activations: keep a bf16 hi/lo copy
-            const int64_t go2 = ((int64_t)tile * kJM + q * 32 + rimm + 4 * hs) * p.ldh;
-            const int k = kb * kJK + half * 32 + 2 * c;
-            *reinterpret_cast<uint32_t*>(p.hid_hi + go2 + k) = hw;
-            if (kTerms > 1) *reinterpret_cast<uint32_t*>(p.hid_lo + go2 + k) = lw;
-          }
         }
       };
       load_batch(0, 0, fa, ga, oka);
@@ -588,6 +610,14 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::kAloCol + kb * (kJK / 2) + half * 16;
           tc::tmem_st8(taddr, v0);
           tc::tmem_st8(taddr + 8, v1);
+          if (kMode >= 1 && tile_ok) {  // pass 2: the lo halves of this lane's row (32 k = 64 contiguous bytes) for dW
+            uint4* dst = reinterpret_cast<uint4*>(p.hid_lo + ((int64_t)tile * kJM + q * 32 + lane) * p.ldh + kb * kJK +
+                                                  half * 32);
+            dst[0] = make_uint4(v0[0], v0[1], v0[2], v0[3]);
+            dst[1] = make_uint4(v0[4], v0[5], v0[6], v0[7]);
+            dst[2] = make_uint4(v1[0], v1[1], v1[2], v1[3]);
+            dst[3] = make_uint4(v1[4], v1[5], v1[6], v1[7]);
+          }
           tc::tmem_st_wait();
           tc::tc_fence_before();
         }
@@ -596,6 +626,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         if (lane == 0) {
           if (kPair) tc::mbar_arrive_cluster(&a_ready[kb], 0);  // the leader's MMA warp waits for both CTAs' A blocks
           else tc::mbar_arrive(&a_ready[kb]);
+          if (kMode >= 1) tc::mbar_arrive(&hid_ready[kb]);      // the local store warp
         }
       }
     }
@@ -838,8 +869,8 @@ static bool joint_use_pair() {
 }
 
 template <int kTerms, int kMode, int kAct, int kPair>
-static int launch_joint_variant(int H, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo, const JointFwdParams& p,
-                                cudaStream_t s) {
+static int launch_joint_variant(int H, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo, const CUtensorMap& t_hid,
+                                const JointFwdParams& p, cudaStream_t s) {
   const int smem = JointCfg<kTerms, kPair>::smem_bytes(H);
   auto kern = joint_fwd_kernel<kTerms, kMode, kAct, kPair>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -855,7 +886,7 @@ static int launch_joint_variant(int H, const CUtensorMap& tw_hi, const CUtensorM
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tw_hi, tw_lo, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tw_hi, tw_lo, t_hid, p);
   if (e != cudaSuccess) {
     set_error("joint kernel launch: %s", cudaGetErrorString(e));
     return CLASR_STATUS_CUDA_ERROR;
@@ -865,10 +896,10 @@ static int launch_joint_variant(int H, const CUtensorMap& tw_hi, const CUtensorM
 
 template <int kTerms, int kMode>
 static int launch_joint_kernel(int activation, int H, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
-                               const JointFwdParams& p, cudaStream_t s) {
+                               const CUtensorMap& t_hid, const JointFwdParams& p, cudaStream_t s) {
 #define CLASR_LAUNCH_JOINT(ACT)                                                                  \
-  (joint_use_pair() ? launch_joint_variant<kTerms, kMode, ACT, 1>(H, tw_hi, tw_lo, p, s)         \
-                    : launch_joint_variant<kTerms, kMode, ACT, 0>(H, tw_hi, tw_lo, p, s))
+  (joint_use_pair() ? launch_joint_variant<kTerms, kMode, ACT, 1>(H, tw_hi, tw_lo, t_hid, p, s)  \
+                    : launch_joint_variant<kTerms, kMode, ACT, 0>(H, tw_hi, tw_lo, t_hid, p, s))
   if (activation == CLASR_ACT_RELU) return CLASR_LAUNCH_JOINT(CLASR_ACT_RELU);
   if (activation == CLASR_ACT_SIGMOID) return CLASR_LAUNCH_JOINT(CLASR_ACT_SIGMOID);
   return CLASR_LAUNCH_JOINT(CLASR_ACT_TANH);
@@ -957,8 +988,8 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
     tw_lo = tw_hi;
   }
   prof_begin("joint_fwd", s);
-  rc = x3 ? launch_joint_kernel<3, 0>(activation, H, tw_hi, tw_lo, p, s)
-          : launch_joint_kernel<1, 0>(activation, H, tw_hi, tw_lo, p, s);
+  rc = x3 ? launch_joint_kernel<3, 0>(activation, H, tw_hi, tw_lo, tw_hi /*unused in pass 1*/, p, s)
+          : launch_joint_kernel<1, 0>(activation, H, tw_hi, tw_lo, tw_hi, p, s);
   if (rc) return rc;
   prof_end("joint_fwd", s);
   CLASR_CHECK_LAUNCH("joint_fwd");
@@ -1026,12 +1057,14 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
     tw_lo = tw_hi;
   }
   prof_begin("joint_bwd_dz", s);
+  CUtensorMap t_hid;  // TMA-store view of Hid_hi: [rows_cap, H] bf16, box = one 128 x 64 A block
+  if ((rc = make_tmap_bf16_2d(&t_hid, sc.hid_hi, (uint64_t)sc.rows_cap, H, sc.ldh, kJM, kJK))) return rc;
   if (mode == 1)
-    rc = x3 ? launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, p, s)
-            : launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, p, s);
+    rc = x3 ? launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, t_hid, p, s)
+            : launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, t_hid, p, s);
   else
-    rc = x3 ? launch_joint_kernel<3, 2>(activation, H, tw_hi, tw_lo, p, s)
-            : launch_joint_kernel<1, 2>(activation, H, tw_hi, tw_lo, p, s);
+    rc = x3 ? launch_joint_kernel<3, 2>(activation, H, tw_hi, tw_lo, t_hid, p, s)
+            : launch_joint_kernel<1, 2>(activation, H, tw_hi, tw_lo, t_hid, p, s);
   if (rc) return rc;
   prof_end("joint_bwd_dz", s);
   CLASR_CHECK_LAUNCH("joint_bwd_dz");
