@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap-ctc", action="store_true", help="keep the CTC branch on the main stream")
     ap.add_argument("--ewc-params", type=int, default=120_000_000, help="size of the stand-alone regulariser sweep probe")
     return ap.parse_args()
 
@@ -216,7 +217,7 @@ class ClockSampler:
 def main_b200(args):
     import torch.distributed as dist
 
-    from indic_cl_asr_b200 import CTCLoss, ConvASRDecoder, RNNTJoint, RNNTLoss, _lib, cl
+    from indic_cl_asr_b200 import CTCLoss, ConvASRDecoder, HybridRNNTCTCLoss, RNNTJoint, RNNTLoss, _lib, cl
     from indic_cl_asr_b200.dist import allreduce_flat_
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,6 +244,7 @@ def main_b200(args):
     head = ConvASRDecoder(feat_in=c["D_enc"], num_classes=c["V"]).to(dev)
     ctc = CTCLoss(num_classes=c["V"], zero_infinity=True)
     model = torch.nn.ModuleDict({"joint": joint, "ctc_decoder": head})
+    hybrid = HybridRNNTCTCLoss(joint, head, ctc, ctc_loss_weight=CTC_WEIGHT, overlap_ctc=not args.no_overlap_ctc)
     fp = cl.flat_params(model)
     theta = cl.get_params(model)
     star = cl.get_params_clone(model)
@@ -261,11 +263,7 @@ def main_b200(args):
         pen, avg = cl.get_penalty_grads_async(ewc_cfg, fish, theta, star, out=fp.grad)  # writes (=) the penalty grads
         enc.grad = None
         dec.grad = None
-        loss_rnnt, _, _, _ = joint(encoder_outputs=enc, decoder_outputs=dec, encoder_lengths=el, transcripts=tr,
-                                   transcript_lengths=tl, compute_wer=False)
-        log_probs = head(encoder_output=enc)
-        loss_ctc = ctc(log_probs=log_probs, targets=tr, input_lengths=el, target_lengths=tl)
-        loss = (1 - CTC_WEIGHT) * loss_rnnt + CTC_WEIGHT * loss_ctc
+        loss, _ = hybrid(enc, el, dec, tr, tl)   # training_step's loss half (hybrid_rnnt_ctc_models.py:868-902)
         (loss / world).backward()            # local mean_batch / N: the SUM all-reduce gives the global mean's gradient
         if world > 1:
             allreduce_flat_(fp.grad)

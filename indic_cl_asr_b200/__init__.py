@@ -11,6 +11,8 @@ include/clasr_b200.h).  There is no CPU path and no fallback: a missing library 
 from . import _lib
 from .losses import CTCLoss, RNNTLoss, RNNTLossNumba, rnnt_loss
 from .modules import ConvASRDecoder, RNNTJoint
+from .hybrid import HybridRNNTCTCLoss
 
-__all__ = ["CTCLoss", "RNNTLoss", "RNNTLossNumba", "rnnt_loss", "ConvASRDecoder", "RNNTJoint", "_lib"]
+__all__ = ["CTCLoss", "RNNTLoss", "RNNTLossNumba", "rnnt_loss", "ConvASRDecoder", "RNNTJoint", "HybridRNNTCTCLoss",
+           "_lib"]
 __version__ = "0.1.0"
