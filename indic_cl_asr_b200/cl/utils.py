@@ -6,7 +6,8 @@ import torch
 
 from .flat import FlatDict, flat_params
 
-__all__ = ["freeze_layer", "get_params", "get_params_clone", "get_zero_params", "get_grads", "set_grads"]
+__all__ = ["freeze_layer", "get_params", "get_params_clone", "get_zero_params", "get_grads", "set_grads",
+           "save_cl_state", "load_cl_state"]
 
 
 def freeze_layer(model, num_layers):
@@ -60,3 +61,48 @@ def set_grads(model, grad_dict):
             param.grad = grad_dict[name]
         else:
             param.grad = None
+
+
+# ------------------------------------------------------------------------------------------------
+# Continual-learning state on disk.  The reference keeps theta*, Fisher / Omega only in process memory
+# (cl_baseline_ewc.py:267-282, cl_baseline_mas.py:283-288; utils.save_model :265-271 stores weights only), so a
+# crashed 12-language run restarts from language 0.  With flat buffers the whole state is a handful of 1-D tensors.
+# ------------------------------------------------------------------------------------------------
+_CL_STATE_VERSION = 1
+
+
+def save_cl_state(path, checkpoint=None, importance=None, **extra) -> None:
+    """Write ``{theta* (checkpoint), F or Omega (importance), names/shapes, extra scalars}`` to ``path``.
+    ``checkpoint`` / ``importance`` are the dicts returned by get_params_clone / get_zero_params (or plain dicts)."""
+    from .flat import as_flat
+
+    ref = checkpoint if checkpoint is not None else importance
+    if ref is None:
+        raise ValueError("save_cl_state: nothing to save")
+    lay = as_flat(ref).layout
+    blob = {"version": _CL_STATE_VERSION, "names": list(lay.names), "shapes": [tuple(s) for s in lay.shapes],
+            "extra": dict(extra)}
+    for key, d in (("checkpoint", checkpoint), ("importance", importance)):
+        blob[key] = None if d is None else as_flat(d, lay).flat.detach().cpu()
+    torch.save(blob, path)
+
+
+def load_cl_state(path, model):
+    """Inverse of save_cl_state for ``model`` (same trainable parameters in the same order, utils.py:273-282).
+    Returns ``(checkpoint, importance, extra)`` as FlatDicts on the model's device (None where not saved)."""
+    fp = flat_params(model)
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    if blob.get("version") != _CL_STATE_VERSION:
+        raise ValueError(f"load_cl_state: unsupported version {blob.get('version')}")
+    if list(blob["names"]) != list(fp.layout.names) or [tuple(s) for s in blob["shapes"]] != [tuple(s) for s in fp.layout.shapes]:
+        raise ValueError("load_cl_state: the saved parameter layout does not match the model's trainable parameters")
+    out = []
+    for key in ("checkpoint", "importance"):
+        t = blob[key]
+        if t is None:
+            out.append(None)
+        else:
+            if t.numel() != fp.layout.total:
+                raise ValueError(f"load_cl_state: `{key}` has {t.numel()} elements, expected {fp.layout.total}")
+            out.append(FlatDict(fp.layout, t.to(fp.device, dtype=torch.float32).contiguous()))
+    return out[0], out[1], blob["extra"]

@@ -162,3 +162,23 @@ def test_sweep_sizes_and_tails(n):
     dst, src = theta.flat.clone(), F.flat.clone()
     _lib.check(L.clasr_cl_scale_merge(dst.data_ptr(), src.data_ptr(), n, 13.0, 0.5, 0, s))
     assert torch.equal(src[:n], F.flat[:n] / 13.0) and torch.equal(dst[:n], theta.flat[:n] * 0.5 + F.flat[:n] / 13.0)
+
+
+def test_cl_state_roundtrip(tmp_path):
+    """save_cl_state / load_cl_state: theta*, importance and scalars survive a restart bit-for-bit; a model with a
+    different trainable-parameter layout is rejected."""
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(13, 7), torch.nn.Linear(7, 5)).to(DEV)
+    star = cl.get_params_clone(m)
+    imp = cl.get_zero_params(m, DEV)
+    imp.flat.uniform_(0, 1)
+    p = tmp_path / "cl_state.pt"
+    cl.save_cl_state(p, checkpoint=star, importance=imp, lang_idx=3, total_ds=1234)
+    m2 = torch.nn.Sequential(torch.nn.Linear(13, 7), torch.nn.Linear(7, 5)).to(DEV)
+    star2, imp2, extra = cl.load_cl_state(p, m2)
+    assert extra == {"lang_idx": 3, "total_ds": 1234}
+    assert torch.equal(star2.flat, star.flat) and torch.equal(imp2.flat, imp.flat)
+    assert list(star2.keys()) == list(star.keys()) and star2.is_intact()
+    bad = torch.nn.Sequential(torch.nn.Linear(13, 8), torch.nn.Linear(8, 5)).to(DEV)
+    with pytest.raises(ValueError):
+        cl.load_cl_state(p, bad)
