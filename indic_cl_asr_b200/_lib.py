@@ -73,12 +73,13 @@ def declared_symbols() -> List[str]:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("CLASR_LIB", LIB_PATH)   # developer override (A/B builds); the product path is LIB_PATH
+        if not os.path.exists(path):
             raise RuntimeError(
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(make -C indic_cl_asr_b200/csrc).  There is no CPU / PyTorch fallback."
             )
-        l = C.CDLL(LIB_PATH)
+        l = C.CDLL(path)
         for name, (res, args) in _PROTOS.items():
             fn = getattr(l, name)
             fn.restype = res

@@ -49,7 +49,7 @@ struct JointCfg {
   static constexpr int kBStageBytes = kParts * kBRows * kJK * 2; // W ring stage (per CTA)
   static constexpr int kStages = kPair ? 2 * kJStages : kJStages;
   static constexpr int kStagingBytes = kTerms == 1 ? 0 : kJProducerWarps * 2048;  // warp-private 32x32 bf16 lo tiles
-  static constexpr int kRowTabBytes = kJProducerWarps * 32 * 4;  // per producer warp: packed (t, u) of its 32 rows
+  static constexpr int kRowTabBytes = 4 * 32 * 8;             // per lane quarter: (f offset, g offset) of its 32 rows
   static constexpr int smem_bytes(int H) {
     return (H / kJK) * kABlockBytes + kStagingBytes + kStages * kBStageBytes + kRowTabBytes + 384 + 1024;
   }
@@ -155,7 +155,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   uint8_t* a_smem = smem;                                          // [kblocks][128 x 64 bf16], SW128 K-major
   uint8_t* staging = a_smem + kblocks * C::kABlockBytes;            // BF16X3 only: 8 warps x [32 rows x 32 k] bf16
   uint8_t* b_ring = staging + C::kStagingBytes;                     // [stages][parts][BN x 64 bf16]
-  uint8_t* rowtab = b_ring + kStages * C::kBStageBytes;             // uint32[8 warps][32 rows]
+  uint8_t* rowtab = b_ring + kStages * C::kBStageBytes;             // int2[4 quarters][32 rows]
   uint64_t* bars = (uint64_t*)(rowtab + C::kRowTabBytes);
   uint64_t* full = bars;                 // [kStages]  W stage landed            (pair: the leader's copy)
   uint64_t* empty = full + kStages;      // [kStages]  W stage consumed
@@ -513,10 +513,11 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     const int q = pw & 3, half = pw >> 2;
     const int hs = lane >> 4, c = lane & 15;
     const uint32_t a_base = tc::smem_u32(a_smem);
-    // PRIVATE to the warp: the two K-half warps of a quarter cover the same rows but drift apart in time (one may already
-    // be writing the next tile's table while the other still reads this tile's) — a shared table was a race that
-    // corrupted single rows of dZ in pass 2a (found by repeating the config-3 parity test)
-    const uint32_t tab = tc::smem_u32(rowtab) + pw * 128;
+    // one table per lane quarter, shared by its two K-half warps.  They drift apart in time (only the a_free waits
+    // gate them), so the table of the next tile must not be written while the sibling still reads this tile's: a
+    // 64-thread named barrier per quarter at every tile start.  (Without it: occasional corrupted dZ rows in pass 2a,
+    // found by repeating the config-3 parity test — tests/test_gpu_repeatability.py.)
+    const uint32_t tab = tc::smem_u32(rowtab) + q * 256;
     const uint32_t stg = tc::smem_u32(staging) + pw * 2048;
     // hi: byte offset of (row = 32q + rl, k = 32*half + 2c) in the SW128 K-major block, rl = (i&3) + 8(i>>2) + 4hs
     uint32_t aoff[4], soff[4];
@@ -536,17 +537,18 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       const int Tb = (int)p.act_lens[b], Ub1 = (int)p.label_lens[b] + 1;
       const int r0 = (tile - p.tile_offsets[b]) * kJM;
       const int cells = tile_ok ? Tb * Ub1 : 0;  // null tile: every row is padding (A = 0)
-      {  // row table: lane l <-> row 32q + l, packed (t << 16 | u); 0xffffffff = padding row
+      {  // row table: lane l <-> row 32q + l (both K-half warps of the quarter write identical values)
         const int r = r0 + q * 32 + lane;
-        uint32_t e = 0xffffffffu;
+        int fo = -1, go_ = -1;
         if (r < cells) {
           const int t = r / Ub1, u = r - t * Ub1;
-          e = ((uint32_t)t << 16) | (uint32_t)u;
+          fo = (b * p.T + t) * p.H;
+          go_ = (b * p.U1 + u) * p.H;
         }
-        tc::st_shared_u32(tab + lane * 4, e);
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");  // the sibling warp is done reading the old table
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tab + lane * 8), "r"(fo), "r"(go_) : "memory");
       }
       __syncwarp();
-      const int fbase = b * p.T, gbase = b * p.U1;
       float2 fa[8], ga[8], fb[8], gb[8];
       uint32_t oka = 0, okb = 0;
       auto load_batch = [&](int kb, int batch, float2 (&fo)[8], float2 (&go_)[8], uint32_t& ok) {
@@ -556,10 +558,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         for (int j = 0; j < 8; ++j) {
           const int i = batch * 8 + j;
           const int rl = (i & 3) + 8 * (i >> 2) + 4 * hs;
-          const uint32_t e = tc::ld_shared_u32(tab + rl * 4);
-          if (e != 0xffffffffu) {
-            fo[j] = __ldg(reinterpret_cast<const float2*>(p.ef + (fbase + (int)(e >> 16)) * p.H + kcol));
-            go_[j] = __ldg(reinterpret_cast<const float2*>(p.eg + (gbase + (int)(e & 0xffffu)) * p.H + kcol));
+          const int2 o = tc::ld_shared_i2(tab + rl * 8);
+          if (o.x >= 0) {
+            fo[j] = __ldg(reinterpret_cast<const float2*>(p.ef + o.x + kcol));
+            go_[j] = __ldg(reinterpret_cast<const float2*>(p.eg + o.y + kcol));
             ok |= 1u << j;
           } else {  // padding row of the utterance's last tile: A row = 0
             fo[j] = make_float2(0.f, 0.f);
@@ -943,7 +945,6 @@ static int check_joint_args(const char* who, const void* f, const void* g, const
   CLASR_CHECK_ARG(f && g && w_out && b_out && act_lens && label_lens && ws, "%s: null pointer", who);
   CLASR_CHECK_ARG(labels || U1 == 1, "%s: null labels", who);
   CLASR_CHECK_ARG(B > 0 && T > 0 && U1 > 0 && H > 0 && Vp > 0, "%s: non-positive dimension", who);
-  CLASR_CHECK_ARG(T < 65536 && U1 < 65536, "%s: T and U+1 must be below 65536", who);
   CLASR_CHECK_ARG(H % kJK == 0 && H <= kJMaxH, "%s: joint_hidden must be a multiple of %d and <= %d (got %d)", who, kJK,
                   kJMaxH, H);
   CLASR_CHECK_ARG(blank >= 0 && blank < Vp, "%s: blank %d outside [0,%d)", who, blank, Vp);
