@@ -43,3 +43,39 @@ def test_fused_joint_is_repeatable(B, T, U, V, H, act, pair, monkeypatch):
         assert torch.equal(costs.detach(), ref_costs), it
         for name, c, r in zip(["d_f", "d_g", "d_W", "d_b"], cur, ref):
             assert rel_err(c.cpu().numpy(), r.cpu().numpy()) <= 2e-5, (it, name)
+
+
+def test_whole_step_is_repeatable():
+    """joint + RNNT + CTC + EWC step through HybridRNNTCTCLoss / ewc_backward, 12 runs on the same inputs."""
+    from helpers import synth_batch
+    from indic_cl_asr_b200 import CTCLoss, ConvASRDecoder, HybridRNNTCTCLoss, RNNTJoint, RNNTLoss, cl
+    from indic_cl_asr_b200.hybrid import ewc_backward
+
+    torch.manual_seed(0)
+    V, H, De, Dp = 256, 640, 512, 640
+    joint = RNNTJoint(jointnet=dict(encoder_hidden=De, pred_hidden=Dp, joint_hidden=H, activation="tanh", dropout=0.0),
+                      num_classes=V, fuse_loss_wer=True, fused_batch_size=4).to(DEV)
+    joint.set_loss(RNNTLoss(num_classes=V))
+    joint.set_wer(object())
+    head = ConvASRDecoder(feat_in=De, num_classes=V).to(DEV)
+    model = torch.nn.ModuleDict({"joint": joint, "ctc_decoder": head})
+    step = HybridRNNTCTCLoss(joint, head, CTCLoss(num_classes=V, zero_infinity=True))
+    enc, dec, tr, el, tl = synth_batch(6, 180, 40, V, De, Dp, seed=2, device=DEV)
+    star = cl.get_params_clone(model)
+    star.flat.add_(0.01 * torch.randn_like(star.flat))
+    fish = cl.get_zero_params(model, DEV)
+    fish.flat.uniform_(0.0, 1.0)
+    ref = None
+    for it in range(12):
+        e1, d1 = enc.clone().requires_grad_(True), dec.clone().requires_grad_(True)
+        loss, _ = step(e1, el, d1, tr, tl)
+        ewc_backward(model, loss, {"cl_config": {"e_lambda": 10.0}}, fish, star)
+        torch.cuda.synchronize()
+        cur = {n: p.grad.clone() for n, p in model.named_parameters()}
+        cur["d_enc"], cur["d_dec"], cur["loss"] = e1.grad.clone(), d1.grad.clone(), loss.detach().clone()
+        if ref is None:
+            ref = cur
+            continue
+        assert torch.equal(cur["loss"], ref["loss"]), it
+        for n in ref:
+            assert rel_err(cur[n].cpu().numpy(), ref[n].cpu().numpy()) <= 2e-5, (it, n)
