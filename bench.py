@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--activation", default="tanh", choices=["tanh", "relu", "sigmoid"])
     ap.add_argument("--ragged", type=int, default=0)
+    ap.add_argument("--dropout", type=float, default=0.0, help="joint dropout (the shipped checkpoint trains with 0.2)")
     ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -236,7 +237,7 @@ def main_b200(args):
 
     torch.manual_seed(1234)
     joint = RNNTJoint(jointnet=dict(encoder_hidden=c["D_enc"], pred_hidden=c["D_pred"], joint_hidden=c["H"],
-                                    activation=args.activation, dropout=0.0),
+                                    activation=args.activation, dropout=args.dropout),
                       num_classes=c["V"], fuse_loss_wer=True, fused_batch_size=4, fused_impl=args.mode,
                       precision=args.precision).to(dev)
     joint.set_loss(RNNTLoss(num_classes=c["V"]))
@@ -402,7 +403,7 @@ def main_b200(args):
             "data": "synthetic",
             "config": {"workload": "configs[1]: standalone RNNT+CTC(+EWC) loss fwd/bwd, B=32 T=250 U=100 V=1024 H=640 "
                                    "per GPU, full-length utterances" + (" (ragged)" if args.ragged else ""),
-                       "per_gpu_batch": c["B"], "global_batch": c["B"] * world, "activation": args.activation,
+                       "per_gpu_batch": c["B"], "global_batch": c["B"] * world, "activation": args.activation, "joint_dropout": args.dropout,
                        "joint_impl": args.mode, "precision": args.precision,
                        "l2": "256 MB buffer written between timed iterations (L2 flush)",
                        "parallelism": f"dp{world}: batch-sharded, one flat-gradient NCCL all-reduce per step"},

@@ -205,13 +205,18 @@ CLASR_API int clasr_debug_mma_rate(int N, int pattern, int iters, long long* out
  *    Pass 1 (tcgen05 GEMM, epilogue = online log-sum-exp + gather) fills the same lattice workspace
  *    as clasr_rnnt_loss_fwd and runs the alpha/beta wavefront; pass 2 recomputes logits tile-wise
  *    and contracts the softmax-fused gradient into d_f, d_g, dW_out, db_out.
+ *    dropout_p > 0 applies the joint's Dropout (modules/rnnt.py:1699-1709: act -> Dropout(p) -> Linear) inside the
+ *    kernels: a counter-based mask keyed by (dropout_seed, compact cell row, feature pair) that the recompute pass and
+ *    the d_f / d_g reduction regenerate; kept activations are scaled by 1 / (1 - p).  The backward calls must be given
+ *    the same (dropout_p, dropout_seed) as the forward call.  (Not bit-compatible with torch's Philox stream.)
  * ------------------------------------------------------------------------------------------ */
 CLASR_API size_t clasr_joint_workspace_bytes(int B, int T, int U1, int H, int Vp, int precision);
 
 CLASR_API int clasr_joint_rnnt_fwd(const float* f, const float* g, const float* w_out, const float* b_out,
                          const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B, int T,
-                         int U1, int H, int Vp, int blank, int activation, int precision, float fastemit_lambda,
-                         float* costs, float* sumsq /* [B,T,U1] sum_v z^2 for MAS, or NULL */, void* workspace,
+                         int U1, int H, int Vp, int blank, int activation, int precision, float dropout_p,
+                         uint64_t dropout_seed, float fastemit_lambda, float* costs,
+                         float* sumsq /* [B,T,U1] sum_v z^2 for MAS, or NULL */, void* workspace,
                          size_t workspace_bytes, void* stream);
 
 /* Backward.  `workspace` is the one the forward call filled (lattice, W split, tile table).  `scratch` holds the
@@ -223,8 +228,9 @@ CLASR_API int clasr_joint_rnnt_fwd(const float* f, const float* g, const float* 
 CLASR_API size_t clasr_joint_bwd_scratch_bytes(int B, int T, int U1, int H, int Vp, int precision);
 CLASR_API int clasr_joint_rnnt_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
                          const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B, int T,
-                         int U1, int H, int Vp, int blank, int activation, int precision, float fastemit_lambda,
-                         float clamp, const float* grad_out /* [B] */, float* d_f, float* d_g, float* d_w_out,
+                         int U1, int H, int Vp, int blank, int activation, int precision, float dropout_p,
+                         uint64_t dropout_seed, float fastemit_lambda, float clamp, const float* grad_out /* [B] */,
+                         float* d_f, float* d_g, float* d_w_out,
                          float* d_b_out, void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
                          void* stream);
 
@@ -236,7 +242,8 @@ CLASR_API int clasr_joint_rnnt_bwd(const float* f, const float* g, const float* 
 CLASR_API int clasr_joint_sumsq_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
                                     const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
                                     int T, int U1, int H, int Vp, int blank, int activation, int precision,
-                                    const float* grad_cells, float* d_f, float* d_g, float* d_w_out, float* d_b_out,
+                                    float dropout_p, uint64_t dropout_seed, const float* grad_cells, float* d_f,
+                                    float* d_g, float* d_w_out, float* d_b_out,
                                     void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
                                     void* stream);
 

@@ -66,6 +66,9 @@ struct JointFwdParams {
   const int* tile_offsets;  // [B+1] prefix sums of per-utterance tile counts
   int B, T, U1, H, Vp, blank;
   LatticeWs w;
+  // joint dropout (modules/rnnt.py:1699-1709): drop element when its 16-bit hash < drop_thresh; kept ones * drop_scale
+  uint32_t drop_thresh, drop_seed_a, drop_seed_b;
+  float drop_scale;
   float* sumsq;        // [B,T,U1] sum_v z^2 (MAS), or nullptr
   // ---- pass 2 (kMode == 1): recompute the logits tile and emit the softmax-fused gradient as GEMM operands
   const float* grad_out;      // [B] upstream gradient of each cost (may be nullptr == 1)
@@ -114,6 +117,17 @@ __device__ __forceinline__ float joint_combine(float a, float b) {
   const float r = tc::rcp_approx(1.f + tc::ex2_approx(a + b));  // 1 + 2^x >= 1; +inf -> 0
   if (kAct == CLASR_ACT_SIGMOID) return r;
   return fmaf(-2.f, r, 1.f);
+}
+
+// Counter-based dropout mask: one 32-bit hash ("lowbias32" finaliser) per PAIR of features (k even, k+1) of one
+// lattice cell, keyed by the cell's compact tile-row index (identical in pass 1, pass 2a and joint_dfg) — its two
+// 16-bit halves are the uniform numbers of the two features.  tests/test_gpu_dropout.py re-derives the mask on the host.
+__host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t pair_index, uint32_t seed_a, uint32_t seed_b) {
+  uint32_t x = (pair_index + seed_a) ^ seed_b;
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= x >> 15; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
 }
 
 __global__ void joint_tile_offsets_kernel(const int64_t* __restrict__ act_lens, const int64_t* __restrict__ label_lens,
@@ -575,8 +589,15 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         for (int j = 0; j < 8; ++j) {
           const int i = batch * 8 + j;
           const bool ok = (okm >> j) & 1u;
-          const float h0 = joint_combine<kAct>(fi[j].x, gi[j].x);
-          const float h1 = joint_combine<kAct>(fi[j].y, gi[j].y);
+          float h0 = joint_combine<kAct>(fi[j].x, gi[j].x);
+          float h1 = joint_combine<kAct>(fi[j].y, gi[j].y);
+          if (p.drop_thresh) {  // warp-uniform
+            const uint32_t crow = (uint32_t)tile * kJM + q * 32 + ((i & 3) + 8 * (i >> 2)) + 4 * hs;
+            const uint32_t x = drop_hash(crow * (uint32_t)(p.H >> 1) + (uint32_t)((kb * kJK + half * 32) >> 1) + c,
+                                         p.drop_seed_a, p.drop_seed_b);
+            h0 = (x & 0xffffu) >= p.drop_thresh ? h0 * p.drop_scale : 0.f;
+            h1 = (x >> 16) >= p.drop_thresh ? h1 * p.drop_scale : 0.f;
+          }
           __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
           __nv_bfloat162 ll = __floats2bfloat162_rn(h0 - __low2float(hh), h1 - __high2float(hh));
           const uint32_t hw = ok ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
@@ -717,7 +738,9 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
                                                               const int* __restrict__ tile_offsets, int T, int U1, int H,
                                                               float* __restrict__ d_f, float* __restrict__ d_g,
                                                               const float* __restrict__ dzb,
-                                                              float* __restrict__ d_w_blank) {
+                                                              float* __restrict__ d_w_blank, uint32_t drop_thresh,
+                                                              uint32_t drop_seed_a, uint32_t drop_seed_b,
+                                                              float drop_scale) {
   extern __shared__ float sm_dfg[];
   const int b = blockIdx.y, k0 = blockIdx.x * 32, t_begin = blockIdx.z * kDfgTChunk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -748,6 +771,14 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
     if (kAct == CLASR_ACT_TANH) { h = fmaf(-2.f, r, 1.f); dh = 4.f * t1; }
     else { h = r; dh = t1; }
   };
+  // dropout between the activation and the output layer: hid = mask * act / (1-p), d hid / d pre = mask * act' / (1-p)
+  const uint32_t kk = (uint32_t)(k0 + lane);
+  auto drop = [&](int64_t row, float& h, float& dh) {
+    const uint32_t x = drop_hash((uint32_t)row * (uint32_t)(H >> 1) + (kk >> 1), drop_seed_a, drop_seed_b);
+    const float m = ((kk & 1u) ? (x >> 16) : (x & 0xffffu)) >= drop_thresh ? drop_scale : 0.f;
+    h *= m;
+    dh *= m;
+  };
   // dW[blank, k] = sum over cells of dZ[cell, blank] * hid[cell, k]: the blank is the (V+1)-th class, a 1025th GEMM row
   // that would cost a whole extra 256-row tile in the dW GEMM; here it is one FMA per element on data already in flight
   float wb = 0.f;
@@ -770,6 +801,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
         for (int j = 0; j < 8; ++j) {
           float h, dh;
           act_pair(fv, eg_s[(u + j) * 32 + lane], h, dh);
+          if (drop_thresh) drop(r0 + u + j, h, dh);
           const float pv = d[j] * dh;
           df += pv;
           atomicAdd(dg_s + (u + j) * 32 + lane, pv);
@@ -779,6 +811,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
       for (; u < Ub1; ++u) {
         float h, dh;
         act_pair(fv, eg_s[u * 32 + lane], h, dh);
+        if (drop_thresh) drop(r0 + u, h, dh);
         const float pv = ld_stream1(dp + (int64_t)u * H) * dh;
         df += pv;
         atomicAdd(dg_s + u * 32 + lane, pv);
@@ -865,6 +898,16 @@ static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, in
   off += ((size_t)B * U1 * H * sizeof(float) + 255) / 256 * 256;
   j.total = off;
   return j;
+}
+
+static int set_dropout(JointFwdParams& p, float dropout_p, uint64_t seed) {
+  CLASR_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "joint: dropout_p must be in [0, 1)");
+  p.drop_thresh = (uint32_t)lrintf(dropout_p * 65536.f);   // p quantised to 1/65536
+  if (p.drop_thresh > 65535u) p.drop_thresh = 65535u;
+  p.drop_scale = p.drop_thresh ? 65536.f / (65536.f - (float)p.drop_thresh) : 1.f;
+  p.drop_seed_a = (uint32_t)seed;
+  p.drop_seed_b = (uint32_t)(seed >> 32);
+  return CLASR_STATUS_SUCCESS;
 }
 
 // CLASR_JOINT_PAIR=0/1 selects the 1-CTA / CTA-pair variant (default: pairs)
@@ -961,8 +1004,8 @@ static int check_joint_args(const char* who, const void* f, const void* g, const
 extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float* w_out, const float* b_out,
                                     const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
                                     int T, int U1, int H, int Vp, int blank, int activation, int precision,
-                                    float fastemit_lambda, float* costs, float* sumsq, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+                                    float dropout_p, uint64_t dropout_seed, float fastemit_lambda, float* costs,
+                                    float* sumsq, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_joint_args("joint_rnnt_fwd", f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank,
                             activation, precision, workspace, workspace_bytes);
   if (rc) return rc;
@@ -983,6 +1026,7 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.sumsq = sumsq;
+  if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;
   CUtensorMap tw_hi, tw_lo;
   const int bn = joint_use_pair() ? (x3 ? JointCfg<3, 1>::kBRows : JointCfg<1, 1>::kBRows)
                                   : (x3 ? JointCfg<3, 0>::kBRows : JointCfg<1, 0>::kBRows);
@@ -1009,8 +1053,9 @@ extern "C" size_t clasr_joint_bwd_scratch_bytes(int B, int T, int U1, int H, int
 // mode 1: transducer-loss backward (grad_out [B]);  mode 2: backward of sum_v z^2 per cell (grad_cells [B,T,U1])
 static int joint_bwd_impl(int mode, const float* f, const float* g, const float* w_out, const float* b_out,
                           const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B, int T, int U1,
-                          int H, int Vp, int blank, int activation, int precision, float fastemit_lambda, float clamp,
-                          const float* grad_out, const float* grad_cells, float* d_f, float* d_g, float* d_w_out,
+                          int H, int Vp, int blank, int activation, int precision, float dropout_p,
+                          uint64_t dropout_seed, float fastemit_lambda, float clamp, const float* grad_out,
+                          const float* grad_cells, float* d_f, float* d_g, float* d_w_out,
                           float* d_b_out, void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
                           void* stream) {
   int rc = check_joint_args("joint_rnnt_bwd", f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank,
@@ -1039,6 +1084,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.grad_out = grad_out; p.grad_cells = grad_cells; p.fastemit_lambda = fastemit_lambda; p.clamp = clamp;
+  if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;
   p.dz_hi = (__nv_bfloat16*)sc.dz_hi; p.dz_lo = (__nv_bfloat16*)sc.dz_lo; p.ldz = sc.ldz;
   p.hid_hi = (__nv_bfloat16*)sc.hid_hi; p.hid_lo = (__nv_bfloat16*)sc.hid_lo; p.ldh = sc.ldh;
   p.rows_pad_dev = rows_pad_dev;
@@ -1101,7 +1147,8 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
     cudaFuncSetAttribute(joint_dfg_fused_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     joint_dfg_fused_kernel<ACT><<<grid, 256, smem, s>>>(sc.dhid, ef_, eg_, act_lens, label_lens, jw.tile_offsets,  \
                                                         T, U1, H, d_f, d_g, blank_split ? sc.dzb : nullptr,        \
-                                                        d_w_out + (size_t)blank * H);                              \
+                                                        d_w_out + (size_t)blank * H, p.drop_thresh, p.drop_seed_a, \
+                                                        p.drop_seed_b, p.drop_scale);                              \
   } while (0)
       if (activation == CLASR_ACT_RELU) CLASR_LAUNCH_DFG(CLASR_ACT_RELU);
       else if (activation == CLASR_ACT_SIGMOID) CLASR_LAUNCH_DFG(CLASR_ACT_SIGMOID);
@@ -1109,6 +1156,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
 #undef CLASR_LAUNCH_DFG
       CLASR_CHECK_LAUNCH("joint_dfg_fused");
     } else {  // very long label sequences: the two-pass kernel (reads dHid twice, no shared-memory partials)
+      CLASR_CHECK_ARG(p.drop_thresh == 0, "joint_rnnt_bwd: in-kernel dropout needs U+1 <= 800 (single-pass d_f/d_g kernel)");
       joint_dfg_kernel<<<dim3(T, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
                                                  activation, 0, d_f);
       CLASR_CHECK_LAUNCH("joint_df");
@@ -1124,22 +1172,25 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
 extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
                                     const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
                                     int T, int U1, int H, int Vp, int blank, int activation, int precision,
-                                    float fastemit_lambda, float clamp, const float* grad_out, float* d_f, float* d_g,
-                                    float* d_w_out, float* d_b_out, void* workspace, size_t workspace_bytes,
-                                    void* scratch, size_t scratch_bytes, void* stream) {
+                                    float dropout_p, uint64_t dropout_seed, float fastemit_lambda, float clamp,
+                                    const float* grad_out, float* d_f, float* d_g, float* d_w_out, float* d_b_out,
+                                    void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                                    void* stream) {
   return joint_bwd_impl(1, f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank, activation,
-                        precision, fastemit_lambda, clamp, grad_out, nullptr, d_f, d_g, d_w_out, d_b_out, workspace,
+                        precision, dropout_p, dropout_seed, fastemit_lambda, clamp, grad_out, nullptr, d_f, d_g, d_w_out, d_b_out, workspace,
                         workspace_bytes, scratch, scratch_bytes, stream);
 }
 
 extern "C" int clasr_joint_sumsq_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
                                      const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
                                      int T, int U1, int H, int Vp, int blank, int activation, int precision,
-                                     const float* grad_cells, float* d_f, float* d_g, float* d_w_out, float* d_b_out,
+                                     float dropout_p, uint64_t dropout_seed, const float* grad_cells, float* d_f,
+                                     float* d_g, float* d_w_out, float* d_b_out,
                                      void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
                                      void* stream) {
   CLASR_CHECK_ARG(grad_cells, "joint_sumsq_bwd: null grad_cells");
   return joint_bwd_impl(2, f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank, activation,
-                        precision, 0.f, 0.f, nullptr, grad_cells, d_f, d_g, d_w_out, d_b_out, workspace, workspace_bytes,
+                        precision, dropout_p, dropout_seed, 0.f, 0.f, nullptr, grad_cells, d_f, d_g, d_w_out, d_b_out,
+                        workspace, workspace_bytes,
                         scratch, scratch_bytes, stream);
 }

@@ -11,7 +11,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["fused_joint_rnnt_loss", "fused_joint_forward_stats", "fused_joint_sumsq", "LazySubLogits"]
+__all__ = ["fused_joint_rnnt_loss", "fused_joint_forward_stats", "fused_joint_sumsq", "LazySubLogits",
+           "dropout_mask_reference"]
 
 
 def _ws(f, B, T, U1, H, Vp, prec):
@@ -23,7 +24,7 @@ def _ws(f, B, T, U1, H, Vp, prec):
 class _FusedJointRNNT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision, fastemit_lambda,
-                clamp, want_sumsq):
+                clamp, want_sumsq, dropout_p=0.0, dropout_seed=0):
         _lib.require_cuda(f, "f")
         if clamp < 0:
             raise ValueError("`clamp` must be 0.0 or positive float value.")
@@ -52,11 +53,12 @@ class _FusedJointRNNT(torch.autograd.Function):
             st = L.clasr_joint_rnnt_fwd(
                 f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
                 act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, int(blank), _lib.ACT[activation], prec,
-                float(fastemit_lambda), costs.data_ptr(), _lib.ptr(sumsq), ws.data_ptr(), nbytes,
-                _lib.stream_ptr(f.device))
+                float(dropout_p), int(dropout_seed), float(fastemit_lambda), costs.data_ptr(), _lib.ptr(sumsq),
+                ws.data_ptr(), nbytes, _lib.stream_ptr(f.device))
         _lib.check(st, "joint_rnnt_fwd")
         ctx.save_for_backward(f, g, weight, bias, labels, act_lens, label_lens, ws)
-        ctx.args = (int(blank), _lib.ACT[activation], prec, float(fastemit_lambda), float(clamp), nbytes)
+        ctx.args = (int(blank), _lib.ACT[activation], prec, float(fastemit_lambda), float(clamp), nbytes,
+                    float(dropout_p), int(dropout_seed))
         if want_sumsq:
             ctx.mark_non_differentiable(sumsq)
             return costs, sumsq
@@ -65,7 +67,7 @@ class _FusedJointRNNT(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_costs, *unused):
         f, g, weight, bias, labels, act_lens, label_lens, ws = ctx.saved_tensors
-        blank, act, prec, fastemit_lambda, clamp, nbytes = ctx.args
+        blank, act, prec, fastemit_lambda, clamp, nbytes, dropout_p, dropout_seed = ctx.args
         B, T, H = f.shape
         U1 = g.shape[1]
         Vp = weight.shape[0]
@@ -80,25 +82,57 @@ class _FusedJointRNNT(torch.autograd.Function):
         with torch.cuda.device(f.device):
             st = L.clasr_joint_rnnt_bwd(
                 f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
-                act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, blank, act, prec, fastemit_lambda, clamp,
-                go.data_ptr(), d_f.data_ptr(), d_g.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ws.data_ptr(), nbytes,
-                scratch.data_ptr(), sbytes, _lib.stream_ptr(f.device))
+                act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, blank, act, prec, dropout_p, dropout_seed,
+                fastemit_lambda, clamp, go.data_ptr(), d_f.data_ptr(), d_g.data_ptr(), d_w.data_ptr(), d_b.data_ptr(),
+                ws.data_ptr(), nbytes, scratch.data_ptr(), sbytes, _lib.stream_ptr(f.device))
         _lib.check(st, "joint_rnnt_bwd")
-        return (d_f, d_g, d_w, d_b) + (None,) * 9
+        return (d_f, d_g, d_w, d_b) + (None,) * 11
 
 
 def fused_joint_rnnt_loss(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh",
-                          precision="bf16x3", fastemit_lambda=0.0, clamp=0.0):
-    """Per-sample transducer costs [B]."""
+                          precision="bf16x3", fastemit_lambda=0.0, clamp=0.0, dropout_p=0.0, dropout_seed=0):
+    """Per-sample transducer costs [B].  ``dropout_p`` > 0 applies the joint's Dropout between the activation and the
+    output layer inside the kernels (mask keyed by ``dropout_seed``; see ``dropout_mask_reference``)."""
     return _FusedJointRNNT.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision,
-                                 fastemit_lambda, clamp, False)
+                                 fastemit_lambda, clamp, False, dropout_p, dropout_seed)
+
+
+def dropout_mask_reference(act_lens, label_lens, T, U1, H, dropout_p, dropout_seed):
+    """Host restatement of the in-kernel dropout mask: bool [B,T,U1,H], True = kept (test / debugging aid).
+
+    A cell's key is its compact tile-row index ``128 * tile_offsets[b] + t * (U_b+1) + u`` with ``tile_offsets`` the
+    prefix sums of ``ceil(T_b (U_b+1) / 128)``; one lowbias32 hash per feature pair, 16 bits per feature."""
+    import numpy as np
+
+    al = [int(x) for x in act_lens]
+    ll = [int(x) for x in label_lens]
+    B = len(al)
+    thresh = min(65535, int(round(float(np.float32(dropout_p) * np.float32(65536.0)))))
+    sa, sb = np.uint32(dropout_seed & 0xFFFFFFFF), np.uint32((dropout_seed >> 32) & 0xFFFFFFFF)
+    keep = np.zeros((B, T, U1, H), dtype=bool)
+    off = 0
+    k = np.arange(H, dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        for b in range(B):
+            Tb, Ub1 = al[b], ll[b] + 1
+            t, u = np.meshgrid(np.arange(Tb, dtype=np.uint32), np.arange(Ub1, dtype=np.uint32), indexing="ij")
+            row = (np.uint32(off * 128) + t * np.uint32(Ub1) + u)[..., None]
+            x = (row * np.uint32(H // 2) + (k >> np.uint32(1)) + sa) ^ sb
+            x ^= x >> np.uint32(16); x *= np.uint32(0x7feb352d)
+            x ^= x >> np.uint32(15); x *= np.uint32(0x846ca68b)
+            x ^= x >> np.uint32(16)
+            r16 = np.where((k & np.uint32(1)) == 1, x >> np.uint32(16), x & np.uint32(0xFFFF))
+            keep[b, :Tb, :Ub1] = r16 >= thresh
+            off += (Tb * Ub1 + 127) // 128
+    scale = 65536.0 / (65536.0 - thresh) if thresh else 1.0
+    return keep, scale
 
 
 def fused_joint_forward_stats(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh",
                               precision="bf16x3"):
     """(costs [B], sum_v z^2 [B,T,U+1]) — the second is what MAS needs from the joint logits."""
     return _FusedJointRNNT.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision, 0.0,
-                                 0.0, True)
+                                 0.0, True, 0.0, 0)
 
 
 class _FusedJointSumsq(torch.autograd.Function):
@@ -106,7 +140,8 @@ class _FusedJointSumsq(torch.autograd.Function):
     joint half of the MAS importance objective (reference cl_baseline_mas.py:258-265) without the logits tensor."""
 
     @staticmethod
-    def forward(ctx, f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision):
+    def forward(ctx, f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision, dropout_p=0.0,
+                dropout_seed=0):
         _lib.require_cuda(f, "f")
         f = f.contiguous().float()
         g = g.contiguous().float()
@@ -127,16 +162,17 @@ class _FusedJointSumsq(torch.autograd.Function):
             st = L.clasr_joint_rnnt_fwd(
                 f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
                 act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, int(blank), _lib.ACT[activation], prec,
-                0.0, costs.data_ptr(), sumsq.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr(f.device))
+                float(dropout_p), int(dropout_seed), 0.0, costs.data_ptr(), sumsq.data_ptr(), ws.data_ptr(), nbytes,
+                _lib.stream_ptr(f.device))
         _lib.check(st, "joint_rnnt_fwd")
         ctx.save_for_backward(f, g, weight, bias, labels, act_lens, label_lens, ws)
-        ctx.args = (int(blank), _lib.ACT[activation], prec, nbytes)
+        ctx.args = (int(blank), _lib.ACT[activation], prec, nbytes, float(dropout_p), int(dropout_seed))
         return sumsq
 
     @staticmethod
     def backward(ctx, grad_sumsq):
         f, g, weight, bias, labels, act_lens, label_lens, ws = ctx.saved_tensors
-        blank, act, prec, nbytes = ctx.args
+        blank, act, prec, nbytes, dropout_p, dropout_seed = ctx.args
         B, T, H = f.shape
         U1 = g.shape[1]
         Vp = weight.shape[0]
@@ -149,16 +185,18 @@ class _FusedJointSumsq(torch.autograd.Function):
         with torch.cuda.device(f.device):
             st = L.clasr_joint_sumsq_bwd(
                 f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
-                act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, blank, act, prec, gc.data_ptr(),
-                d_f.data_ptr(), d_g.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ws.data_ptr(), nbytes,
+                act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, blank, act, prec, dropout_p, dropout_seed,
+                gc.data_ptr(), d_f.data_ptr(), d_g.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ws.data_ptr(), nbytes,
                 scratch.data_ptr(), sbytes, _lib.stream_ptr(f.device))
         _lib.check(st, "joint_sumsq_bwd")
-        return (d_f, d_g, d_w, d_b) + (None,) * 6
+        return (d_f, d_g, d_w, d_b) + (None,) * 8
 
 
-def fused_joint_sumsq(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh", precision="bf16x3"):
+def fused_joint_sumsq(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh", precision="bf16x3",
+                      dropout_p=0.0, dropout_seed=0):
     """[B,T,U+1] tensor of sum_v z^2 (zero outside the cells selected by the lengths), with autograd."""
-    return _FusedJointSumsq.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision)
+    return _FusedJointSumsq.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision,
+                                  dropout_p, dropout_seed)
 
 
 class LazySubLogits:

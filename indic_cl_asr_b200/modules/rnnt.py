@@ -337,8 +337,8 @@ class RNNTJoint(torch.nn.Module):
 
     # -- B200 path: fused joint + loss, logits never materialised -----------------------------------
     def _tcgen05_supported(self, language_ids) -> bool:
-        if self._dropout_p > 0.0 and self.training:
-            return False  # TODO(fused dropout): Philox mask regenerated in the recompute pass
+        if self._dropout_p >= 1.0:
+            return False
         if self.temperature != 1.0 or self.log_softmax:
             return False
         if self.joint_hidden % 64 != 0:
@@ -346,6 +346,14 @@ class RNNTJoint(torch.nn.Module):
         if isinstance(self.joint_net[-1], torch.nn.ModuleDict):
             return language_ids is not None and len(set(language_ids)) == 1
         return True
+
+    def _dropout_args(self):
+        """(p, seed) of the joint's Dropout (reference modules/rnnt.py:1699-1709) for the fused kernels: active in
+        training mode only; the seed is drawn from torch's CPU generator (no device sync, reproducible under
+        torch.manual_seed)."""
+        if self._dropout_p > 0.0 and self.training:
+            return self._dropout_p, int(torch.randint(0, 2 ** 62, (1,)).item())
+        return 0.0, 0
 
     def _lazy_store_list(self, enc, dec, enc_lens, transcripts, transcript_lens, language_ids):
         """``store_list`` for ``store_sub_logits`` on the fused path (reference modules/rnnt.py:1480-1496, 1649-1650).
@@ -365,8 +373,10 @@ class RNNTJoint(torch.nn.Module):
             box_t[begin:end], box_u[begin:end] = mt, mu
             boxes.append((begin, end, mt, mu))
         f, g = self.project_encoder(enc), self.project_prednet(dec)
+        p_drop, seed = self._dropout_args()
         sumsq = fused_joint_sumsq(f, g, lin.weight, lin.bias, transcripts, box_t, box_u, blank=self.loss._blank,
-                                  activation=self.activation, precision=self.precision)
+                                  activation=self.activation, precision=self.precision, dropout_p=p_drop,
+                                  dropout_seed=seed)
         vp = int(lin.weight.shape[0])
         out = []
         for begin, end, mt, mu in boxes:
@@ -387,9 +397,10 @@ class RNNTJoint(torch.nn.Module):
         f = self.project_encoder(enc)   # [B,T,H]  (tcgen05 GEMM)
         g = self.project_prednet(dec)   # [B,U1,H]
         loss_mod = self.loss
+        p_drop, seed = self._dropout_args()
         per_sample = fused_joint_rnnt_loss(
             f, g, lin.weight, lin.bias, transcripts, enc_lens, transcript_lens,
             blank=loss_mod._blank, activation=self.activation, precision=self.precision,
             fastemit_lambda=float(getattr(loss_mod, "fastemit_lambda", 0.0)),
-            clamp=float(getattr(loss_mod, "clamp", 0.0)))
+            clamp=float(getattr(loss_mod, "clamp", 0.0)), dropout_p=p_drop, dropout_seed=seed)
         return loss_mod.reduce(per_sample, transcript_lens.long())
