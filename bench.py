@@ -327,6 +327,7 @@ def main_b200(args):
                "loss": float(host_out[0])}
 
     # ---------------- per-kernel durations (library-side CUDA events on the launch stream) -> roofline
+    hybrid.overlap_ctc = False   # per-kernel durations must not include time shared with the side-stream CTC branch
     L.clasr_set_profiling(1)
     L.clasr_profile_reset()
     for _ in range(min(args.steps, 5)):
