@@ -347,7 +347,11 @@ def main_b200(args):
         ach = gemm_flops / (kern["joint_fwd"] * 1e-3) / 1e12
         roofline = {"kernel": "joint_fwd_kernel (pass 1: joint GEMM + online log-softmax)", "bound": "tensor",
                     "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full`
+                    # (profiles/r01bcd_ncu_joint_and_gemm.md, r01g capture: 31.5 MB read, ~0 written; the algorithmic
+                    # output is 20 B per lattice cell = 16 MB, the inputs f/g/W = 30 MB)
+                    "traffic": 31.5e6 if (args.precision == "bf16x3" and not args.ragged) else None,
+                    "peak_source": pk["source"] + " bf16 sustained",
                     "algorithmic_flops_per_launch": gemm_flops, "ms": kern["joint_fwd"],
                     "mma_issue_multiplier": 3 if args.precision == "bf16x3" else 1}
         tensor_ms = sum(kern.get(k, 0.0) for k in ("joint_fwd", "joint_bwd_dz", "gemm_dhid", "gemm_dw"))
