@@ -82,6 +82,12 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                "f"(v.w)
                : "memory");
 }
+// 256-bit global store (sm_100: STG.E.ENL2.256): one full 32-byte sector per thread per instruction; p 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ float ld_stream1(const float* p) {
   float r;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));

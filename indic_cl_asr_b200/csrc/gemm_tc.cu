@@ -255,6 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int row = m0 + q * 32 + lane;
       float* crow = p.C + (int64_t)row * p.ldc;
       const bool vec_ok = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+      const bool vec32_ok = ((p.ldc & 7) == 0) && ((((uintptr_t)p.C) & 31) == 0);
 #pragma unroll 1
       for (int c = 0; c < kBN / 32; ++c) {
         uint32_t r[32];
@@ -266,15 +267,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) atomicAdd(crow + col0 + j, __uint_as_float(r[j]));
           } else if (vec_ok && col0 + 32 <= p.N) {
+            if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                     __uint_as_float(r[j + 3]));
-              if (p.bias) {
-                v.x += __ldg(p.bias + col0 + j);     v.y += __ldg(p.bias + col0 + j + 1);
-                v.z += __ldg(p.bias + col0 + j + 2); v.w += __ldg(p.bias + col0 + j + 3);
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(p.bias + col0 + j));
+            }
+            if (vec32_ok) {  // 32-byte-aligned rows: 256-bit stores, one full sector each
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint32_t v[8] = {r[j], r[j + 1], r[j + 2], r[j + 3], r[j + 4], r[j + 5], r[j + 6], r[j + 7]};
+                st_global_256(crow + col0 + j, v);
               }
-              *reinterpret_cast<float4*>(crow + col0 + j) = v;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(crow + col0 + j) =
+                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                __uint_as_float(r[j + 3]));
             }
           } else {
             for (int j = 0; j < 32; ++j)
@@ -479,6 +487,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int row = m0 + q * 32 + lane;
       float* crow = p.C + (int64_t)row * p.ldc;
       const bool vec_ok = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+      const bool vec32_ok = ((p.ldc & 7) == 0) && ((((uintptr_t)p.C) & 31) == 0);
 #pragma unroll 1
       for (int c = 0; c < nw / 32; ++c) {
         uint32_t r[32];
@@ -490,15 +499,22 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) atomicAdd(crow + col0 + j, __uint_as_float(r[j]));
           } else if (vec_ok && col0 + 32 <= p.N) {
+            if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                     __uint_as_float(r[j + 3]));
-              if (p.bias) {
-                v.x += __ldg(p.bias + col0 + j);     v.y += __ldg(p.bias + col0 + j + 1);
-                v.z += __ldg(p.bias + col0 + j + 2); v.w += __ldg(p.bias + col0 + j + 3);
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(p.bias + col0 + j));
+            }
+            if (vec32_ok) {  // 32-byte-aligned rows: 256-bit stores, one full sector each
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint32_t v[8] = {r[j], r[j + 1], r[j + 2], r[j + 3], r[j + 4], r[j + 5], r[j + 6], r[j + 7]};
+                st_global_256(crow + col0 + j, v);
               }
-              *reinterpret_cast<float4*>(crow + col0 + j) = v;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(crow + col0 + j) =
+                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                __uint_as_float(r[j + 3]));
             }
           } else {
             for (int j = 0; j < 32; ++j)

@@ -30,7 +30,8 @@ int launch_split_bf16(const float* src, int64_t rows, int cols, int64_t src_ld, 
 constexpr int kJM = 128;            // rows (lattice cells) per tile
 constexpr int kJK = 64;             // K block (one 128-byte swizzle span of bf16)
 constexpr int kJMaxH = 640;         // A tile (128 x H bf16) must stay resident in shared memory
-constexpr int kJThreads = 512;      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue, 8-15 A producers
+constexpr int kJThreads = 512;      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 Hid store, 4-7 epilogue, 8-15 A producers
+constexpr int kJThreadsWide = 640;  // kWide: 4-7 epilogue of accumulator 0, 8-11 of accumulator 1, 12-19 A producers
 constexpr int kJProducerWarps = 8;
 constexpr int kJStages = 2;
 
@@ -76,7 +77,7 @@ struct JointFwdParams {
   float fastemit_lambda, clamp;
   __nv_bfloat16* dz_hi;       // [rows_pad, ldz]  dZ split hi/lo, compact tile-row order
   __nv_bfloat16* dz_lo;
-  int ldz;                    // multiple of 8, >= Vp
+  int ldz;                    // multiple of 16, >= Vp (32-byte sectors per 16-column epilogue piece)
   __nv_bfloat16* hid_hi;      // [rows_pad, ldh]  act(f+g) split hi/lo
   __nv_bfloat16* hid_lo;
   int ldh;                    // H
@@ -157,12 +158,20 @@ __device__ __forceinline__ int find_utterance(const int* __restrict__ offs, int 
   return lo;
 }
 
-template <int kTerms, int kMode, int kAct, int kPair>
-__global__ void __launch_bounds__(kJThreads, 1)
+// kWide = 1 (pass 2): the gradient epilogue is the bottleneck of pass 2a (r01g profile: epilogue warps 82 % busy, MMA
+// warp 26 % waiting on tmem_empty), so it gets EIGHT warps — one warpgroup per TMEM accumulator buffer, alternating N
+// tiles — in a 640-thread CTA whose register file is re-split with setmaxnreg (control warps 32, epilogue 112,
+// producers 112 registers per thread).
+template <int kTerms, int kMode, int kAct, int kPair, int kWide>
+__global__ void __launch_bounds__(kWide ? kJThreadsWide : kJThreads, 1)
 joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                  const __grid_constant__ CUtensorMap tmHid, JointFwdParams p) {
   using C = JointCfg<kTerms, kPair>;
   constexpr int kStages = C::kStages;
+  constexpr int kEpiWarps = kWide ? 8 : 4;
+  constexpr int kProdWarp0 = 4 + kEpiWarps;          // first producer warp (a multiple of 4: warp % 4 = TMEM quarter)
+  constexpr int kBatch = kWide ? 4 : 8;              // row pairs per producer load batch (register budget)
+  constexpr int kNB = 16 / kBatch;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   const int kblocks = p.H / kJK;
@@ -220,6 +229,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   tc::tc_fence_after();
   const uint32_t tmem_base = tc::uniform_u32(*tmem_base_slot);
 
+  // kWide: the register file is re-split between the warpgroups; every setmaxnreg sits at the top of the branch whose
+  // code it governs (ptxas allocates registers per such region), executed by all four warps of the warpgroup.  The
+  // pool is what the CTA got at launch (640 x 96 = 61 440 registers, NOT the SM's 65 536): 128 x 32 + 512 x 112 = 61 440.
+  // (A first version asked for 64 512 and its last setmaxnreg.inc blocked forever.)
+  if (warp < 4) {
+  if (kWide) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   if (warp == 0) {
     // ============================ TMA producer: W ring (whole warp loops, one elected lane issues) ===========
     int stage = 0;
@@ -343,12 +358,15 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     }
     if (tc::elect_one()) tc::bulk_wait_group0();  // all stores complete before the CTA exits
     __syncwarp();
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if (warp < kProdWarp0) {
+    if (kWide) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ============================ epilogue ============================
     // kMode 0: online log-sum-exp + gather of logit[blank] / logit[label]  (pass 1)
     // kMode 1: softmax-fused gradient dZ = clamp(exp(logp + occupancy) - blank/label terms) * grad_out, split into
     //          bf16 hi/lo and written in tile-row order as the operand of the two backward GEMMs (pass 2)
     const int q = warp & 3;
+    const int egrp = (warp - 4) >> 2;   // kWide: this warpgroup serves accumulator buffer `egrp` only
     const int row = q * 32 + lane;
     int acc_it = 0;
     for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
@@ -388,18 +406,19 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
         const int acc = acc_it & 1;
         const uint32_t acc_phase = (acc_it >> 1) & 1;
+        if (kWide && acc != egrp) continue;
         tc::mbar_wait(&tmem_full[acc], acc_phase);
         tc::tc_fence_after();
         // columns this N tile must cover: up to Vp (stats) or up to the padded operand width ldz (gradient)
         const int width = (kMode >= 1 ? p.ldz : p.Vp);
         const int ncols = (nt == n_tiles - 1) ? (width - nt * C::kBN) : C::kBN;
+        if (kMode == 0) {
 #pragma unroll 1
-        for (int c = 0; tile_ok && c * 32 < ncols; ++c) {
-          uint32_t rr[32];
-          tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN + c * 32, rr);
-          tc::tmem_ld_wait();
-          const int col0 = nt * C::kBN + c * 32;
-          if (kMode == 0) {
+          for (int c = 0; tile_ok && c * 32 < ncols; ++c) {
+            uint32_t rr[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN + c * 32, rr);
+            tc::tmem_ld_wait();
+            const int col0 = nt * C::kBN + c * 32;
             float z[32];
             float cm = -INFINITY;
 #pragma unroll
@@ -418,89 +437,96 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) s += __expf(z[j] - m);
-          } else {
-            // branch-free per element; every special case is a warp-uniform branch around a whole 32-column chunk
-            float gr[32];
+          }
+        } else {
+          // pass 2: 16-column pieces (register budget: 96 per thread in the 640-thread layout), branch-free per element;
+          // every special case is a warp-uniform branch around a whole piece
+#pragma unroll 1
+          for (int c = 0; tile_ok && c * 16 < ncols; ++c) {
+            uint32_t rr[16];
+            tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN + c * 16, rr);
+            const int col0 = nt * C::kBN + c * 16;
+            float gr[16];
             const float4* bias4 = reinterpret_cast<const float4*>(p.bias_pad + col0);  // zero-padded copy
+            float4 bv[4];
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bv = __ldg(bias4 + j4);
-              gr[4 * j4 + 0] = __uint_as_float(rr[4 * j4 + 0]) + bv.x;
-              gr[4 * j4 + 1] = __uint_as_float(rr[4 * j4 + 1]) + bv.y;
-              gr[4 * j4 + 2] = __uint_as_float(rr[4 * j4 + 2]) + bv.z;
-              gr[4 * j4 + 3] = __uint_as_float(rr[4 * j4 + 3]) + bv.w;
+            for (int j4 = 0; j4 < 4; ++j4) bv[j4] = __ldg(bias4 + j4);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              gr[4 * j4 + 0] = __uint_as_float(rr[4 * j4 + 0]) + bv[j4].x;
+              gr[4 * j4 + 1] = __uint_as_float(rr[4 * j4 + 1]) + bv[j4].y;
+              gr[4 * j4 + 2] = __uint_as_float(rr[4 * j4 + 2]) + bv[j4].z;
+              gr[4 * j4 + 3] = __uint_as_float(rr[4 * j4 + 3]) + bv[j4].w;
             }
             if (kMode == 2) {
               // MAS importance objective: dZ = 2 z * upstream (go); nothing else to do per logit
             } else if (p.fastemit_lambda > 0.f) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
+              for (int j = 0; j < 16; ++j)
                 gr[j] = fmaf(fe_coef, tc::ex2_approx(fmaf(gr[j], kLog2e, fe_base2)),
                              tc::ex2_approx(fmaf(gr[j], kLog2e, base2)));
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) gr[j] = tc::ex2_approx(fmaf(gr[j], kLog2e, base2));
+              for (int j = 0; j < 16; ++j) gr[j] = tc::ex2_approx(fmaf(gr[j], kLog2e, base2));
             }
-            if (col0 + 32 > p.Vp) {  // padded tail columns of the operand
+            if (col0 + 16 > p.Vp) {  // padded tail columns of the operand
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
+              for (int j = 0; j < 16; ++j)
                 if (col0 + j >= p.Vp) gr[j] = 0.f;
             }
-            if (kMode == 1 && p.blank >= col0 && p.blank < col0 + 32) {
+            if (kMode == 1 && p.blank >= col0 && p.blank < col0 + 16) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
+              for (int j = 0; j < 16; ++j)
                 if (col0 + j == p.blank) gr[j] -= blank_sub;
             }
-            if (kMode == 1 && __any_sync(0xffffffffu, label >= col0 && label < col0 + 32)) {
+            if (kMode == 1 && __any_sync(0xffffffffu, label >= col0 && label < col0 + 16)) {
               const int jl = label - col0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
+              for (int j = 0; j < 16; ++j)
                 if (j == jl) gr[j] -= label_sub;
             }
             if (kMode == 1 && p.clamp > 0.f) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) gr[j] = fmaxf(fminf(gr[j], p.clamp), -p.clamp);
+              for (int j = 0; j < 16; ++j) gr[j] = fmaxf(fminf(gr[j], p.clamp), -p.clamp);
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) gr[j] *= go;
-            if (p.dzb && p.blank >= col0 && p.blank < col0 + 32) {
+            for (int j = 0; j < 16; ++j) gr[j] *= go;
+            if (p.dzb && p.blank >= col0 && p.blank < col0 + 16) {
               float zb_ = 0.f;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
+              for (int j = 0; j < 16; ++j)
                 if (col0 + j == p.blank) zb_ = gr[j];
               p.dzb[grow] = zb_;
             }
-            __nv_bfloat16* dh = p.dz_hi + grow * p.ldz + col0;
-            __nv_bfloat16* dl = p.dz_lo + grow * p.ldz + col0;
+            {  // ldz is a multiple of 16: the piece is one whole 32-byte sector of the hi (and lo) operand row
+              uint32_t ph[8], pl[8];
 #pragma unroll
-            for (int j8 = 0; j8 < 32; j8 += 8) {
-              if (col0 + j8 < p.ldz) {  // ldz is a multiple of 8: whole 16-byte groups
-                uint32_t ph[4], pl[4];
-#pragma unroll
-                for (int j2 = 0; j2 < 4; ++j2) {
-                  const float g0 = gr[j8 + 2 * j2], g1 = gr[j8 + 2 * j2 + 1];
-                  __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
-                  __nv_bfloat162 ll = __floats2bfloat162_rn(g0 - __low2float(hh), g1 - __high2float(hh));
-                  ph[j2] = *reinterpret_cast<uint32_t*>(&hh);
-                  pl[j2] = *reinterpret_cast<uint32_t*>(&ll);
-                }
-                *reinterpret_cast<uint4*>(dh + j8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                if (kTerms > 1) *reinterpret_cast<uint4*>(dl + j8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              for (int j2 = 0; j2 < 8; ++j2) {
+                const float g0 = gr[2 * j2], g1 = gr[2 * j2 + 1];
+                __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
+                __nv_bfloat162 ll = __floats2bfloat162_rn(g0 - __low2float(hh), g1 - __high2float(hh));
+                ph[j2] = *reinterpret_cast<uint32_t*>(&hh);
+                pl[j2] = *reinterpret_cast<uint32_t*>(&ll);
               }
+              st_global_256(p.dz_hi + grow * p.ldz + col0, ph);
+              if (kTerms > 1) st_global_256(p.dz_lo + grow * p.ldz + col0, pl);
             }
-            // bias gradient d_b[v] = sum over cells of dZ[., v]: transpose-reduce the warp's 32 rows x 32 columns with
-            // 31 shuffles (lane l ends up with the column-(col0 + l) sum), then one coalesced fp32 RED per warp
+            // bias gradient d_b[v] = sum over cells of dZ[., v]: transpose-reduce the warp's 32 rows x 16 columns with
+            // 16 shuffles (lanes 2c and 2c+1 end up with the column-(col0 + c) sum), one coalesced fp32 RED per warp
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
+            for (int off = 16; off >= 2; off >>= 1) {
               const bool up = (lane & off) != 0;
+              const int half_n = off >> 1;  // values kept after this step
 #pragma unroll
-              for (int j = 0; j < off; ++j) {
-                const float send = up ? gr[j] : gr[j + off];
+              for (int j = 0; j < half_n; ++j) {
+                const float send = up ? gr[j] : gr[j + half_n];
                 const float recv = __shfl_xor_sync(0xffffffffu, send, off);
-                gr[j] = (up ? gr[j + off] : gr[j]) + recv;
+                gr[j] = (up ? gr[j + half_n] : gr[j]) + recv;
               }
             }
-            if (col0 + lane < p.Vp) atomicAdd(p.db_acc + col0 + lane, gr[0]);
+            gr[0] += __shfl_xor_sync(0xffffffffu, gr[0], 1);
+            if ((lane & 1) == 0 && col0 + (lane >> 1) < p.Vp) atomicAdd(p.db_acc + col0 + (lane >> 1), gr[0]);
           }
         }
         tc::tc_fence_before();
@@ -517,13 +543,14 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         if (p.sumsq) p.sumsq[((int64_t)b * p.T + t) * p.U1 + u] = ssq;
       }
     }
-  } else if (warp >= 8) {
+  } else {
+    if (kWide) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ============================ A producers: act(f + g) -> bf16 UMMA tiles ============================
     // Warp pw owns the 32 rows [32q, 32q+32) of the tile (q = pw & 3: the TMEM lane quarter it may write) and the
     // 32-wide K half `half = pw >> 2` of every 64-wide K block.  Compute mapping: half-warp hs handles one row at a
     // time (16 lanes x 2 consecutive k = 128 contiguous bytes of ef / eg per row), 16 row pairs per K block.  The lo
     // halves are transposed through a warp-private smem tile (no block-level barrier) into the warp's TMEM lanes.
-    const int pw = warp - 8;
+    const int pw = warp - kProdWarp0;
     const int q = pw & 3, half = pw >> 2;
     const int hs = lane >> 4, c = lane & 15;
     const uint32_t a_base = tc::smem_u32(a_smem);
@@ -563,14 +590,14 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tab + lane * 8), "r"(fo), "r"(go_) : "memory");
       }
       __syncwarp();
-      float2 fa[8], ga[8], fb[8], gb[8];
+      float2 fa[kBatch], ga[kBatch], fb[kBatch], gb[kBatch];
       uint32_t oka = 0, okb = 0;
-      auto load_batch = [&](int kb, int batch, float2 (&fo)[8], float2 (&go_)[8], uint32_t& ok) {
+      auto load_batch = [&](int kb, int batch, float2 (&fo)[kBatch], float2 (&go_)[kBatch], uint32_t& ok) {
         const int kcol = kb * kJK + half * 32 + 2 * c;
         ok = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int i = batch * 8 + j;
+        for (int j = 0; j < kBatch; ++j) {
+          const int i = batch * kBatch + j;
           const int rl = (i & 3) + 8 * (i >> 2) + 4 * hs;
           const int2 o = tc::ld_shared_i2(tab + rl * 8);
           if (o.x >= 0) {
@@ -583,11 +610,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           }
         }
       };
-      auto compute_batch = [&](int kb, int batch, const float2 (&fi)[8], const float2 (&gi)[8], uint32_t okm) {
+      auto compute_batch = [&](int kb, int batch, const float2 (&fi)[kBatch], const float2 (&gi)[kBatch],
+                               uint32_t okm) {
         const uint32_t ablk = a_base + kb * C::kABlockBytes;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int i = batch * 8 + j;
+        for (int j = 0; j < kBatch; ++j) {
+          const int i = batch * kBatch + j;
           const bool ok = (okm >> j) & 1u;
           float h0 = joint_combine<kAct>(fi[j].x, gi[j].x);
           float h1 = joint_combine<kAct>(fi[j].y, gi[j].y);
@@ -609,14 +637,20 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       };
       load_batch(0, 0, fa, ga, oka);
       for (int kb = 0; kb < kblocks; ++kb) {
-        load_batch(kb, 1, fb, gb, okb);
-        if (tile_it > 0) {  // the previous row tile's last MMAs on this K block have retired
-          tc::mbar_wait(&a_free[kb], (tile_it - 1) & 1);
-          tc::tc_fence_after();
+        // software pipeline over the kNB batches of the block: the loads of batch i+1 are in flight while batch i is
+        // computed (two register buffers, ping-pong; kNB is even, so a K block always starts on buffer a)
+#pragma unroll
+        for (int bi = 0; bi < kNB; bi += 2) {
+          load_batch(kb, bi + 1, fb, gb, okb);
+          if (bi == 0 && tile_it > 0) {  // the previous row tile's last MMAs on this K block have retired
+            tc::mbar_wait(&a_free[kb], (tile_it - 1) & 1);
+            tc::tc_fence_after();
+          }
+          compute_batch(kb, bi, fa, ga, oka);
+          if (bi + 2 < kNB) load_batch(kb, bi + 2, fa, ga, oka);
+          else if (kb + 1 < kblocks) load_batch(kb + 1, 0, fa, ga, oka);
+          compute_batch(kb, bi + 1, fb, gb, okb);
         }
-        compute_batch(kb, 0, fa, ga, oka);
-        if (kb + 1 < kblocks) load_batch(kb + 1, 0, fa, ga, oka);
-        compute_batch(kb, 1, fb, gb, okb);
         if (kTerms > 1) {
           // warp-private staging (row-major, swizzled) -> tensor memory: lane l owns row 32q + l of the tile
           __syncwarp();
@@ -637,12 +671,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           tc::tmem_st8(taddr, v0);
           tc::tmem_st8(taddr + 8, v1);
           if (kMode >= 1 && tile_ok) {  // pass 2: the lo halves of this lane's row (32 k = 64 contiguous bytes) for dW
-            uint4* dst = reinterpret_cast<uint4*>(p.hid_lo + ((int64_t)tile * kJM + q * 32 + lane) * p.ldh + kb * kJK +
-                                                  half * 32);
-            dst[0] = make_uint4(v0[0], v0[1], v0[2], v0[3]);
-            dst[1] = make_uint4(v0[4], v0[5], v0[6], v0[7]);
-            dst[2] = make_uint4(v1[0], v1[1], v1[2], v1[3]);
-            dst[3] = make_uint4(v1[4], v1[5], v1[6], v1[7]);
+            __nv_bfloat16* dst = p.hid_lo + ((int64_t)tile * kJM + q * 32 + lane) * p.ldh + kb * kJK + half * 32;
+            st_global_256(dst, v0);
+            st_global_256(dst + 16, v1);
           }
           tc::tmem_st_wait();
           tc::tc_fence_before();
@@ -863,7 +894,7 @@ static inline JointBwdScratch joint_bwd_scratch_carve(void* base, int B, int T, 
   JointBwdScratch sc;
   const bool x3 = precision == CLASR_PREC_BF16X3;
   sc.rows_cap = (int64_t)B * ((((int64_t)T * U1) + kJM - 1) / kJM) * kJM;
-  sc.ldz = (Vp + 7) / 8 * 8;
+  sc.ldz = (Vp + 15) / 16 * 16;
   sc.ldh = H;
   char* p = (char*)base;
   size_t off = 0;
@@ -916,15 +947,15 @@ static bool joint_use_pair() {
   return e ? atoi(e) != 0 : true;
 }
 
-template <int kTerms, int kMode, int kAct, int kPair>
+template <int kTerms, int kMode, int kAct, int kPair, int kWide>
 static int launch_joint_variant(int H, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo, const CUtensorMap& t_hid,
                                 const JointFwdParams& p, cudaStream_t s) {
   const int smem = JointCfg<kTerms, kPair>::smem_bytes(H);
-  auto kern = joint_fwd_kernel<kTerms, kMode, kAct, kPair>;
+  auto kern = joint_fwd_kernel<kTerms, kMode, kAct, kPair, kWide>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kNumSMs & ~1);
-  cfg.blockDim = dim3(kJThreads);
+  cfg.blockDim = dim3(kWide ? kJThreadsWide : kJThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -945,9 +976,16 @@ static int launch_joint_variant(int H, const CUtensorMap& tw_hi, const CUtensorM
 template <int kTerms, int kMode>
 static int launch_joint_kernel(int activation, int H, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
                                const CUtensorMap& t_hid, const JointFwdParams& p, cudaStream_t s) {
-#define CLASR_LAUNCH_JOINT(ACT)                                                                  \
-  (joint_use_pair() ? launch_joint_variant<kTerms, kMode, ACT, 1>(H, tw_hi, tw_lo, t_hid, p, s)  \
-                    : launch_joint_variant<kTerms, kMode, ACT, 0>(H, tw_hi, tw_lo, t_hid, p, s))
+  // pass 2 (kMode >= 1) runs the 640-thread layout with two epilogue warpgroups unless CLASR_JOINT_WIDE=0
+  constexpr int kW = kMode >= 1 ? 1 : 0;
+  const char* we = getenv("CLASR_JOINT_WIDE");
+  const bool wide = kW && (we ? atoi(we) != 0 : true);
+#define CLASR_LAUNCH_JOINT(ACT)                                                                             \
+  (joint_use_pair()                                                                                         \
+       ? (wide ? launch_joint_variant<kTerms, kMode, ACT, 1, kW>(H, tw_hi, tw_lo, t_hid, p, s)              \
+               : launch_joint_variant<kTerms, kMode, ACT, 1, 0>(H, tw_hi, tw_lo, t_hid, p, s))              \
+       : (wide ? launch_joint_variant<kTerms, kMode, ACT, 0, kW>(H, tw_hi, tw_lo, t_hid, p, s)              \
+               : launch_joint_variant<kTerms, kMode, ACT, 0, 0>(H, tw_hi, tw_lo, t_hid, p, s)))
   if (activation == CLASR_ACT_RELU) return CLASR_LAUNCH_JOINT(CLASR_ACT_RELU);
   if (activation == CLASR_ACT_SIGMOID) return CLASR_LAUNCH_JOINT(CLASR_ACT_SIGMOID);
   return CLASR_LAUNCH_JOINT(CLASR_ACT_TANH);
