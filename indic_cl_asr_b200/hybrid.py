@@ -61,8 +61,10 @@ class HybridRNNTCTCLoss(torch.nn.Module):
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 loss_ctc = ctc_branch()
-            for t in (encoded, encoded_len, transcript, transcript_len):
-                t.record_stream(side)
+            # no record_stream(): the inputs stay referenced by the caller / the autograd graph until backward has run,
+            # the main stream joins the side stream below, and autograd joins all streams at the end of backward;
+            # record_stream() made the caching allocator defer block reuse and fall into cudaMalloc/cudaFree churn
+            # (end-to-end step 13.5 -> 17-20 ms, erratic)
         loss_rnnt, wer, _, _ = self.joint(encoder_outputs=encoded, decoder_outputs=decoder,
                                           encoder_lengths=encoded_len, transcripts=transcript,
                                           transcript_lengths=transcript_len, compute_wer=compute_wer, **kw)  # :880-888
