@@ -341,8 +341,8 @@ class RNNTJoint(torch.nn.Module):
             return False
         if self.temperature != 1.0 or self.log_softmax:
             return False
-        if self.joint_hidden % 64 != 0:
-            return False
+        if self.joint_hidden % 64 != 0 or self.joint_hidden > 640:
+            return False  # the 128-row A tile (128 x H bf16) must fit in shared memory next to the W ring
         if isinstance(self.joint_net[-1], torch.nn.ModuleDict):
             return language_ids is not None and len(set(language_ids)) == 1
         return True
