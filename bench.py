@@ -149,8 +149,10 @@ class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region: NVML (10 ms period) when importable, else
     nvidia-smi (the B200_PROFILING.md clocks line, ~5 samples/s)."""
 
-    _REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
-                ("sw_power_cap", 0x4))
+    # NVML clocks-event (throttle) reason bits; gpu_idle (0x1) is not a throttle and is left out
+    _REASONS = (("applications_clocks_setting", 0x2), ("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sync_boost", 0x10),
+                ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80),
+                ("display_clock_setting", 0x100))
 
     def __init__(self, index):
         self.index = index
@@ -184,7 +186,7 @@ class ClockSampler:
                              capture_output=True, text=True, timeout=5).stdout.strip()
         if out:
             p = [x.strip() for x in out.split(",")]
-            names = [nm for nm, _ in self._REASONS]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
             self.samples.append((float(p[0]), float(p[1]),
                                  [nm for nm, v in zip(names, p[2:6]) if v.lower().startswith("active")]))
 
