@@ -336,8 +336,8 @@ def main_b200(args):
         flush.zero_()
         step(enc_d, dec_d, tr_d, el_d, tl_d)
     torch.cuda.synchronize()
-    kern = {k: _lib.profile_ms(k) for k in ("joint_fwd", "joint_bwd_dz", "gemm_dhid", "gemm_dw", "joint_dfg",
-                                            "rnnt_lattice", "rnnt_lse", "rnnt_grad", "ctc_lattice", "ctc_grad",
+    kern = {k: _lib.profile_ms(k) for k in ("joint_fwd", "joint_bwd_dz", "joint_dz_sweep", "gemm_dhid", "gemm_dw",
+                                            "joint_dfg", "rnnt_lattice", "rnnt_lse", "rnnt_grad", "ctc_lattice", "ctc_grad",
                                             "cl_penalty_grad")}
     kern = {k: v for k, v in kern.items() if v >= 0}
     L.clasr_set_profiling(0)
@@ -361,7 +361,17 @@ def main_b200(args):
         extra_roof["joint_fwd_bwd"] = {"bound": "tensor", "achieved": ach_all, "peak": pk["tf_sustained"],
                                        "unit": "TFLOP/s", "frac": ach_all / pk["tf_sustained"], "ms": tensor_ms,
                                        "algorithmic_flops": 3.0 * gemm_flops,
-                                       "note": "fwd + dHid + dW credited; the pass-2 logits recompute is overhead"}
+                                       "note": "fwd + dHid + dW credited; a pass-2 logits recompute "
+                                               "(CLASR_JOINT_STASH=0) is overhead"}
+        if "joint_dz_sweep" in kern:
+            # dZ from the kept logits: reads z fp32 [cells, round_up(Vp,32)], writes dZ bf16 hi+lo [cells, round_up(Vp,16)]
+            vp = c["V"] + 1
+            terms = 2 if args.precision == "bf16x3" else 1
+            by = cells * (4.0 * ((vp + 31) // 32 * 32) + 2.0 * terms * ((vp + 15) // 16 * 16))
+            ach_dz = by / (kern["joint_dz_sweep"] * 1e-3) / 1e9
+            extra_roof["joint_dz_sweep"] = {"bound": "hbm", "achieved": ach_dz, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                            "frac": ach_dz / pk["hbm_gbs"], "ms": kern["joint_dz_sweep"],
+                                            "algorithmic_bytes": by}
     elif "rnnt_lse" in kern:
         # materialised mode runs the reference's sub-batch loop (fused_batch_size = 4): several launches per step
         by = 3.0 * cells * (c["V"] + 1) * 4

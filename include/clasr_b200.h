@@ -217,14 +217,21 @@ CLASR_API int clasr_joint_rnnt_fwd(const float* f, const float* g, const float* 
                          int U1, int H, int Vp, int blank, int activation, int precision, float dropout_p,
                          uint64_t dropout_seed, float fastemit_lambda, float* costs,
                          float* sumsq /* [B,T,U1] sum_v z^2 for MAS, or NULL */, void* workspace,
-                         size_t workspace_bytes, void* stream);
+                         size_t workspace_bytes, void* stash /* or NULL */, size_t stash_bytes, void* stream);
+
+/* Optional `stash` (clasr_joint_stash_bytes): when given, pass 1 also keeps z (fp32, compact tile-row order) and the
+ * bf16 hi/lo hidden activations, and a backward call given the SAME stash computes dZ with one streaming sweep over z
+ * instead of a second joint GEMM (about 2 ms less per step at B32/T250/U100/V1024, for 4 (Vp + H) bytes per lattice
+ * cell of HBM held between the two calls).  With stash == NULL the logits are never stored and the backward pass
+ * recomputes them tile-wise — the memory-lean mode for lattices that would not fit. */
+CLASR_API size_t clasr_joint_stash_bytes(int B, int T, int U1, int H, int Vp, int precision);
 
 /* Backward.  `workspace` is the one the forward call filled (lattice, W split, tile table).  `scratch` holds the
  * GEMM operands of the backward pass (dZ and the hidden activations as bf16 hi/lo in compact tile-row order, dHid,
  * dW accumulator); it is caller-owned and reusable across steps.
- * ROUND-1 STATE: pass 2 recomputes the logits tile-wise on the tensor cores (they are still never stored), but the
- * softmax-fused gradient dZ is staged through `scratch` as bf16 hi/lo before the two tcgen05 GEMMs
- * (dHid = dZ.W, dW = dZ^T.Hid) consume it; fusing those contractions into the recompute kernel is next. */
+ * Pass 2a produces the softmax-fused gradient dZ as bf16 hi/lo in `scratch` — from the stashed logits when `stash`
+ * is given, else by recomputing the logits tile-wise on the tensor cores — and the two tcgen05 GEMMs
+ * (dHid = dZ.W, dW = dZ^T.Hid) consume it. */
 CLASR_API size_t clasr_joint_bwd_scratch_bytes(int B, int T, int U1, int H, int Vp, int precision);
 CLASR_API int clasr_joint_rnnt_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
                          const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B, int T,
@@ -232,7 +239,7 @@ CLASR_API int clasr_joint_rnnt_bwd(const float* f, const float* g, const float* 
                          uint64_t dropout_seed, float fastemit_lambda, float clamp, const float* grad_out /* [B] */,
                          float* d_f, float* d_g, float* d_w_out,
                          float* d_b_out, void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
-                         void* stream);
+                         void* stash /* the forward call's, or NULL */, size_t stash_bytes, void* stream);
 
 /* Backward of the per-cell sum_v z^2 that clasr_joint_rnnt_fwd writes into `sumsq` — the joint half of the MAS
  * importance objective (cl_baseline_mas.py:258-265: mean over the stored sub-batch logits of sum_v z^2): dZ = 2 z *
@@ -245,7 +252,7 @@ CLASR_API int clasr_joint_sumsq_bwd(const float* f, const float* g, const float*
                                     float dropout_p, uint64_t dropout_seed, const float* grad_cells, float* d_f,
                                     float* d_g, float* d_w_out, float* d_b_out,
                                     void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
-                                    void* stream);
+                                    void* stash /* the forward call's, or NULL */, size_t stash_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,10 +56,11 @@ _PROTOS: Dict[str, Tuple[object, List[object]]] = {
     "clasr_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "clasr_linear_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "clasr_joint_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "clasr_joint_rnnt_fwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, C.c_uint64, _f, _vp, _vp, _vp, _sz, _vp]),
+    "clasr_joint_rnnt_fwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, C.c_uint64, _f, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "clasr_joint_stash_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "clasr_joint_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "clasr_joint_sumsq_bwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
-    "clasr_joint_rnnt_bwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, C.c_uint64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "clasr_joint_sumsq_bwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
+    "clasr_joint_rnnt_bwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, C.c_uint64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
 }
 
 

@@ -39,7 +39,7 @@ constexpr int kJStages = 2;
 // every CTA keeps its own A tile (smem hi / TMEM lo) and loads only HALF of each W tile, so the W ring holds twice as
 // many stages in the same bytes, the L2->smem traffic per CTA halves, and an SS MMA reads 4 KB (A) + 1.5 KB (B half)
 // of shared memory per 48 clocks instead of 4 + 3 KB (the 1-CTA N = 96 MMA is smem-bandwidth-bound: r01b profile).
-template <int kTerms, int kPair = 0>
+template <int kTerms, int kPair, int kStash = 0>
 struct JointCfg {
   static constexpr int kBN = kTerms == 1 ? 256 : 96;          // accumulator tile width (TMEM columns)
   static constexpr int kParts = kTerms == 1 ? 1 : 2;          // W parts streamed per stage (hi[,lo])
@@ -48,11 +48,13 @@ struct JointCfg {
   static constexpr int kABlockBytes = kJM * kJK * 2;          // 16 KB per K block of A
   static constexpr int kBRows = kBN / (kPair ? 2 : 1);        // W rows this CTA loads per N tile
   static constexpr int kBStageBytes = kParts * kBRows * kJK * 2; // W ring stage (per CTA)
-  static constexpr int kStages = kPair ? 2 * kJStages : kJStages;
+  // kStash (kMode 3, pairs): one ring stage less (measured: no slowdown) pays for the z staging tiles
+  static constexpr int kStages = kPair ? (kStash ? 3 : 2 * kJStages) : kJStages;
+  static constexpr int kZStageBytes = (kStash && kPair) ? 4 * 2048 : 0;  // per epilogue warp: 32 rows x 16 fp32, SW64
   static constexpr int kStagingBytes = kTerms == 1 ? 0 : kJProducerWarps * 2048;  // warp-private 32x32 bf16 lo tiles
   static constexpr int kRowTabBytes = 4 * 32 * 8;             // per lane quarter: (f offset, g offset) of its 32 rows
   static constexpr int smem_bytes(int H) {
-    return (H / kJK) * kABlockBytes + kStagingBytes + kStages * kBStageBytes + kRowTabBytes + 384 + 1024;
+    return (H / kJK) * kABlockBytes + kStagingBytes + kStages * kBStageBytes + kZStageBytes + kRowTabBytes + 384 + 1024;
   }
 };
 
@@ -84,7 +86,46 @@ struct JointFwdParams {
   float* dzb;                 // [rows_pad] dZ[., blank] per compact row (feeds the blank row of dW in joint_dfg), or null
   float* db_acc;              // [Vp] bias gradient: column sums of dZ, accumulated by the pass-2 epilogue (zeroed first)
   int* rows_pad_dev;          // [1] total_tiles * 128 (written by the tile-offset kernel)
+  // ---- kMode 3 (forward that keeps the logits for the backward): z = logits + bias, fp32, compact tile-row order
+  float* zbuf;                // [rows_pad, ldzf]
+  int ldzf;                   // round_up(Vp, 32): whole 32-column epilogue pieces
 };
+
+// Per-row scalars of the softmax-fused gradient (same algebra as rnnt_grad_kernel, gpu_rnnt_kernel.py:351-396), with
+// the exponents pre-scaled by log2(e) so that each logit costs one FFMA + one MUFU.EX2:
+//   dZ[v] = go * clamp( 2^(z log2e + base2) + fe_coef 2^(z log2e + fe_base2) - [v==blank] blank_sub - [v==label] label_sub )
+// Padding rows: base2 = -inf, go = 0 -> dZ = 0.   kMode 2 (MAS): dZ = go * z with go = 2 * upstream.
+struct RowGrad {
+  float base2, fe_base2, fe_coef, blank_sub, label_sub, go;
+};
+
+template <int kMode>
+__device__ __forceinline__ RowGrad joint_row_grad(const JointFwdParams& p, int b, int t, int u, int Tb, int Ub1,
+                                                  bool valid) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  RowGrad rg;
+  rg.base2 = -INFINITY; rg.fe_base2 = -INFINITY; rg.fe_coef = 0.f; rg.blank_sub = 0.f; rg.label_sub = 0.f; rg.go = 0.f;
+  if (kMode == 2 && valid) rg.go = 2.f * p.grad_cells[((int64_t)b * p.T + t) * p.U1 + u];  // d(sum z^2)/dz = 2z
+  if (kMode == 1 && valid) {
+    const int64_t idx = ((int64_t)b * p.w.ND + t + u) * p.U1 + u;
+    const double a = p.w.alpha[idx], bt = p.w.beta[idx], ll = p.w.ll_fwd[b];
+    const float dn = p.w.denom[idx];
+    const float2 lpair = p.w.lp[idx];
+    rg.go = p.grad_out ? p.grad_out[b] : 1.f;
+    const bool has_label = u < Ub1 - 1;
+    const double beta_t1 = (t < Tb - 1) ? p.w.beta[idx + p.U1] : 0.0;
+    const double beta_u1 = has_label ? p.w.beta[idx + p.U1 + 1] : 0.0;
+    rg.base2 = ((float)(a + bt - ll) + dn) * kLog2e;
+    if (p.fastemit_lambda > 0.f && has_label) {
+      rg.fe_coef = p.fastemit_lambda;
+      rg.fe_base2 = ((float)(a + beta_u1 - ll + (double)lpair.y) + dn) * kLog2e;
+    }
+    if (t == Tb - 1 && u == Ub1 - 1) rg.blank_sub += expf((float)(a - ll + (double)lpair.x));
+    if (t < Tb - 1) rg.blank_sub += expf((float)(a + beta_t1 - ll + (double)lpair.x));
+    rg.label_sub = has_label ? expf(log1pf(p.fastemit_lambda) + (float)(a + beta_u1 - ll + (double)lpair.y)) : 0.f;
+  }
+  return rg;
+}
 
 __device__ __forceinline__ float joint_act(float x, int act) {
   if (act == CLASR_ACT_RELU) return fmaxf(x, 0.f);
@@ -165,20 +206,25 @@ __device__ __forceinline__ int find_utterance(const int* __restrict__ offs, int 
 template <int kTerms, int kMode, int kAct, int kPair, int kWide>
 __global__ void __launch_bounds__(kWide ? kJThreadsWide : kJThreads, 1)
 joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                 const __grid_constant__ CUtensorMap tmHid, JointFwdParams p) {
-  using C = JointCfg<kTerms, kPair>;
+                 const __grid_constant__ CUtensorMap tmHid, const __grid_constant__ CUtensorMap tmZ, JointFwdParams p) {
+  using C = JointCfg<kTerms, kPair, kMode == 3>;
+  constexpr bool kZStage = C::kZStageBytes > 0;   // z leaves through swizzled smem tiles + TMA stores
   constexpr int kStages = C::kStages;
   constexpr int kEpiWarps = kWide ? 8 : 4;
   constexpr int kProdWarp0 = 4 + kEpiWarps;          // first producer warp (a multiple of 4: warp % 4 = TMEM quarter)
   constexpr int kBatch = kWide ? 4 : 8;              // row pairs per producer load batch (register budget)
   constexpr int kNB = 16 / kBatch;
+  // kMode 0: forward statistics;  3: the same + keep z and Hid for the backward;  1 / 2: gradient passes (recompute)
+  constexpr bool kStats = kMode == 0 || kMode == 3;
+  constexpr bool kGrad = kMode == 1 || kMode == 2;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   const int kblocks = p.H / kJK;
   uint8_t* a_smem = smem;                                          // [kblocks][128 x 64 bf16], SW128 K-major
   uint8_t* staging = a_smem + kblocks * C::kABlockBytes;            // BF16X3 only: 8 warps x [32 rows x 32 k] bf16
   uint8_t* b_ring = staging + C::kStagingBytes;                     // [stages][parts][BN x 64 bf16]
-  uint8_t* rowtab = b_ring + kStages * C::kBStageBytes;             // int2[4 quarters][32 rows]
+  uint8_t* zstage = b_ring + kStages * C::kBStageBytes;             // kZStage: [4 epilogue warps][32 rows x 64 B]
+  uint8_t* rowtab = zstage + C::kZStageBytes;                       // int2[4 quarters][32 rows]
   uint64_t* bars = (uint64_t*)(rowtab + C::kRowTabBytes);
   uint64_t* full = bars;                 // [kStages]  W stage landed            (pair: the leader's copy)
   uint64_t* empty = full + kStages;      // [kStages]  W stage consumed
@@ -207,6 +253,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     tc::prefetch_tmap(&tmW_hi);
     if (kTerms > 1) tc::prefetch_tmap(&tmW_lo);
     if (kMode >= 1) tc::prefetch_tmap(&tmHid);
+    if (kZStage) tc::prefetch_tmap(&tmZ);
   }
   if (warp == 1 && tc::elect_one()) {
     constexpr int kCtas = kPair ? 2 : 1;
@@ -380,29 +427,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       const int label = (valid && u < Ub1 - 1) ? (int)p.labels[(int64_t)b * (p.U1 - 1) + u] : -1;
       const int64_t idx = ((int64_t)b * p.w.ND + t + u) * p.U1 + u;
       float m = -INFINITY, s = 0.f, zb = 0.f, zl = 0.f, ssq = 0.f;
-      // pass-2 per-row scalars (same algebra as rnnt_grad_kernel, gpu_rnnt_kernel.py:351-396), exponents pre-scaled
-      // by log2(e) so that each logit costs one FFMA + one MUFU.EX2.  Padding rows: base2 = -inf, go = 0 -> dZ = 0.
-      constexpr float kLog2e = 1.4426950408889634f;
-      float base2 = -INFINITY, fe_base2 = -INFINITY, fe_coef = 0.f, blank_sub = 0.f, label_sub = 0.f, go = 0.f;
-      if (kMode == 2 && valid) go = 2.f * p.grad_cells[((int64_t)b * p.T + t) * p.U1 + u];  // d(sum z^2)/dz = 2z
-      if (kMode == 1 && valid) {
-        const double a = p.w.alpha[idx], bt = p.w.beta[idx], ll = p.w.ll_fwd[b];
-        const float dn = p.w.denom[idx];
-        const float2 lpair = p.w.lp[idx];
-        go = p.grad_out ? p.grad_out[b] : 1.f;
-        const bool has_label = u < Ub1 - 1;
-        const double beta_t1 = (t < Tb - 1) ? p.w.beta[idx + p.U1] : 0.0;
-        const double beta_u1 = has_label ? p.w.beta[idx + p.U1 + 1] : 0.0;
-        base2 = ((float)(a + bt - ll) + dn) * kLog2e;
-        if (p.fastemit_lambda > 0.f && has_label) {
-          fe_coef = p.fastemit_lambda;
-          fe_base2 = ((float)(a + beta_u1 - ll + (double)lpair.y) + dn) * kLog2e;
-        }
-        if (t == Tb - 1 && u == Ub1 - 1) blank_sub += expf((float)(a - ll + (double)lpair.x));
-        if (t < Tb - 1) blank_sub += expf((float)(a + beta_t1 - ll + (double)lpair.x));
-        label_sub = has_label ? expf(log1pf(p.fastemit_lambda) + (float)(a + beta_u1 - ll + (double)lpair.y)) : 0.f;
-      }
       const int64_t grow = (int64_t)tile * kJM + row;  // compact tile-row index of this thread's row
+      // pass-2 per-row scalars (joint_row_grad)
+      constexpr float kLog2e = 1.4426950408889634f;
+      const RowGrad rg = joint_row_grad<kGrad ? kMode : 0>(p, b, t, u, Tb, Ub1, valid);
+      const float base2 = rg.base2, fe_base2 = rg.fe_base2, fe_coef = rg.fe_coef, blank_sub = rg.blank_sub,
+                  label_sub = rg.label_sub, go = rg.go;
       for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
         const int acc = acc_it & 1;
         const uint32_t acc_phase = (acc_it >> 1) & 1;
@@ -410,33 +440,101 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         tc::mbar_wait(&tmem_full[acc], acc_phase);
         tc::tc_fence_after();
         // columns this N tile must cover: up to Vp (stats) or up to the padded operand width ldz (gradient)
-        const int width = (kMode >= 1 ? p.ldz : p.Vp);
+        const int width = (kGrad ? p.ldz : p.Vp);
         const int ncols = (nt == n_tiles - 1) ? (width - nt * C::kBN) : C::kBN;
-        if (kMode == 0) {
+        if (kStats) {
 #pragma unroll 1
           for (int c = 0; tile_ok && c * 32 < ncols; ++c) {
             uint32_t rr[32];
             tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN + c * 32, rr);
-            tc::tmem_ld_wait();
             const int col0 = nt * C::kBN + c * 32;
+            // branch-free per element; every special case (tail columns, blank, label, sum of squares) is a
+            // warp-uniform branch around the whole piece.  bias_pad is zero-padded to whole pieces.
+            const float4* bias4 = reinterpret_cast<const float4*>(p.bias_pad + col0);
+            float4 bv[8];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) bv[j4] = __ldg(bias4 + j4);
+            tc::tmem_ld_wait();
             float z[32];
-            float cm = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              const bool in = col < p.Vp;
-              z[j] = in ? __uint_as_float(rr[j]) + __ldg(p.bias + (in ? col : 0)) : -INFINITY;
-              cm = fmaxf(cm, z[j]);
-              if (col == p.blank) zb = z[j];
-              if (col == label) zl = z[j];
-              if (in) ssq = fmaf(z[j], z[j], ssq);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              z[4 * j4 + 0] = __uint_as_float(rr[4 * j4 + 0]) + bv[j4].x;
+              z[4 * j4 + 1] = __uint_as_float(rr[4 * j4 + 1]) + bv[j4].y;
+              z[4 * j4 + 2] = __uint_as_float(rr[4 * j4 + 2]) + bv[j4].z;
+              z[4 * j4 + 3] = __uint_as_float(rr[4 * j4 + 3]) + bv[j4].w;
             }
-            if (cm > m) {
-              s *= __expf(m - cm);
-              m = cm;
-            }
+            const bool tail = col0 + 32 > p.Vp;
+            if (p.sumsq) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) s += __expf(z[j] - m);
+              for (int j = 0; j < 32; ++j) {
+                const float zz = (tail && col0 + j >= p.Vp) ? 0.f : z[j];
+                ssq = fmaf(zz, zz, ssq);
+              }
+            }
+            if (tail) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j >= p.Vp) z[j] = -INFINITY;
+            }
+            if (p.blank >= col0 && p.blank < col0 + 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j == p.blank) zb = z[j];
+            }
+            if (__any_sync(0xffffffffu, label >= col0 && label < col0 + 32)) {
+              const int jl = label - col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j == jl) zl = z[j];
+            }
+            float cm = z[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) cm = fmaxf(cm, z[j]);
+            // running maximum in the log2 domain: every term is 2^(z log2e - m) with the SAME rounded m, so the
+            // rounding of m cancels in lse = (m + log2 s) ln 2
+            const float cm2 = cm * kLog2e;
+            if (cm2 > m) {
+              s *= tc::ex2_approx(m - cm2);
+              m = cm2;
+            }
+            const float nm2 = -m;   // finite: the first piece of a row always holds valid columns
+            if (kMode == 3 && kZStage) {
+              // keep the logits: the warp's 32 rows x 32 columns leave as two [32 x 16] fp32 boxes through a
+              // 64-byte-swizzled smem tile and a TMA store (row-per-lane global stores would cost the LSU one
+              // wavefront per 32 bytes — measured +0.7 ms, taken from the A producers that share it)
+              const uint32_t zs = tc::smem_u32(zstage) + q * 2048;
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                if (lane == 0) tc::bulk_wait_group_read0();  // the previous box has been read out of the tile
+                __syncwarp();
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+                  tc::st_shared_v4(zs + lane * 64 + ((c4 ^ ((lane >> 1) & 3)) * 16), __float_as_uint(z[16 * hf + 4 * c4]),
+                                   __float_as_uint(z[16 * hf + 4 * c4 + 1]), __float_as_uint(z[16 * hf + 4 * c4 + 2]),
+                                   __float_as_uint(z[16 * hf + 4 * c4 + 3]));
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tc::tma_store_2d(&tmZ, zstage + q * 2048, col0 + 16 * hf, tile * kJM + q * 32);
+                  tc::bulk_commit_group();
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s += tc::ex2_approx(fmaf(z[16 * hf + j], kLog2e, nm2));
+              }
+            } else {
+              if (kMode == 3) {  // 1-CTA variant: row-per-lane 256-bit stores
+                float* zrow = p.zbuf + grow * p.ldzf + col0;
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                  uint32_t pk[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) pk[j] = __float_as_uint(z[8 * j8 + j]);
+                  st_global_256(zrow + 8 * j8, pk);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s += tc::ex2_approx(fmaf(z[j], kLog2e, nm2));
+            }
           }
         } else {
           // pass 2: 16-column pieces (register budget: 96 per thread in the 640-thread layout), branch-free per element;
@@ -536,12 +634,16 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           else tc::mbar_arrive(&tmem_empty[acc]);
         }
       }
-      if (kMode == 0 && valid) {
-        const float lse = m + logf(s);
+      if (kStats && valid) {
+        const float lse = (m + log2f(s)) * 0.6931471805599453f;
         p.w.denom[idx] = -lse;
         p.w.lp[idx] = make_float2(zb - lse, label >= 0 ? zl - lse : -INFINITY);
         if (p.sumsq) p.sumsq[((int64_t)b * p.T + t) * p.U1 + u] = ssq;
       }
+    }
+    if (kZStage) {  // all z boxes written before the CTA (and its shared memory) goes away
+      if (lane == 0) tc::bulk_wait_group0();
+      __syncwarp();
     }
   } else {
     if (kWide) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
@@ -696,6 +798,177 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     if (kPair) tc::tmem_dealloc_2sm(tmem_base, 512);
     else tc::tmem_dealloc(tmem_base, 512);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward pass 2a when the forward kept the logits (kMode 3): dZ from z in ONE streaming sweep instead of a second
+// joint GEMM.  Reads z [rows_pad, ldzf] fp32, writes dZ as bf16 hi/lo GEMM operands [rows_pad, ldz], dZ[., blank]
+// and the bias gradient.  A thread owns one 8-column group for the whole kernel (column sums stay in registers,
+// one RED per column per block at the end); a block walks chunks of kDzRows rows whose per-row scalars
+// (joint_row_grad) are computed once into shared memory.  Algorithmic bytes per lattice cell: 4 ldzf + 4 ldz.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDzRows = 32;        // rows per chunk (one scalar set per row, computed by one warp)
+constexpr int kDzBatch = 4;        // rows whose loads are in flight per thread (2 x LDG.128 each)
+constexpr int kDzMaxGroups = 512;  // 8-column groups per block (beyond that: blockIdx.y chunks)
+constexpr int kDzMaxThreads = kDzMaxGroups + 32;
+
+struct DzRowScalars {
+  float base2[kDzRows], fe_base2[kDzRows], fe_coef[kDzRows], blank_sub[kDzRows], label_sub[kDzRows], go[kDzRows];
+  int label[kDzRows];
+};
+
+// `groups` = column groups per block (a multiple of 32 is NOT required).  The LAST warp of the block computes the
+// next chunk's row scalars into the other half of a double buffer while the block streams the current chunk; the
+// launcher adds a warp for it when the last column warp would be more than half busy.
+template <int kTerms, int kMode>
+__global__ void __maxnreg__(80) joint_dz_kernel(JointFwdParams p, int groups) {
+  __shared__ DzRowScalars sc[2];
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int ncg = p.ldz >> 3;
+  const int cg = blockIdx.y * groups + threadIdx.x;
+  const bool col_ok = (int)threadIdx.x < groups && cg < ncg;
+  const int col0 = cg * 8;
+  const int rows_pad = p.rows_pad_dev[0];
+  const int nchunks = rows_pad / kDzRows;  // rows_pad is a multiple of 128
+  const bool has_blank = p.blank >= col0 && p.blank < col0 + 8;
+  const int scalar_lane = (int)threadIdx.x - ((int)blockDim.x - 32);  // >= 0: this thread belongs to the scalar warp
+  float db[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) db[j] = 0.f;
+
+  auto fill_scalars = [&](int chunk, DzRowScalars& o) {
+    const int i = scalar_lane;
+    const int64_t grow = (int64_t)chunk * kDzRows + i;
+    const int tile = (int)(grow / kJM);
+    const int b = find_utterance(p.tile_offsets, p.B, tile);
+    const int Tb = (int)p.act_lens[b], Ub1 = (int)p.label_lens[b] + 1;
+    const int r = (tile - p.tile_offsets[b]) * kJM + (int)(grow % kJM);
+    const bool valid = r < Tb * Ub1;
+    const int t = valid ? r / Ub1 : 0;
+    const int u = valid ? r - t * Ub1 : 0;
+    const RowGrad rg = joint_row_grad<kMode>(p, b, t, u, Tb, Ub1, valid);
+    o.base2[i] = rg.base2; o.fe_base2[i] = rg.fe_base2; o.fe_coef[i] = rg.fe_coef;
+    o.blank_sub[i] = rg.blank_sub; o.label_sub[i] = rg.label_sub; o.go[i] = rg.go;
+    o.label[i] = (valid && u < Ub1 - 1) ? (int)p.labels[(int64_t)b * (p.U1 - 1) + u] : -1;
+  };
+
+  if (scalar_lane >= 0 && (int)blockIdx.x < nchunks) fill_scalars(blockIdx.x, sc[0]);
+  __syncthreads();
+  int it = 0;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+    const DzRowScalars& cur = sc[it & 1];
+    if (scalar_lane >= 0 && chunk + (int)gridDim.x < nchunks) fill_scalars(chunk + gridDim.x, sc[(it + 1) & 1]);
+    if (col_ok) {
+      const int64_t grow0 = (int64_t)chunk * kDzRows;
+#pragma unroll 1
+      for (int r0 = 0; r0 < kDzRows; r0 += kDzBatch) {
+        float4 za[kDzBatch], zb[kDzBatch];
+#pragma unroll
+        for (int j = 0; j < kDzBatch; ++j) {  // all loads of the batch first: they do not move past the stores below
+          const float4* zp = reinterpret_cast<const float4*>(p.zbuf + (grow0 + r0 + j) * p.ldzf + col0);
+          za[j] = ld_stream(zp);
+          zb[j] = ld_stream(zp + 1);
+        }
+#pragma unroll
+        for (int jr = 0; jr < kDzBatch; ++jr) {
+          const int r = r0 + jr;
+          const int64_t grow = grow0 + r;
+          float gr[8] = {za[jr].x, za[jr].y, za[jr].z, za[jr].w, zb[jr].x, zb[jr].y, zb[jr].z, zb[jr].w};
+          const float go = cur.go[r];
+          if (kMode == 1) {
+            const float base2 = cur.base2[r];
+            if (p.fastemit_lambda > 0.f) {
+              const float fe_coef = cur.fe_coef[r], fe_base2 = cur.fe_base2[r];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                gr[j] = fmaf(fe_coef, tc::ex2_approx(fmaf(gr[j], kLog2e, fe_base2)),
+                             tc::ex2_approx(fmaf(gr[j], kLog2e, base2)));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gr[j] = tc::ex2_approx(fmaf(gr[j], kLog2e, base2));
+            }
+          }
+          if (col0 + 8 > p.Vp) {  // padded tail columns of the operand
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col0 + j >= p.Vp) gr[j] = 0.f;
+          }
+          if (kMode == 1) {
+            if (has_blank) {
+              const float bs = cur.blank_sub[r];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (col0 + j == p.blank) gr[j] -= bs;
+            }
+            const int jl = cur.label[r] - col0;
+            if (jl >= 0 && jl < 8) {
+              const float ls = cur.label_sub[r];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j == jl) gr[j] -= ls;
+            }
+            if (p.clamp > 0.f) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gr[j] = fmaxf(fminf(gr[j], p.clamp), -p.clamp);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            gr[j] *= go;
+            db[j] += gr[j];
+          }
+          if (p.dzb && has_blank) {
+            float zb_ = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col0 + j == p.blank) zb_ = gr[j];
+            p.dzb[grow] = zb_;
+          }
+          uint4 ph, pl;
+          uint32_t* phw = reinterpret_cast<uint32_t*>(&ph);
+          uint32_t* plw = reinterpret_cast<uint32_t*>(&pl);
+#pragma unroll
+          for (int j2 = 0; j2 < 4; ++j2) {
+            const float g0 = gr[2 * j2], g1 = gr[2 * j2 + 1];
+            __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
+            __nv_bfloat162 ll = __floats2bfloat162_rn(g0 - __low2float(hh), g1 - __high2float(hh));
+            phw[j2] = *reinterpret_cast<uint32_t*>(&hh);
+            plw[j2] = *reinterpret_cast<uint32_t*>(&ll);
+          }
+          *reinterpret_cast<uint4*>(p.dz_hi + grow * p.ldz + col0) = ph;
+          if (kTerms > 1) *reinterpret_cast<uint4*>(p.dz_lo + grow * p.ldz + col0) = pl;
+        }
+      }
+    }
+    __syncthreads();  // the next chunk's scalars are complete; this chunk's are no longer read
+  }
+  if (col_ok) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (col0 + j < p.Vp) atomicAdd(p.db_acc + col0 + j, db[j]);
+  }
+}
+
+template <int kTerms, int kMode>
+static int launch_joint_dz(const JointFwdParams& p, cudaStream_t s) {
+  const int ncg = p.ldz / 8;
+  const int ychunks = (ncg + kDzMaxGroups - 1) / kDzMaxGroups;
+  const int groups = (ncg + ychunks - 1) / ychunks;
+  int threads = (groups + 31) / 32 * 32;
+  const int last = groups - (threads - 32);            // column lanes of the last warp
+  if (last > 16) threads += 32;                        // dedicated scalar warp
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, joint_dz_kernel<kTerms, kMode>, threads, 0);
+  if (per_sm < 1) per_sm = 1;
+  int gx = kNumSMs * per_sm / ychunks;
+  if (gx < 1) gx = 1;
+  joint_dz_kernel<kTerms, kMode><<<dim3(gx, ychunks), threads, 0, s>>>(p, groups);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("joint_dz launch: %s", cudaGetErrorString(e));
+    return CLASR_STATUS_CUDA_ERROR;
+  }
+  return CLASR_STATUS_SUCCESS;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -909,6 +1182,31 @@ static inline JointBwdScratch joint_bwd_scratch_carve(void* base, int B, int T, 
   return sc;
 }
 
+// What a kMode-3 forward leaves behind for the backward: the logits and the bf16 hi/lo hidden activations (caller-
+// allocated, lives from the forward call to the backward call).
+struct JointStash {
+  float* z;                     // [rows_cap, ldzf]
+  void* hid_hi; void* hid_lo;   // [rows_cap, H] bf16
+  int64_t rows_cap;
+  int ldzf;
+  size_t total;
+};
+
+static inline JointStash joint_stash_carve(void* base, int B, int T, int U1, int H, int Vp, int precision) {
+  JointStash st;
+  const bool x3 = precision == CLASR_PREC_BF16X3;
+  st.rows_cap = (int64_t)B * ((((int64_t)T * U1) + kJM - 1) / kJM) * kJM;
+  st.ldzf = (Vp + 31) / 32 * 32;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* r = p + off; off += (bytes + 255) / 256 * 256; return r; };
+  st.z = (float*)take((size_t)st.rows_cap * st.ldzf * 4);
+  st.hid_hi = take((size_t)st.rows_cap * H * 2);
+  st.hid_lo = x3 ? take((size_t)st.rows_cap * H * 2) : st.hid_hi;
+  st.total = off;
+  return st;
+}
+
 static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, int Vp, int precision) {
   JointWs j;
   char* p = (char*)base;
@@ -949,8 +1247,8 @@ static bool joint_use_pair() {
 
 template <int kTerms, int kMode, int kAct, int kPair, int kWide>
 static int launch_joint_variant(int H, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo, const CUtensorMap& t_hid,
-                                const JointFwdParams& p, cudaStream_t s) {
-  const int smem = JointCfg<kTerms, kPair>::smem_bytes(H);
+                                const CUtensorMap& t_z, const JointFwdParams& p, cudaStream_t s) {
+  const int smem = JointCfg<kTerms, kPair, kMode == 3>::smem_bytes(H);
   auto kern = joint_fwd_kernel<kTerms, kMode, kAct, kPair, kWide>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaLaunchConfig_t cfg = {};
@@ -965,7 +1263,7 @@ static int launch_joint_variant(int H, const CUtensorMap& tw_hi, const CUtensorM
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tw_hi, tw_lo, t_hid, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tw_hi, tw_lo, t_hid, t_z, p);
   if (e != cudaSuccess) {
     set_error("joint kernel launch: %s", cudaGetErrorString(e));
     return CLASR_STATUS_CUDA_ERROR;
@@ -975,17 +1273,18 @@ static int launch_joint_variant(int H, const CUtensorMap& tw_hi, const CUtensorM
 
 template <int kTerms, int kMode>
 static int launch_joint_kernel(int activation, int H, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
-                               const CUtensorMap& t_hid, const JointFwdParams& p, cudaStream_t s) {
-  // pass 2 (kMode >= 1) runs the 640-thread layout with two epilogue warpgroups unless CLASR_JOINT_WIDE=0
-  constexpr int kW = kMode >= 1 ? 1 : 0;
+                               const CUtensorMap& t_hid, const CUtensorMap& t_z, const JointFwdParams& p,
+                               cudaStream_t s) {
+  // pass 2 (kMode 1 / 2) runs the 640-thread layout with two epilogue warpgroups unless CLASR_JOINT_WIDE=0
+  constexpr int kW = (kMode == 1 || kMode == 2) ? 1 : 0;
   const char* we = getenv("CLASR_JOINT_WIDE");
   const bool wide = kW && (we ? atoi(we) != 0 : true);
 #define CLASR_LAUNCH_JOINT(ACT)                                                                             \
   (joint_use_pair()                                                                                         \
-       ? (wide ? launch_joint_variant<kTerms, kMode, ACT, 1, kW>(H, tw_hi, tw_lo, t_hid, p, s)              \
-               : launch_joint_variant<kTerms, kMode, ACT, 1, 0>(H, tw_hi, tw_lo, t_hid, p, s))              \
-       : (wide ? launch_joint_variant<kTerms, kMode, ACT, 0, kW>(H, tw_hi, tw_lo, t_hid, p, s)              \
-               : launch_joint_variant<kTerms, kMode, ACT, 0, 0>(H, tw_hi, tw_lo, t_hid, p, s)))
+       ? (wide ? launch_joint_variant<kTerms, kMode, ACT, 1, kW>(H, tw_hi, tw_lo, t_hid, t_z, p, s)              \
+               : launch_joint_variant<kTerms, kMode, ACT, 1, 0>(H, tw_hi, tw_lo, t_hid, t_z, p, s))              \
+       : (wide ? launch_joint_variant<kTerms, kMode, ACT, 0, kW>(H, tw_hi, tw_lo, t_hid, t_z, p, s)              \
+               : launch_joint_variant<kTerms, kMode, ACT, 0, 0>(H, tw_hi, tw_lo, t_hid, t_z, p, s)))
   if (activation == CLASR_ACT_RELU) return CLASR_LAUNCH_JOINT(CLASR_ACT_RELU);
   if (activation == CLASR_ACT_SIGMOID) return CLASR_LAUNCH_JOINT(CLASR_ACT_SIGMOID);
   return CLASR_LAUNCH_JOINT(CLASR_ACT_TANH);
@@ -1043,11 +1342,16 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
                                     const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
                                     int T, int U1, int H, int Vp, int blank, int activation, int precision,
                                     float dropout_p, uint64_t dropout_seed, float fastemit_lambda, float* costs,
-                                    float* sumsq, void* workspace, size_t workspace_bytes, void* stream) {
+                                    float* sumsq, void* workspace, size_t workspace_bytes, void* stash,
+                                    size_t stash_bytes, void* stream) {
   int rc = check_joint_args("joint_rnnt_fwd", f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank,
                             activation, precision, workspace, workspace_bytes);
   if (rc) return rc;
   CLASR_CHECK_ARG(costs, "joint_rnnt_fwd: null costs");
+  if (stash) {
+    CLASR_CHECK_ARG(stash_bytes >= clasr_joint_stash_bytes(B, T, U1, H, Vp, precision), "joint_rnnt_fwd: stash too small");
+    CLASR_CHECK_ARG((((uintptr_t)stash) & 255) == 0, "joint_rnnt_fwd: stash must be 256-byte aligned");
+  }
   cudaStream_t s = (cudaStream_t)stream;
   JointWs jw = joint_ws_carve(workspace, B, T, U1, H, Vp, precision);
   const bool x3 = precision == CLASR_PREC_BF16X3;
@@ -1075,12 +1379,30 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
     tw_lo = tw_hi;
   }
   prof_begin("joint_fwd", s);
-  rc = x3 ? launch_joint_kernel<3, 0>(activation, H, tw_hi, tw_lo, tw_hi /*unused in pass 1*/, p, s)
-          : launch_joint_kernel<1, 0>(activation, H, tw_hi, tw_lo, tw_hi, p, s);
+  if (stash) {  // keep z and Hid for the backward (kMode 3)
+    JointStash st = joint_stash_carve(stash, B, T, U1, H, Vp, precision);
+    CLASR_CHECK_ARG(st.rows_cap < 2147483647LL, "joint_rnnt_fwd: too many lattice cells");
+    p.zbuf = st.z; p.ldzf = st.ldzf;
+    p.hid_hi = (__nv_bfloat16*)st.hid_hi; p.hid_lo = (__nv_bfloat16*)st.hid_lo; p.ldh = H;
+    CUtensorMap t_hid, t_z;
+    if ((rc = make_tmap_bf16_2d(&t_hid, st.hid_hi, (uint64_t)st.rows_cap, H, H, kJM, kJK))) return rc;
+    // TMA-store view of z: [rows_cap, ldzf] fp32, box = 32 rows x 16 columns (64-byte rows, 64-byte swizzle)
+    if ((rc = make_tmap_2d(&t_z, st.z, (uint64_t)st.rows_cap, st.ldzf, st.ldzf, 32, 16, 4, 64))) return rc;
+    rc = x3 ? launch_joint_kernel<3, 3>(activation, H, tw_hi, tw_lo, t_hid, t_z, p, s)
+            : launch_joint_kernel<1, 3>(activation, H, tw_hi, tw_lo, t_hid, t_z, p, s);
+  } else {
+    rc = x3 ? launch_joint_kernel<3, 0>(activation, H, tw_hi, tw_lo, tw_hi /*unused in pass 1*/, tw_hi, p, s)
+            : launch_joint_kernel<1, 0>(activation, H, tw_hi, tw_lo, tw_hi, tw_hi, p, s);
+  }
   if (rc) return rc;
   prof_end("joint_fwd", s);
   CLASR_CHECK_LAUNCH("joint_fwd");
   return launch_rnnt_lattice(p.w, act_lens, label_lens, B, T, U1, fastemit_lambda, costs, s);
+}
+
+extern "C" size_t clasr_joint_stash_bytes(int B, int T, int U1, int H, int Vp, int precision) {
+  if (B <= 0 || T <= 0 || U1 <= 0 || H <= 0 || Vp <= 0) return 0;
+  return joint_stash_carve(nullptr, B, T, U1, H, Vp, precision).total;
 }
 
 extern "C" size_t clasr_joint_bwd_scratch_bytes(int B, int T, int U1, int H, int Vp, int precision) {
@@ -1095,7 +1417,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
                           uint64_t dropout_seed, float fastemit_lambda, float clamp, const float* grad_out,
                           const float* grad_cells, float* d_f, float* d_g, float* d_w_out,
                           float* d_b_out, void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
-                          void* stream) {
+                          void* stash, size_t stash_bytes, void* stream) {
   int rc = check_joint_args("joint_rnnt_bwd", f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank,
                             activation, precision, workspace, workspace_bytes);
   if (rc) return rc;
@@ -1105,6 +1427,10 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
                   "joint_rnnt_bwd: scratch too small");
   CLASR_CHECK_ARG((((uintptr_t)scratch) & 255) == 0, "joint_rnnt_bwd: scratch must be 256-byte aligned");
   CLASR_CHECK_ARG((H & 3) == 0, "joint_rnnt_bwd: H must be a multiple of 4");
+  if (stash) {
+    CLASR_CHECK_ARG(stash_bytes >= clasr_joint_stash_bytes(B, T, U1, H, Vp, precision), "joint_rnnt_bwd: stash too small");
+    CLASR_CHECK_ARG((((uintptr_t)stash) & 255) == 0, "joint_rnnt_bwd: stash must be 256-byte aligned");
+  }
   cudaStream_t s = (cudaStream_t)stream;
   const bool x3 = precision == CLASR_PREC_BF16X3;
   JointWs jw = joint_ws_carve(workspace, B, T, U1, H, Vp, precision);   // filled by the forward call
@@ -1145,18 +1471,32 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   } else {
     tw_lo = tw_hi;
   }
-  prof_begin("joint_bwd_dz", s);
-  CUtensorMap t_hid;  // TMA-store view of Hid_hi: [rows_cap, H] bf16, box = one 128 x 64 A block
-  if ((rc = make_tmap_bf16_2d(&t_hid, sc.hid_hi, (uint64_t)sc.rows_cap, H, sc.ldh, kJM, kJK))) return rc;
-  if (mode == 1)
-    rc = x3 ? launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, t_hid, p, s)
-            : launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, t_hid, p, s);
-  else
-    rc = x3 ? launch_joint_kernel<3, 2>(activation, H, tw_hi, tw_lo, t_hid, p, s)
-            : launch_joint_kernel<1, 2>(activation, H, tw_hi, tw_lo, t_hid, p, s);
-  if (rc) return rc;
-  prof_end("joint_bwd_dz", s);
-  CLASR_CHECK_LAUNCH("joint_bwd_dz");
+  const void* hid_hi = sc.hid_hi;
+  const void* hid_lo = sc.hid_lo;
+  if (stash) {
+    // the forward call kept z and Hid (kMode 3): dZ is one streaming sweep over z
+    JointStash st = joint_stash_carve(stash, B, T, U1, H, Vp, precision);
+    p.zbuf = st.z; p.ldzf = st.ldzf;
+    hid_hi = st.hid_hi; hid_lo = st.hid_lo;
+    prof_begin("joint_dz_sweep", s);
+    if (mode == 1) rc = x3 ? launch_joint_dz<3, 1>(p, s) : launch_joint_dz<1, 1>(p, s);
+    else rc = x3 ? launch_joint_dz<3, 2>(p, s) : launch_joint_dz<1, 2>(p, s);
+    if (rc) return rc;
+    prof_end("joint_dz_sweep", s);
+  } else {
+    prof_begin("joint_bwd_dz", s);
+    CUtensorMap t_hid;  // TMA-store view of Hid_hi: [rows_cap, H] bf16, box = one 128 x 64 A block
+    if ((rc = make_tmap_bf16_2d(&t_hid, sc.hid_hi, (uint64_t)sc.rows_cap, H, sc.ldh, kJM, kJK))) return rc;
+    if (mode == 1)
+      rc = x3 ? launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+              : launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s);
+    else
+      rc = x3 ? launch_joint_kernel<3, 2>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+              : launch_joint_kernel<1, 2>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s);
+    if (rc) return rc;
+    prof_end("joint_bwd_dz", s);
+    CLASR_CHECK_LAUNCH("joint_bwd_dz");
+  }
 
   // ---- pass 2b: dHid[rows, H] = dZ[rows, Vp] . W[Vp, H]      (A K-major, B = W consumed MN-major: no transpose)
   prof_begin("gemm_dhid", s);
@@ -1166,7 +1506,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   prof_end("gemm_dhid", s);
   // ---- pass 2c: dW[Vp, H] = dZ^T . Hid       (both operands MN-major, split-K over the rows, fp32 atomics)
   prof_begin("gemm_dw", s);
-  if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, sc.hid_hi, sc.hid_lo, sc.ldh, 1, blank_split ? Vp - 1 : Vp, H,
+  if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, hid_hi, hid_lo, sc.ldh, 1, blank_split ? Vp - 1 : Vp, H,
                            (int)sc.rows_cap, d_w_out, H, precision, 1, /*auto split-K*/ 0, s, nullptr, rows_pad_dev)))
     return rc;
   prof_end("gemm_dw", s);
@@ -1213,10 +1553,10 @@ extern "C" int clasr_joint_rnnt_bwd(const float* f, const float* g, const float*
                                     float dropout_p, uint64_t dropout_seed, float fastemit_lambda, float clamp,
                                     const float* grad_out, float* d_f, float* d_g, float* d_w_out, float* d_b_out,
                                     void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
-                                    void* stream) {
+                                    void* stash, size_t stash_bytes, void* stream) {
   return joint_bwd_impl(1, f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank, activation,
                         precision, dropout_p, dropout_seed, fastemit_lambda, clamp, grad_out, nullptr, d_f, d_g, d_w_out, d_b_out, workspace,
-                        workspace_bytes, scratch, scratch_bytes, stream);
+                        workspace_bytes, scratch, scratch_bytes, stash, stash_bytes, stream);
 }
 
 extern "C" int clasr_joint_sumsq_bwd(const float* f, const float* g, const float* w_out, const float* b_out,
@@ -1225,10 +1565,10 @@ extern "C" int clasr_joint_sumsq_bwd(const float* f, const float* g, const float
                                      float dropout_p, uint64_t dropout_seed, const float* grad_cells, float* d_f,
                                      float* d_g, float* d_w_out, float* d_b_out,
                                      void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
-                                     void* stream) {
+                                     void* stash, size_t stash_bytes, void* stream) {
   CLASR_CHECK_ARG(grad_cells, "joint_sumsq_bwd: null grad_cells");
   return joint_bwd_impl(2, f, g, w_out, b_out, labels, act_lens, label_lens, B, T, U1, H, Vp, blank, activation,
                         precision, dropout_p, dropout_seed, 0.f, 0.f, nullptr, grad_cells, d_f, d_g, d_w_out, d_b_out,
                         workspace, workspace_bytes,
-                        scratch, scratch_bytes, stream);
+                        scratch, scratch_bytes, stash, stash_bytes, stream);
 }

@@ -31,6 +31,9 @@ __device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 r;
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
@@ -312,5 +315,8 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 // so the library still loads on a GPU-less host for the ABI test).
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                       uint32_t box_rows, uint32_t box_cols);
+// general form: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 128 or 64 (= box_cols * elem_bytes)
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                 uint32_t box_rows, uint32_t box_cols, int elem_bytes, int swizzle_bytes);
 
 }  // namespace clasr

@@ -7,12 +7,33 @@ RNNTLoss with reduction=None (:1475-1508) — without the [B,T,U+1,V+1] logits e
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
 
 __all__ = ["fused_joint_rnnt_loss", "fused_joint_forward_stats", "fused_joint_sumsq", "LazySubLogits",
            "dropout_mask_reference"]
+
+
+def _stash_limit_bytes() -> int:
+    """CLASR_JOINT_STASH: "0" = never keep the logits (the backward pass recomputes them), a number = the largest
+    stash in GiB that a forward call may allocate (default 48 GiB of the B200's 180)."""
+    v = os.environ.get("CLASR_JOINT_STASH", "")
+    gib = 48.0 if v == "" else float(v)
+    return int(gib * (1 << 30))
+
+
+def _stash(f, B, T, U1, H, Vp, prec, needs_grad):
+    """(tensor | None, nbytes): the logits / hidden-activation stash a differentiated forward call leaves for its
+    backward call (include/clasr_b200.h: clasr_joint_stash_bytes)."""
+    if not needs_grad:
+        return None, 0
+    nbytes = _lib.lib().clasr_joint_stash_bytes(B, T, U1, H, Vp, prec)
+    if nbytes == 0 or nbytes > _stash_limit_bytes():
+        return None, 0
+    return torch.empty(nbytes, dtype=torch.uint8, device=f.device), nbytes
 
 
 def _ws(f, B, T, U1, H, Vp, prec):
@@ -28,6 +49,7 @@ class _FusedJointRNNT(torch.autograd.Function):
         _lib.require_cuda(f, "f")
         if clamp < 0:
             raise ValueError("`clamp` must be 0.0 or positive float value.")
+        needs_grad = any(ctx.needs_input_grad[:4])
         f = f.contiguous().float()
         g = g.contiguous().float()
         weight = weight.contiguous().float()
@@ -46,6 +68,7 @@ class _FusedJointRNNT(torch.autograd.Function):
             labels = labels[:, : U1 - 1].contiguous()
         prec = _lib.PREC[precision]
         ws, nbytes = _ws(f, B, T, U1, H, Vp, prec)
+        stash, stash_bytes = _stash(f, B, T, U1, H, Vp, prec, needs_grad)
         costs = torch.empty(B, dtype=torch.float32, device=f.device)
         sumsq = torch.zeros(B, T, U1, dtype=torch.float32, device=f.device) if want_sumsq else None
         L = _lib.lib()
@@ -54,9 +77,10 @@ class _FusedJointRNNT(torch.autograd.Function):
                 f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
                 act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, int(blank), _lib.ACT[activation], prec,
                 float(dropout_p), int(dropout_seed), float(fastemit_lambda), costs.data_ptr(), _lib.ptr(sumsq),
-                ws.data_ptr(), nbytes, _lib.stream_ptr(f.device))
+                ws.data_ptr(), nbytes, _lib.ptr(stash), stash_bytes, _lib.stream_ptr(f.device))
         _lib.check(st, "joint_rnnt_fwd")
         ctx.save_for_backward(f, g, weight, bias, labels, act_lens, label_lens, ws)
+        ctx.stash = (stash, stash_bytes)
         ctx.args = (int(blank), _lib.ACT[activation], prec, float(fastemit_lambda), float(clamp), nbytes,
                     float(dropout_p), int(dropout_seed))
         if want_sumsq:
@@ -68,6 +92,7 @@ class _FusedJointRNNT(torch.autograd.Function):
     def backward(ctx, grad_costs, *unused):
         f, g, weight, bias, labels, act_lens, label_lens, ws = ctx.saved_tensors
         blank, act, prec, fastemit_lambda, clamp, nbytes, dropout_p, dropout_seed = ctx.args
+        stash, stash_bytes = ctx.stash
         B, T, H = f.shape
         U1 = g.shape[1]
         Vp = weight.shape[0]
@@ -84,7 +109,9 @@ class _FusedJointRNNT(torch.autograd.Function):
                 f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
                 act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, blank, act, prec, dropout_p, dropout_seed,
                 fastemit_lambda, clamp, go.data_ptr(), d_f.data_ptr(), d_g.data_ptr(), d_w.data_ptr(), d_b.data_ptr(),
-                ws.data_ptr(), nbytes, scratch.data_ptr(), sbytes, _lib.stream_ptr(f.device))
+                ws.data_ptr(), nbytes, scratch.data_ptr(), sbytes, _lib.ptr(stash), stash_bytes,
+                _lib.stream_ptr(f.device))
+        ctx.stash = (None, 0)   # the logits are dead once dZ exists
         _lib.check(st, "joint_rnnt_bwd")
         return (d_f, d_g, d_w, d_b) + (None,) * 11
 
@@ -143,6 +170,7 @@ class _FusedJointSumsq(torch.autograd.Function):
     def forward(ctx, f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision, dropout_p=0.0,
                 dropout_seed=0):
         _lib.require_cuda(f, "f")
+        needs_grad = any(ctx.needs_input_grad[:4])
         f = f.contiguous().float()
         g = g.contiguous().float()
         weight = weight.contiguous().float()
@@ -155,6 +183,7 @@ class _FusedJointSumsq(torch.autograd.Function):
         label_lens = label_lens.contiguous().long()
         prec = _lib.PREC[precision]
         ws, nbytes = _ws(f, B, T, U1, H, Vp, prec)
+        stash, stash_bytes = _stash(f, B, T, U1, H, Vp, prec, needs_grad)
         costs = torch.empty(B, dtype=torch.float32, device=f.device)  # by-product of the same pass; not used here
         sumsq = torch.zeros(B, T, U1, dtype=torch.float32, device=f.device)
         L = _lib.lib()
@@ -163,9 +192,10 @@ class _FusedJointSumsq(torch.autograd.Function):
                 f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
                 act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, int(blank), _lib.ACT[activation], prec,
                 float(dropout_p), int(dropout_seed), 0.0, costs.data_ptr(), sumsq.data_ptr(), ws.data_ptr(), nbytes,
-                _lib.stream_ptr(f.device))
+                _lib.ptr(stash), stash_bytes, _lib.stream_ptr(f.device))
         _lib.check(st, "joint_rnnt_fwd")
         ctx.save_for_backward(f, g, weight, bias, labels, act_lens, label_lens, ws)
+        ctx.stash = (stash, stash_bytes)
         ctx.args = (int(blank), _lib.ACT[activation], prec, nbytes, float(dropout_p), int(dropout_seed))
         return sumsq
 
@@ -173,6 +203,7 @@ class _FusedJointSumsq(torch.autograd.Function):
     def backward(ctx, grad_sumsq):
         f, g, weight, bias, labels, act_lens, label_lens, ws = ctx.saved_tensors
         blank, act, prec, nbytes, dropout_p, dropout_seed = ctx.args
+        stash, stash_bytes = ctx.stash
         B, T, H = f.shape
         U1 = g.shape[1]
         Vp = weight.shape[0]
@@ -187,7 +218,8 @@ class _FusedJointSumsq(torch.autograd.Function):
                 f.data_ptr(), g.data_ptr(), weight.data_ptr(), bias.data_ptr(), _lib.ptr(labels) if U1 > 1 else 0,
                 act_lens.data_ptr(), label_lens.data_ptr(), B, T, U1, H, Vp, blank, act, prec, dropout_p, dropout_seed,
                 gc.data_ptr(), d_f.data_ptr(), d_g.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ws.data_ptr(), nbytes,
-                scratch.data_ptr(), sbytes, _lib.stream_ptr(f.device))
+                scratch.data_ptr(), sbytes, _lib.ptr(stash), stash_bytes, _lib.stream_ptr(f.device))
+        ctx.stash = (None, 0)
         _lib.check(st, "joint_sumsq_bwd")
         return (d_f, d_g, d_w, d_b) + (None,) * 8
 

@@ -58,7 +58,10 @@ def test_forward_costs_and_sumsq(B, T, U, V, H, act, precision):
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
 @pytest.mark.parametrize("B,T,U,V,H,act", [(2, 9, 4, 20, 64, "tanh"), (3, 40, 17, 256, 128, "relu"),
                                            (2, 33, 12, 1024, 640, "tanh")])
-def test_backward(B, T, U, V, H, act, precision):
+@pytest.mark.parametrize("stash", ["", "0"], ids=["stash", "recompute"])
+def test_backward(B, T, U, V, H, act, precision, stash, monkeypatch):
+    # both backward modes: dZ from the logits the forward kept (default) / from a tile-wise recompute (CLASR_JOINT_STASH=0)
+    monkeypatch.setenv("CLASR_JOINT_STASH", stash)
     f, g, W, b, lab, al, ll = make(B, T, U, V, H, seed=7 * B + T + V)
     fd, gd, Wd, bd = [x.to(DEV).requires_grad_(True) for x in (f, g, W, b)]
     costs = fused_joint_rnnt_loss(fd, gd, Wd, bd, lab.to(DEV), al.to(DEV), ll.to(DEV), V, act, precision)
