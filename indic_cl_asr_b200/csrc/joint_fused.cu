@@ -50,7 +50,7 @@ struct JointCfg {
   static constexpr int kBStageBytes = kParts * kBRows * kJK * 2; // W ring stage (per CTA)
   // kStash (kMode 3, pairs): one ring stage less (measured: no slowdown) pays for the z staging tiles
   static constexpr int kStages = kPair ? (kStash ? 3 : 2 * kJStages) : kJStages;
-  static constexpr int kZStageBytes = (kStash && kPair) ? 4 * 2048 : 0;  // per epilogue warp: 32 rows x 16 fp32, SW64
+  static constexpr int kZStageBytes = (kStash && kPair) ? 4 * 2048 : 0;  // per epilogue warp: 2 tiles of 32 rows x 8 fp32, SW32
   static constexpr int kStagingBytes = kTerms == 1 ? 0 : kJProducerWarps * 2048;  // warp-private 32x32 bf16 lo tiles
   static constexpr int kRowTabBytes = 4 * 32 * 8;             // per lane quarter: (f offset, g offset) of its 32 rows
   static constexpr int smem_bytes(int H) {
@@ -90,6 +90,22 @@ struct JointFwdParams {
   float* zbuf;                // [rows_pad, ldzf]
   int ldzf;                   // round_up(Vp, 32): whole 32-column epilogue pieces
 };
+
+// Developer instrumentation (built only with -DCLASR_TRACE, never into the product library): cycles each role spends
+// in its barrier waits, per CTA.  Slots: 0 MMA<-tmem_empty, 1 MMA<-a_ready, 2 MMA<-full, 3 epilogue<-tmem_full (warp 4),
+// 4 producer<-a_free (first producer warp), 5 TMA<-empty, 6 total kernel cycles, 7 epilogue z-store waits.
+#ifdef CLASR_TRACE
+__device__ unsigned long long g_joint_trace[160 * 8];
+#define CLASR_TRACE_DECL unsigned long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tr_t0 = clock64();
+#define CLASR_TRACE_WAIT(slot, stmt) do { const long long t_ = clock64(); stmt; tr_acc[slot] += (unsigned long long)(clock64() - t_); } while (0)
+#define CLASR_TRACE_FLUSH(slot) do { if (lane == 0) g_joint_trace[blockIdx.x * 8 + (slot)] = tr_acc[slot]; } while (0)
+#define CLASR_TRACE_TOTAL() do { if (threadIdx.x == 0) g_joint_trace[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - tr_t0); } while (0)
+#else
+#define CLASR_TRACE_DECL
+#define CLASR_TRACE_WAIT(slot, stmt) stmt
+#define CLASR_TRACE_FLUSH(slot)
+#define CLASR_TRACE_TOTAL()
+#endif
 
 // Per-row scalars of the softmax-fused gradient (same algebra as rnnt_grad_kernel, gpu_rnnt_kernel.py:351-396), with
 // the exponents pre-scaled by log2(e) so that each logit costs one FFMA + one MUFU.EX2:
@@ -223,7 +239,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   uint8_t* a_smem = smem;                                          // [kblocks][128 x 64 bf16], SW128 K-major
   uint8_t* staging = a_smem + kblocks * C::kABlockBytes;            // BF16X3 only: 8 warps x [32 rows x 32 k] bf16
   uint8_t* b_ring = staging + C::kStagingBytes;                     // [stages][parts][BN x 64 bf16]
-  uint8_t* zstage = b_ring + kStages * C::kBStageBytes;             // kZStage: [4 epilogue warps][32 rows x 64 B]
+  uint8_t* zstage = b_ring + kStages * C::kBStageBytes;             // kZStage: [4 epilogue warps][2 tiles][32 rows x 32 B]
   uint8_t* rowtab = zstage + C::kZStageBytes;                       // int2[4 quarters][32 rows]
   uint64_t* bars = (uint64_t*)(rowtab + C::kRowTabBytes);
   uint64_t* full = bars;                 // [kStages]  W stage landed            (pair: the leader's copy)
@@ -238,6 +254,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
 
   const int warp = tc::warp_idx_uniform();
   const int lane = threadIdx.x & 31;
+  CLASR_TRACE_DECL
   const int total_tiles = (int)tc::uniform_u32((uint32_t)p.tile_offsets[p.B]);
   // pair mode: the cluster walks PAIRS of consecutive row tiles; this CTA owns tile 2*step + rank (possibly a null
   // tile past the end, which still takes part in every barrier hand-shake)
@@ -292,7 +309,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         const int n_cur = (nt == n_tiles - 1) ? n_last : C::kBN;
         const int n0 = nt * C::kBN + (kPair ? (int)cta_rank * (n_cur / 2) : 0);
         for (int kb = 0; kb < kblocks; ++kb) {
-          tc::mbar_wait(&empty[stage], phase ^ 1);
+          CLASR_TRACE_WAIT(5, tc::mbar_wait(&empty[stage], phase ^ 1));
           if (tc::elect_one()) {
             uint8_t* st = b_ring + stage * C::kBStageBytes;
             if (kPair) {
@@ -327,12 +344,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         const uint32_t acc_phase = (acc_it >> 1) & 1;
         const bool last_nt = nt == n_tiles - 1;
         const uint32_t idesc = last_nt ? idesc_last : idesc_full;
-        tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        CLASR_TRACE_WAIT(0, tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1));
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::kBN;
         for (int kb = 0; kb < kblocks; ++kb) {
-          if (nt == 0) tc::mbar_wait(&a_ready[kb], tile_phase);
-          tc::mbar_wait(&full[stage], phase);
+          if (nt == 0) CLASR_TRACE_WAIT(1, tc::mbar_wait(&a_ready[kb], tile_phase));
+          CLASR_TRACE_WAIT(2, tc::mbar_wait(&full[stage], phase));
           tc::tc_fence_after();
           if (tc::elect_one()) {
             const uint32_t a_hi = a_base + kb * C::kABlockBytes;
@@ -437,7 +454,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         const int acc = acc_it & 1;
         const uint32_t acc_phase = (acc_it >> 1) & 1;
         if (kWide && acc != egrp) continue;
-        tc::mbar_wait(&tmem_full[acc], acc_phase);
+        CLASR_TRACE_WAIT(3, tc::mbar_wait(&tmem_full[acc], acc_phase));
         tc::tc_fence_after();
         // columns this N tile must cover: up to Vp (stats) or up to the padded operand width ldz (gradient)
         const int width = (kGrad ? p.ldz : p.Vp);
@@ -499,27 +516,27 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             }
             const float nm2 = -m;   // finite: the first piece of a row always holds valid columns
             if (kMode == 3 && kZStage) {
-              // keep the logits: the warp's 32 rows x 32 columns leave as two [32 x 16] fp32 boxes through a
-              // 64-byte-swizzled smem tile and a TMA store (row-per-lane global stores would cost the LSU one
-              // wavefront per 32 bytes — measured +0.7 ms, taken from the A producers that share it)
+              // keep the logits: the warp's 32 rows x 32 columns leave as four [32 x 8] fp32 boxes through two
+              // alternating 32-byte-swizzled smem tiles and TMA stores.  (Row-per-lane global stores cost the LSU a
+              // wavefront per 32 bytes, and a single tile exposes the TMA's read latency twice per piece.)
               const uint32_t zs = tc::smem_u32(zstage) + q * 2048;
 #pragma unroll
-              for (int hf = 0; hf < 2; ++hf) {
-                if (lane == 0) tc::bulk_wait_group_read0();  // the previous box has been read out of the tile
-                __syncwarp();
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4)
-                  tc::st_shared_v4(zs + lane * 64 + ((c4 ^ ((lane >> 1) & 3)) * 16), __float_as_uint(z[16 * hf + 4 * c4]),
-                                   __float_as_uint(z[16 * hf + 4 * c4 + 1]), __float_as_uint(z[16 * hf + 4 * c4 + 2]),
-                                   __float_as_uint(z[16 * hf + 4 * c4 + 3]));
+              for (int sb = 0; sb < 4; ++sb) {
+                CLASR_TRACE_WAIT(7, if (lane == 0) tc::bulk_wait_group_read1(); __syncwarp());  // the box stored from THIS tile two steps ago is out
+                const uint32_t zt = zs + (sb & 1) * 1024 + lane * 32;
+                const int sw = (lane >> 2) & 1;
+                tc::st_shared_v4(zt + ((0 ^ sw) * 16), __float_as_uint(z[8 * sb + 0]), __float_as_uint(z[8 * sb + 1]),
+                                 __float_as_uint(z[8 * sb + 2]), __float_as_uint(z[8 * sb + 3]));
+                tc::st_shared_v4(zt + ((1 ^ sw) * 16), __float_as_uint(z[8 * sb + 4]), __float_as_uint(z[8 * sb + 5]),
+                                 __float_as_uint(z[8 * sb + 6]), __float_as_uint(z[8 * sb + 7]));
                 tc::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                  tc::tma_store_2d(&tmZ, zstage + q * 2048, col0 + 16 * hf, tile * kJM + q * 32);
+                  tc::tma_store_2d(&tmZ, zstage + q * 2048 + (sb & 1) * 1024, col0 + 8 * sb, tile * kJM + q * 32);
                   tc::bulk_commit_group();
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) s += tc::ex2_approx(fmaf(z[16 * hf + j], kLog2e, nm2));
+                for (int j = 0; j < 8; ++j) s += tc::ex2_approx(fmaf(z[8 * sb + j], kLog2e, nm2));
               }
             } else {
               if (kMode == 3) {  // 1-CTA variant: row-per-lane 256-bit stores
@@ -745,7 +762,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         for (int bi = 0; bi < kNB; bi += 2) {
           load_batch(kb, bi + 1, fb, gb, okb);
           if (bi == 0 && tile_it > 0) {  // the previous row tile's last MMAs on this K block have retired
-            tc::mbar_wait(&a_free[kb], (tile_it - 1) & 1);
+            CLASR_TRACE_WAIT(4, tc::mbar_wait(&a_free[kb], (tile_it - 1) & 1));
             tc::tc_fence_after();
           }
           compute_batch(kb, bi, fa, ga, oka);
@@ -790,6 +807,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       }
     }
   }
+#ifdef CLASR_TRACE
+  if (warp == 0) CLASR_TRACE_FLUSH(5);
+  if (warp == 1 && leader) { CLASR_TRACE_FLUSH(0); CLASR_TRACE_FLUSH(1); CLASR_TRACE_FLUSH(2); }
+  if (warp == 4) { CLASR_TRACE_FLUSH(3); CLASR_TRACE_FLUSH(7); }
+  if (warp == kProdWarp0) CLASR_TRACE_FLUSH(4);
+#endif
   tc::tc_fence_before();
   if (kPair) tc::cluster_sync_all();  // nobody leaves while the peer may still read its smem / signal its barriers
   else __syncthreads();
@@ -798,6 +821,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     if (kPair) tc::tmem_dealloc_2sm(tmem_base, 512);
     else tc::tmem_dealloc(tmem_base, 512);
   }
+  CLASR_TRACE_TOTAL();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1386,8 +1410,8 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
     p.hid_hi = (__nv_bfloat16*)st.hid_hi; p.hid_lo = (__nv_bfloat16*)st.hid_lo; p.ldh = H;
     CUtensorMap t_hid, t_z;
     if ((rc = make_tmap_bf16_2d(&t_hid, st.hid_hi, (uint64_t)st.rows_cap, H, H, kJM, kJK))) return rc;
-    // TMA-store view of z: [rows_cap, ldzf] fp32, box = 32 rows x 16 columns (64-byte rows, 64-byte swizzle)
-    if ((rc = make_tmap_2d(&t_z, st.z, (uint64_t)st.rows_cap, st.ldzf, st.ldzf, 32, 16, 4, 64))) return rc;
+    // TMA-store view of z: [rows_cap, ldzf] fp32, box = 32 rows x 8 columns (32-byte rows, 32-byte swizzle)
+    if ((rc = make_tmap_2d(&t_z, st.z, (uint64_t)st.rows_cap, st.ldzf, st.ldzf, 32, 8, 4, 32))) return rc;
     rc = x3 ? launch_joint_kernel<3, 3>(activation, H, tw_hi, tw_lo, t_hid, t_z, p, s)
             : launch_joint_kernel<1, 3>(activation, H, tw_hi, tw_lo, t_hid, t_z, p, s);
   } else {
@@ -1572,3 +1596,11 @@ extern "C" int clasr_joint_sumsq_bwd(const float* f, const float* g, const float
                         workspace, workspace_bytes,
                         scratch, scratch_bytes, stash, stash_bytes, stream);
 }
+
+#ifdef CLASR_TRACE
+// developer builds only: copies the per-CTA wait-cycle counters of the LAST joint kernel launch to host memory
+extern "C" __attribute__((visibility("default"))) int clasr_debug_joint_trace(unsigned long long* out_host, int n) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out_host, clasr::g_joint_trace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif

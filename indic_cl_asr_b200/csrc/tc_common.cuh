@@ -119,6 +119,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk groups of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -315,7 +316,7 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 // so the library still loads on a GPU-less host for the ABI test).
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                       uint32_t box_rows, uint32_t box_cols);
-// general form: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 128 or 64 (= box_cols * elem_bytes)
+// general form: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 128, 64 or 32 (>= box_cols * elem_bytes)
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                  uint32_t box_rows, uint32_t box_cols, int elem_bytes, int swizzle_bytes);
 
