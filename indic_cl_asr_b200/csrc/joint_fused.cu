@@ -93,13 +93,14 @@ struct JointFwdParams {
 
 // Developer instrumentation (built only with -DCLASR_TRACE, never into the product library): cycles each role spends
 // in its barrier waits, per CTA.  Slots: 0 MMA<-tmem_empty, 1 MMA<-a_ready, 2 MMA<-full, 3 epilogue<-tmem_full (warp 4),
-// 4 producer<-a_free (first producer warp), 5 TMA<-empty, 6 total kernel cycles, 7 epilogue z-store waits.
+// 4 producer<-a_free (first producer warp), 5 TMA<-empty, 6 total kernel cycles, 7 epilogue z-store waits,
+// 8 producer load+activation phase, 9 producer lo-transpose + tcgen05.st phase, 10 producer fence + arrive.
 #ifdef CLASR_TRACE
-__device__ unsigned long long g_joint_trace[160 * 8];
-#define CLASR_TRACE_DECL unsigned long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tr_t0 = clock64();
+__device__ unsigned long long g_joint_trace[160 * 12];
+#define CLASR_TRACE_DECL unsigned long long tr_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long tr_t0 = clock64();
 #define CLASR_TRACE_WAIT(slot, stmt) do { const long long t_ = clock64(); stmt; tr_acc[slot] += (unsigned long long)(clock64() - t_); } while (0)
-#define CLASR_TRACE_FLUSH(slot) do { if (lane == 0) g_joint_trace[blockIdx.x * 8 + (slot)] = tr_acc[slot]; } while (0)
-#define CLASR_TRACE_TOTAL() do { if (threadIdx.x == 0) g_joint_trace[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - tr_t0); } while (0)
+#define CLASR_TRACE_FLUSH(slot) do { if (lane == 0) g_joint_trace[blockIdx.x * 12 + (slot)] = tr_acc[slot]; } while (0)
+#define CLASR_TRACE_TOTAL() do { if (threadIdx.x == 0) g_joint_trace[blockIdx.x * 12 + 6] = (unsigned long long)(clock64() - tr_t0); } while (0)
 #else
 #define CLASR_TRACE_DECL
 #define CLASR_TRACE_WAIT(slot, stmt) stmt
@@ -303,6 +304,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     // ============================ TMA producer: W ring (whole warp loops, one elected lane issues) ===========
     int stage = 0;
     uint32_t phase = 0;
+    const uint64_t pol_keep = tc::l2_policy_evict_last();
     for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
       for (int nt = 0; nt < n_tiles; ++nt) {
         // pair: this CTA loads rows [n0 + rank * width/2, +kBRows) of the W tile (the MMA reads width/2 of them)
@@ -314,8 +316,14 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             uint8_t* st = b_ring + stage * C::kBStageBytes;
             if (kPair) {
               if (leader) tc::mbar_expect_tx(&full[stage], 2 * C::kBStageBytes);
-              tc::tma_load_2d_2sm(st, &tmW_hi, &full[stage], kb * kJK, n0);
-              if (kTerms > 1) tc::tma_load_2d_2sm(st + C::kBRows * kJK * 2, &tmW_lo, &full[stage], kb * kJK, n0);
+              if (kMode >= 1) {  // the kernel streams GBs of stores through L2: keep the 2.6 MB of W resident
+                tc::tma_load_2d_2sm_hint(st, &tmW_hi, &full[stage], kb * kJK, n0, pol_keep);
+                if (kTerms > 1)
+                  tc::tma_load_2d_2sm_hint(st + C::kBRows * kJK * 2, &tmW_lo, &full[stage], kb * kJK, n0, pol_keep);
+              } else {
+                tc::tma_load_2d_2sm(st, &tmW_hi, &full[stage], kb * kJK, n0);
+                if (kTerms > 1) tc::tma_load_2d_2sm(st + C::kBRows * kJK * 2, &tmW_lo, &full[stage], kb * kJK, n0);
+              }
             } else {
               tc::mbar_expect_tx(&full[stage], C::kBStageBytes);
               tc::tma_load_2d(st, &tmW_hi, &full[stage], kb * kJK, n0);
@@ -404,12 +412,13 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     // [128 rows x 64 k] blocks = exactly a TMA box): one elected lane stores each block with a TMA store as soon as
     // the producers have written it, and releases the block (second arrival on a_free) once the store has read it.
     int tile_it = 0;
+    const uint64_t pol_stream = tc::l2_policy_evict_first();
     for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++tile_it) {
       const bool tile_ok = tile < total_tiles;
       for (int kb = 0; kb < kblocks; ++kb) {
         tc::mbar_wait(&hid_ready[kb], tile_it & 1);
         if (tile_ok && tc::elect_one()) {
-          tc::tma_store_2d(&tmHid, a_smem + kb * C::kABlockBytes, kb * kJK, tile * kJM);
+          tc::tma_store_2d_hint(&tmHid, a_smem + kb * C::kABlockBytes, kb * kJK, tile * kJM, pol_stream);
           tc::bulk_commit_group();
         }
         __syncwarp();
@@ -431,6 +440,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     //          bf16 hi/lo and written in tile-row order as the operand of the two backward GEMMs (pass 2)
     const int q = warp & 3;
     const int egrp = (warp - 4) >> 2;   // kWide: this warpgroup serves accumulator buffer `egrp` only
+    const uint64_t pol_stream = tc::l2_policy_evict_first();
+    (void)pol_stream;
     const int row = q * 32 + lane;
     int acc_it = 0;
     for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
@@ -532,7 +543,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
                 tc::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                  tc::tma_store_2d(&tmZ, zstage + q * 2048 + (sb & 1) * 1024, col0 + 8 * sb, tile * kJM + q * 32);
+                  tc::tma_store_2d_hint(&tmZ, zstage + q * 2048 + (sb & 1) * 1024, col0 + 8 * sb, tile * kJM + q * 32,
+                                        pol_stream);
                   tc::bulk_commit_group();
                 }
 #pragma unroll
@@ -758,6 +770,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       for (int kb = 0; kb < kblocks; ++kb) {
         // software pipeline over the kNB batches of the block: the loads of batch i+1 are in flight while batch i is
         // computed (two register buffers, ping-pong; kNB is even, so a K block always starts on buffer a)
+#ifdef CLASR_TRACE
+        long long tp0 = clock64();
+#endif
 #pragma unroll
         for (int bi = 0; bi < kNB; bi += 2) {
           load_batch(kb, bi + 1, fb, gb, okb);
@@ -770,6 +785,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           else if (kb + 1 < kblocks) load_batch(kb + 1, 0, fa, ga, oka);
           compute_batch(kb, bi + 1, fb, gb, okb);
         }
+#ifdef CLASR_TRACE
+        { const long long t_ = clock64(); tr_acc[8] += (unsigned long long)(t_ - tp0); tp0 = t_; }
+#endif
         if (kTerms > 1) {
           // warp-private staging (row-major, swizzled) -> tensor memory: lane l owns row 32q + l of the tile
           __syncwarp();
@@ -797,6 +815,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           tc::tmem_st_wait();
           tc::tc_fence_before();
         }
+#ifdef CLASR_TRACE
+        { const long long t_ = clock64(); tr_acc[9] += (unsigned long long)(t_ - tp0); tp0 = t_; }
+#endif
         tc::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the UMMA (async proxy) reads
         __syncwarp();                  // also: staging reads done before the next K block's writes
         if (lane == 0) {
@@ -804,6 +825,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           else tc::mbar_arrive(&a_ready[kb]);
           if (kMode >= 1) tc::mbar_arrive(&hid_ready[kb]);      // the local store warp
         }
+#ifdef CLASR_TRACE
+        { const long long t_ = clock64(); tr_acc[10] += (unsigned long long)(t_ - tp0); }
+#endif
       }
     }
   }
@@ -811,7 +835,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   if (warp == 0) CLASR_TRACE_FLUSH(5);
   if (warp == 1 && leader) { CLASR_TRACE_FLUSH(0); CLASR_TRACE_FLUSH(1); CLASR_TRACE_FLUSH(2); }
   if (warp == 4) { CLASR_TRACE_FLUSH(3); CLASR_TRACE_FLUSH(7); }
-  if (warp == kProdWarp0) CLASR_TRACE_FLUSH(4);
+  if (warp == kProdWarp0) { CLASR_TRACE_FLUSH(4); CLASR_TRACE_FLUSH(8); CLASR_TRACE_FLUSH(9); CLASR_TRACE_FLUSH(10); }
 #endif
   tc::tc_fence_before();
   if (kPair) tc::cluster_sync_all();  // nobody leaves while the peer may still read its smem / signal its barriers

@@ -16,7 +16,7 @@ from indic_cl_asr_b200 import _lib  # noqa: E402
 from indic_cl_asr_b200.fused import fused_joint_rnnt_loss  # noqa: E402
 
 SLOTS = ["MMA<-tmem_empty", "MMA<-a_ready", "MMA<-full", "epi<-tmem_full", "prod<-a_free", "TMA<-empty", "total",
-         "epi<-zstore"]
+         "epi<-zstore", "prod load+act", "prod lo->TMEM", "prod fence+arrive"]
 
 
 def read_trace():
@@ -24,10 +24,10 @@ def read_trace():
     fn = L.clasr_debug_joint_trace
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.c_int]
-    buf = (C.c_ulonglong * (148 * 8))()
-    rc = fn(buf, 148 * 8)
+    buf = (C.c_ulonglong * (148 * 12))()
+    rc = fn(buf, 148 * 12)
     assert rc == 0, rc
-    return np.array(buf[:], dtype=np.float64).reshape(148, 8)
+    return np.array(buf[:], dtype=np.float64).reshape(148, 12)
 
 
 def main():
