@@ -116,6 +116,7 @@ struct GemmParams {
   const int* k_dev;  // optional device-side K (<= K)
   const float* bias; // optional [N]: C = acc + bias[n] (non-atomic epilogue only)
   int group_n;       // pair kernel, no split-K: walk all N tiles of a row block back to back
+  int b_keep;        // pair kernel: B is small and re-read by every row block -> TMA loads carry L2 evict_last
 };
 
 template <int kTerms>
@@ -393,6 +394,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     // ================= TMA producer (both CTAs: own A rows, own half of B; bytes land on the leader's barrier) ====
     int stage = 0;
     uint32_t phase = 0;
+    const uint64_t pol_keep = tc::l2_policy_evict_last();
     for (int wi = 0, tile; (tile = tile_at(wi)) >= 0; ++wi) {
       const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
       const int m0 = (mn / n_tiles) * kPM + (int)cta_rank * kBM;
@@ -417,7 +419,15 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               for (int j = 0; j < kBM / 64; ++j)
                 tc::tma_load_2d_2sm(sa + j * 8192, ta, &full[stage], m0 + 64 * j, kb * kBK);
             }
-            if (!p.b_mn) {
+            if (p.b_keep) {  // (the A operand and the output stream through L2 and would otherwise push B out)
+              if (!p.b_mn) {
+                tc::tma_load_2d_2sm_hint(sb, tb, &full[stage], kb * kBK, n0, pol_keep);
+              } else {
+#pragma unroll
+                for (int j = 0; j < kBN / 128; ++j)
+                  tc::tma_load_2d_2sm_hint(sb + j * 8192, tb, &full[stage], n0 + 64 * j, kb * kBK, pol_keep);
+              }
+            } else if (!p.b_mn) {
               tc::tma_load_2d_2sm(sb, tb, &full[stage], kb * kBK, n0);
             } else {
 #pragma unroll
@@ -596,7 +606,8 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
   }
   const char* ge = getenv("CLASR_GEMM_GROUP");
   GemmParams p{M, N, K, C, ldc, atomic_add, k_splits, a_mn, b_mn, m_dev, k_dev, atomic_add ? nullptr : bias,
-               ge ? atoi(ge) : 0};
+               ge ? atoi(ge) : 0,
+               /*b_keep*/ ((size_t)N * K * 2 * (x3 ? 2 : 1) <= ((size_t)16 << 20) && (int64_t)M >= 8 * (int64_t)N) ? 1 : 0};
   if (use_pair) {
     const int tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN) * k_splits;
     int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
