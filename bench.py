@@ -355,7 +355,9 @@ def main_b200(args):
                     "traffic": 31.5e6 if (args.precision == "bf16x3" and not args.ragged) else None,
                     "peak_source": pk["source"] + " bf16 sustained",
                     "algorithmic_flops_per_launch": gemm_flops, "ms": kern["joint_fwd"],
-                    "mma_issue_multiplier": 3 if args.precision == "bf16x3" else 1}
+                    "mma_issue_multiplier": 3 if args.precision == "bf16x3" else 1,
+                    # the same launch counted in MMA issues (what the tensor pipe actually executes)
+                    "frac_of_mma_issue_rate": (3 if args.precision == "bf16x3" else 1) * ach / pk["tf_sustained"]}
         tensor_ms = sum(kern.get(k, 0.0) for k in ("joint_fwd", "joint_bwd_dz", "gemm_dhid", "gemm_dw"))
         ach_all = 3.0 * gemm_flops / (tensor_ms * 1e-3) / 1e12
         extra_roof["joint_fwd_bwd"] = {"bound": "tensor", "achieved": ach_all, "peak": pk["tf_sustained"],

@@ -708,46 +708,41 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       const int b = find_utterance(p.tile_offsets, p.B, tile_ok ? tile : 0);
       const int Tb = (int)p.act_lens[b], Ub1 = (int)p.label_lens[b] + 1;
       const int r0 = (tile - p.tile_offsets[b]) * kJM;
-      const int cells = tile_ok ? Tb * Ub1 : 0;  // null tile: every row is padding (A = 0)
-      {  // row table: lane l <-> row 32q + l (both K-half warps of the quarter write identical values)
-        const int r = r0 + q * 32 + lane;
-        int fo = -1, go_ = -1;
-        if (r < cells) {
-          const int t = r / Ub1, u = r - t * Ub1;
-          fo = (b * p.T + t) * p.H;
-          go_ = (b * p.U1 + u) * p.H;
-        }
+      {  // row table: lane l <-> row 32q + l (both K-half warps of the quarter write identical values).
+        // Padding rows (tail of an utterance's last tile, null tiles of a pair) alias the utterance's last cell: their
+        // A rows only have to be FINITE — every consumer of a padding row multiplies it by an exact zero (go = 0 /
+        // dZ = 0) or skips it (`valid`), so the producers carry no per-row predicates at all.
+        const int r = min(r0 + q * 32 + lane, Tb * Ub1 - 1);
+        const int t = r / Ub1, u = r - t * Ub1;
+        const uint32_t fo = (uint32_t)((b * p.T + t) * p.H);
+        const uint32_t go_ = (uint32_t)((b * p.U1 + u) * p.H);
         asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");  // the sibling warp is done reading the old table
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tab + lane * 8), "r"(fo), "r"(go_) : "memory");
       }
       __syncwarp();
       float2 fa[kBatch], ga[kBatch], fb[kBatch], gb[kBatch];
-      uint32_t oka = 0, okb = 0;
-      auto load_batch = [&](int kb, int batch, float2 (&fo)[kBatch], float2 (&go_)[kBatch], uint32_t& ok) {
-        const int kcol = kb * kJK + half * 32 + 2 * c;
-        ok = 0;
+      const float* __restrict__ ef_lane = p.ef + half * 32 + 2 * c;   // this lane's two features of a row
+      const float* __restrict__ eg_lane = p.eg + half * 32 + 2 * c;
+      auto load_batch = [&](int kb, int batch, float2 (&fo)[kBatch], float2 (&go_)[kBatch]) {
+        const uint64_t ef_kb = (uint64_t)(ef_lane + kb * kJK), eg_kb = (uint64_t)(eg_lane + kb * kJK);
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
           const int i = batch * kBatch + j;
           const int rl = (i & 3) + 8 * (i >> 2) + 4 * hs;
           const int2 o = tc::ld_shared_i2(tab + rl * 8);
-          if (o.x >= 0) {
-            fo[j] = __ldg(reinterpret_cast<const float2*>(p.ef + o.x + kcol));
-            go_[j] = __ldg(reinterpret_cast<const float2*>(p.eg + o.y + kcol));
-            ok |= 1u << j;
-          } else {  // padding row of the utterance's last tile: A row = 0
-            fo[j] = make_float2(0.f, 0.f);
-            go_[j] = make_float2(0.f, 0.f);
-          }
+          // unsigned 32-bit element offsets: ONE IMAD.WIDE.U32 per address (nvcc otherwise spends four)
+          uint64_t pf, pg;
+          asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(pf) : "r"(o.x), "l"(ef_kb));
+          asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(pg) : "r"(o.y), "l"(eg_kb));
+          fo[j] = __ldg(reinterpret_cast<const float2*>(pf));
+          go_[j] = __ldg(reinterpret_cast<const float2*>(pg));
         }
       };
-      auto compute_batch = [&](int kb, int batch, const float2 (&fi)[kBatch], const float2 (&gi)[kBatch],
-                               uint32_t okm) {
+      auto compute_batch = [&](int kb, int batch, const float2 (&fi)[kBatch], const float2 (&gi)[kBatch]) {
         const uint32_t ablk = a_base + kb * C::kABlockBytes;
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
           const int i = batch * kBatch + j;
-          const bool ok = (okm >> j) & 1u;
           float h0 = joint_combine<kAct>(fi[j].x, gi[j].x);
           float h1 = joint_combine<kAct>(fi[j].y, gi[j].y);
           if (p.drop_thresh) {  // warp-uniform
@@ -759,14 +754,14 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           }
           __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
           __nv_bfloat162 ll = __floats2bfloat162_rn(h0 - __low2float(hh), h1 - __high2float(hh));
-          const uint32_t hw = ok ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
-          const uint32_t lw = ok ? *reinterpret_cast<uint32_t*>(&ll) : 0u;
+          const uint32_t hw = *reinterpret_cast<uint32_t*>(&hh);
+          const uint32_t lw = *reinterpret_cast<uint32_t*>(&ll);
           const int rimm = (i & 3) + 8 * (i >> 2);  // compile-time part of the row index
           tc::st_shared_u32(ablk + aoff[i & 3] + rimm * 128, hw);
           if (kTerms > 1) tc::st_shared_u32(stg + soff[i & 3] + 8 * (i >> 2) * 64, lw);
         }
       };
-      load_batch(0, 0, fa, ga, oka);
+      load_batch(0, 0, fa, ga);
       for (int kb = 0; kb < kblocks; ++kb) {
         // software pipeline over the kNB batches of the block: the loads of batch i+1 are in flight while batch i is
         // computed (two register buffers, ping-pong; kNB is even, so a K block always starts on buffer a)
@@ -775,15 +770,15 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
 #endif
 #pragma unroll
         for (int bi = 0; bi < kNB; bi += 2) {
-          load_batch(kb, bi + 1, fb, gb, okb);
+          load_batch(kb, bi + 1, fb, gb);
           if (bi == 0 && tile_it > 0) {  // the previous row tile's last MMAs on this K block have retired
             CLASR_TRACE_WAIT(4, tc::mbar_wait(&a_free[kb], (tile_it - 1) & 1));
             tc::tc_fence_after();
           }
-          compute_batch(kb, bi, fa, ga, oka);
-          if (bi + 2 < kNB) load_batch(kb, bi + 2, fa, ga, oka);
-          else if (kb + 1 < kblocks) load_batch(kb + 1, 0, fa, ga, oka);
-          compute_batch(kb, bi + 1, fb, gb, okb);
+          compute_batch(kb, bi, fa, ga);
+          if (bi + 2 < kNB) load_batch(kb, bi + 2, fa, ga);
+          else if (kb + 1 < kblocks) load_batch(kb + 1, 0, fa, ga);
+          compute_batch(kb, bi + 1, fb, gb);
         }
 #ifdef CLASR_TRACE
         { const long long t_ = clock64(); tr_acc[8] += (unsigned long long)(t_ - tp0); tp0 = t_; }
