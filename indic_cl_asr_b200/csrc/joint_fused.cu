@@ -1085,7 +1085,8 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
                                                               const int* __restrict__ tile_offsets, int T, int U1, int H,
                                                               float* __restrict__ d_f, float* __restrict__ d_g,
                                                               const float* __restrict__ dzb,
-                                                              float* __restrict__ d_w_blank, uint32_t drop_thresh,
+                                                              float* __restrict__ d_w_blank,
+                                                              const float* __restrict__ w_blank, uint32_t drop_thresh,
                                                               uint32_t drop_seed_a, uint32_t drop_seed_b,
                                                               float drop_scale) {
   extern __shared__ float sm_dfg[];
@@ -1129,6 +1130,8 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
   // dW[blank, k] = sum over cells of dZ[cell, blank] * hid[cell, k]: the blank is the (V+1)-th class, a 1025th GEMM row
   // that would cost a whole extra 256-row tile in the dW GEMM; here it is one FMA per element on data already in flight
   float wb = 0.f;
+  // ... and the blank column of the dHid GEMM (K = V instead of V+1): dHid[cell, k] += dZ[cell, blank] * W[blank, k]
+  const float wbk = (dzb && live) ? __ldg(w_blank + k0 + lane) : 0.f;
   for (int t = t_begin + warp; t < t_end; t += nw) {
     float df = 0.f;
     if (t < Tb) {
@@ -1149,7 +1152,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
           float h, dh;
           act_pair(fv, eg_s[(u + j) * 32 + lane], h, dh);
           if (drop_thresh) drop(r0 + u + j, h, dh);
-          const float pv = d[j] * dh;
+          const float pv = (dzb ? fmaf(zb[j], wbk, d[j]) : d[j]) * dh;
           df += pv;
           atomicAdd(dg_s + (u + j) * 32 + lane, pv);
           if (dzb) wb = fmaf(zb[j], h, wb);
@@ -1159,10 +1162,11 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
         float h, dh;
         act_pair(fv, eg_s[u * 32 + lane], h, dh);
         if (drop_thresh) drop(r0 + u, h, dh);
-        const float pv = ld_stream1(dp + (int64_t)u * H) * dh;
+        const float zb1 = dzb ? __ldg(dzb + r0 + u) : 0.f;
+        const float pv = fmaf(zb1, wbk, ld_stream1(dp + (int64_t)u * H)) * dh;
         df += pv;
         atomicAdd(dg_s + u * 32 + lane, pv);
-        if (dzb) wb = fmaf(__ldg(dzb + r0 + u), h, wb);
+        if (dzb) wb = fmaf(zb1, h, wb);
       }
     }
     d_f[((int64_t)b * T + t) * H + k0 + lane] = df;
@@ -1543,8 +1547,10 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
 
   // ---- pass 2b: dHid[rows, H] = dZ[rows, Vp] . W[Vp, H]      (A K-major, B = W consumed MN-major: no transpose)
   prof_begin("gemm_dhid", s);
-  if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 0, jw.w_hi, jw.w_lo, H, 1, (int)sc.rows_cap, H, Vp, sc.dhid, H,
-                           precision, 0, 1, s, rows_pad_dev, nullptr)))
+  // blank_split: the blank column (class V, the only one past a multiple of 64 in K when V = 1024) would cost a whole
+  // extra K block; its rank-1 contribution dZ[., blank] x W[blank, :] is added by joint_dfg from dzb instead
+  if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 0, jw.w_hi, jw.w_lo, H, 1, (int)sc.rows_cap, H,
+                           blank_split ? Vp - 1 : Vp, sc.dhid, H, precision, 0, 1, s, rows_pad_dev, nullptr)))
     return rc;
   prof_end("gemm_dhid", s);
   // ---- pass 2c: dW[Vp, H] = dZ^T . Hid       (both operands MN-major, split-K over the rows, fp32 atomics)
@@ -1568,7 +1574,8 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
     cudaFuncSetAttribute(joint_dfg_fused_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     joint_dfg_fused_kernel<ACT><<<grid, 256, smem, s>>>(sc.dhid, ef_, eg_, act_lens, label_lens, jw.tile_offsets,  \
                                                         T, U1, H, d_f, d_g, blank_split ? sc.dzb : nullptr,        \
-                                                        d_w_out + (size_t)blank * H, p.drop_thresh, p.drop_seed_a, \
+                                                        d_w_out + (size_t)blank * H, w_out + (size_t)blank * H,    \
+                                                        p.drop_thresh, p.drop_seed_a,                              \
                                                         p.drop_seed_b, p.drop_scale);                              \
   } while (0)
       if (activation == CLASR_ACT_RELU) CLASR_LAUNCH_DFG(CLASR_ACT_RELU);
