@@ -357,10 +357,13 @@ def main_b200(args):
         ach = gemm_flops / (kern["joint_fwd"] * 1e-3) / 1e12
         roofline = {"kernel": "joint_fwd_kernel (pass 1: joint GEMM + online log-softmax)", "bound": "tensor",
                     "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full`
-                    # (profiles/r01bcd_ncu_joint_and_gemm.md, r01g capture: 31.5 MB read, ~0 written; the algorithmic
-                    # output is 20 B per lattice cell = 16 MB, the inputs f/g/W = 30 MB)
-                    "traffic": 31.5e6 if (args.precision == "bf16x3" and not args.ragged) else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full`.
+                    # stash mode (profiles/r01k_ncu_stash_mode.md): 0.032 GB read + 5.460 GB written — the algorithmic
+                    # output is the kept logits and hidden activations, 4*pad32(V+1) + 4*H bytes per cell = 5.48 GB.
+                    # recompute mode (r01bcd, r01g capture): 31.5 MB read, ~0 written (outputs 20 B per cell).
+                    "traffic": (None if (args.precision != "bf16x3" or args.ragged or args.dropout > 0)
+                                else 31.5e6 if os.environ.get("CLASR_JOINT_STASH", "") == "0" else 5.492e9),
+                    "backward_mode": "recompute" if os.environ.get("CLASR_JOINT_STASH", "") == "0" else "stash",
                     "peak_source": pk["source"] + " bf16 sustained",
                     "algorithmic_flops_per_launch": gemm_flops, "ms": kern["joint_fwd"],
                     "mma_issue_multiplier": 3 if args.precision == "bf16x3" else 1,
