@@ -851,7 +851,15 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
 // (joint_row_grad) are computed once into shared memory.  Algorithmic bytes per lattice cell: 4 ldzf + 4 ldz.
 // ------------------------------------------------------------------------------------------------
 constexpr int kDzRows = 32;        // rows per chunk (one scalar set per row, computed by one warp)
-constexpr int kDzBatch = 4;        // rows whose loads are in flight per thread (2 x LDG.128 each)
+// measured at B32/T250/U100/V1024 (ms in the step): (rows in flight, register cap) = (2,48) 1.33, (1,40) 1.40, (4,64) 1.41,
+// (1,32) 1.42, (8,128) 1.44, (2,40) 1.46, (4,80) 1.41-1.5, (8,96) 1.51 — occupancy beats per-thread batching
+#ifndef CLASR_DZ_BATCH
+#define CLASR_DZ_BATCH 2
+#endif
+#ifndef CLASR_DZ_REGS
+#define CLASR_DZ_REGS 48
+#endif
+constexpr int kDzBatch = CLASR_DZ_BATCH;  // rows whose loads are in flight per thread (2 x LDG.128 each)
 constexpr int kDzMaxGroups = 512;  // 8-column groups per block (beyond that: blockIdx.y chunks)
 constexpr int kDzMaxThreads = kDzMaxGroups + 32;
 
@@ -864,7 +872,7 @@ struct DzRowScalars {
 // next chunk's row scalars into the other half of a double buffer while the block streams the current chunk; the
 // launcher adds a warp for it when the last column warp would be more than half busy.
 template <int kTerms, int kMode>
-__global__ void __maxnreg__(80) joint_dz_kernel(JointFwdParams p, int groups) {
+__global__ void __maxnreg__(CLASR_DZ_REGS) joint_dz_kernel(JointFwdParams p, int groups) {
   __shared__ DzRowScalars sc[2];
   constexpr float kLog2e = 1.4426950408889634f;
   const int ncg = p.ldz >> 3;
