@@ -2,6 +2,10 @@
 (see csrc/joint_fused.cu: CLASR_TRACE_WAIT) selected through CLASR_LIB.  Prints, per mode, the mean over CTAs of the
 cycles each role spent in its barrier waits as a fraction of the kernel's cycles.
 
+    cd indic_cl_asr_b200/csrc && touch joint_fused.cu && \
+      make NVCCFLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
+                      -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -DCLASR_TRACE" && \
+      cp ../libclasr_sm100.so build/libclasr_trace.so && touch joint_fused.cu && make     # product library again
     CLASR_LIB=indic_cl_asr_b200/csrc/build/libclasr_trace.so python tools/joint_trace.py
 """
 import ctypes as C
@@ -21,6 +25,9 @@ SLOTS = ["MMA<-tmem_empty", "MMA<-a_ready", "MMA<-full", "epi<-tmem_full", "prod
 
 def read_trace():
     L = _lib.lib()
+    if not hasattr(L, "clasr_debug_joint_trace"):
+        raise SystemExit("this library was not built with -DCLASR_TRACE: build one (see the module docstring) and "
+                         "point CLASR_LIB at it")
     fn = L.clasr_debug_joint_trace
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.c_int]
