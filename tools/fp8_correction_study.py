@@ -43,6 +43,12 @@ def study(M=4096, K=640, N=1025, seed=0, trained_scale=1.0):
     out["bf16x3 (3 issues)"] = Ah @ Wh.T + Ah @ Wl.T + Al @ Wh.T
     out["bf16 + 2 x mxfp8 corrections (2 issue-equivalents)"] = (
         Ah @ Wh.T + e4m3_block(Ah) @ e4m3_block(Wl).T + e4m3_block(Al) @ e4m3_block(Wh).T)
+    Ah16 = A.astype(np.float16).astype(np.float64); Al16 = A - Ah16
+    Wh16 = W.astype(np.float16).astype(np.float64); Wl16 = W - Wh16
+    out["fp16 (1 issue)"] = Ah16 @ Wh16.T
+    out["fp16 + 2 x mxfp8 corrections (2 issue-equivalents)"] = (
+        Ah16 @ Wh16.T + e4m3_block(Ah16) @ e4m3_block(Wl16).T + e4m3_block(Al16) @ e4m3_block(Wh16).T)
+    out["fp16 + 1 x mxfp8 correction of A only (1.5)"] = Ah16 @ Wh16.T + e4m3_block(Al16) @ e4m3_block(Wh16).T
     zmax = np.abs(z).max()
     for k, v in out.items():
         err = np.abs(v - z)
