@@ -156,6 +156,84 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* __restrict__ 
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// ---- CTA-pair variant: cluster of 2, tcgen05 cta_group::2, M = 256 (128 rows per CTA), N = 256 (each CTA holds half of
+// B), K = 128.  Hypothesis under test (from CUTLASS' TileShape_SF): every CTA keeps SFA for ITS 128 rows and SFB for
+// ALL 256 columns in its own shared memory at the same offsets, and the leader's cta_group::2 tcgen05.cp moves both
+// CTAs' copies into their own tensor memories.
+constexpr int kN2 = 256;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+probe2_kernel(const uint8_t* __restrict__ a8, const uint8_t* __restrict__ b8, const uint8_t* __restrict__ sfa,
+              const uint8_t* __restrict__ sfb, float* __restrict__ c) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_s = smem;                 // this CTA's 128 rows of A
+  uint8_t* b_s = smem + 16384;         // this CTA's 128 columns (rows of B) = half of N
+  uint8_t* sfa_s = smem + 32768;       // 1 atom: this CTA's rows
+  uint8_t* sfb_s = sfa_s + 512;        // 2 atoms: all 256 columns
+  uint64_t* bar = (uint64_t*)(sfb_s + 1024);
+  uint32_t* slot = (uint32_t*)(bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = tc::cluster_ctarank();
+  const uint8_t* a_src = a8 + (size_t)rank * 128 * kK;
+  const uint8_t* b_src = b8 + (size_t)rank * 128 * kK;
+  for (int i = tid; i < 128 * 8; i += 128) {
+    const int row = i >> 3, ch = i & 7;
+    *reinterpret_cast<uint4*>(a_s + row * 128 + ((ch ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(a_src + row * kK + ch * 16);
+    *reinterpret_cast<uint4*>(b_s + row * 128 + ((ch ^ (row & 7)) * 16)) = *reinterpret_cast<const uint4*>(b_src + row * kK + ch * 16);
+  }
+  for (int i = tid; i < 512; i += 128) {
+    const int row = i >> 2, kb = i & 3;
+    sfa_s[(row & 31) * 16 + (row >> 5) * 4 + kb] = sfa[(rank * 128 + row) * 4 + kb];
+  }
+  for (int i = tid; i < 1024; i += 128) {
+    const int col = i >> 2, kb = i & 3;   // column 0..255 -> atom col / 128
+    sfb_s[(col >> 7) * 512 + (col & 31) * 16 + ((col >> 5) & 3) * 4 + kb] = sfb[col * 4 + kb];
+  }
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
+  tc::cluster_sync_all();
+  if (warp == 0) tc::tmem_alloc_2sm(slot, 512);
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();             // both CTAs' operands and scale atoms are in place
+  tc::tc_fence_after();
+  const uint32_t tmem = *slot;
+  const uint32_t t_sfa = tmem + 256, t_sfb = tmem + 264;
+  if (rank == 0 && warp == 0) {
+    if (tc::elect_one()) {
+      asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(t_sfa), "l"(make_desc_sf(tc::smem_u32(sfa_s))));
+      asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(t_sfb), "l"(make_desc_sf(tc::smem_u32(sfb_s))));
+      asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(t_sfb + 4), "l"(make_desc_sf(tc::smem_u32(sfb_s) + 512)));
+      for (int kb = 0; kb < kK / 32; ++kb) {
+        const uint64_t da = tc::make_desc_kmajor_sw128(tc::smem_u32(a_s) + kb * 32);
+        const uint64_t db = tc::make_desc_kmajor_sw128(tc::smem_u32(b_s) + kb * 32);
+        const uint32_t idesc = make_idesc_mx(256, kN2, kb);
+        const uint32_t acc = kb > 0;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem),
+            "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(t_sfa), "r"(t_sfb)
+            : "memory");
+      }
+      tc::umma_commit_2sm(bar, 0b11);   // arrives on both CTAs' barriers
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(bar, 0);
+  tc::tc_fence_after();
+  const int row = rank * 128 + warp * 32 + (tid & 31);
+  for (int cb = 0; cb < kN2 / 32; ++cb) {
+    uint32_t r[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, r);
+    tc::tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) c[row * kN2 + cb * 32 + j] = __uint_as_float(r[j]);
+  }
+  tc::tc_fence_before();
+  tc::cluster_sync_all();
+  if (warp == 0) tc::tmem_dealloc_2sm(tmem, 512);
+}
+
 // ---- host: e4m3 encode / decode, block quantisation
 static float e4m3_decode(uint8_t v) {
   const int s = v >> 7, e = (v >> 3) & 15, m = v & 7;
@@ -258,6 +336,59 @@ int main() {
   }
   printf("%d of %d rows off; %s\n", rows_off, kM, rows_off == 0 ? "PROBE OK" : "PROBE MISMATCH");
   rc_total |= rows_off != 0;
+  }
+
+  {  // ---- CTA pair: M = 256, N = 256
+    printf("---- cta_group::2: M=256, N=256, K=128 block-scaled\n");
+    std::vector<float> A2((size_t)256 * kK), B2((size_t)256 * kK);
+    for (auto& v : A2) v = (rand() / (float)RAND_MAX * 2 - 1) * std::ldexp(1.f, rand() % 24 - 20);
+    for (auto& v : B2) v = (rand() / (float)RAND_MAX * 2 - 1) * std::ldexp(1.f, rand() % 12 - 10);
+    std::vector<uint8_t> qa, qb, sa, sb;
+    quantise(A2, 256, qa, sa);
+    quantise(B2, 256, qb, sb);
+    std::vector<double> ref2((size_t)256 * 256);
+    for (int m = 0; m < 256; ++m)
+      for (int n = 0; n < 256; ++n) {
+        double acc = 0;
+        for (int kb = 0; kb < 4; ++kb) {
+          double part = 0;
+          for (int k = 0; k < 32; ++k) part += (double)e4m3_decode(qa[m * kK + kb * 32 + k]) * e4m3_decode(qb[n * kK + kb * 32 + k]);
+          acc += part * std::ldexp(1.0, sa[m * 4 + kb] - 127) * std::ldexp(1.0, sb[n * 4 + kb] - 127);
+        }
+        ref2[(size_t)m * 256 + n] = acc;
+      }
+    uint8_t *pa, *pb, *psa, *psb;
+    float* pc;
+    cudaMalloc(&pa, qa.size()); cudaMalloc(&pb, qb.size()); cudaMalloc(&psa, sa.size()); cudaMalloc(&psb, sb.size());
+    cudaMalloc(&pc, ref2.size() * 4);
+    cudaMemset(pc, 0, ref2.size() * 4);
+    cudaMemcpy(pa, qa.data(), qa.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(pb, qb.data(), qb.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(psa, sa.data(), sa.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(psb, sb.data(), sb.size(), cudaMemcpyHostToDevice);
+    const int smem2 = 32768 + 512 + 1024 + 64 + 1024;
+    cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    probe2_kernel<<<2, 128, smem2>>>(pa, pb, psa, psb, pc);
+    cudaError_t e2 = cudaDeviceSynchronize();
+    if (e2 != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e2)); return 1; }
+    std::vector<float> got2(ref2.size());
+    cudaMemcpy(got2.data(), pc, got2.size() * 4, cudaMemcpyDeviceToHost);
+    int rows_off = 0, cols_off = 0;
+    double maxref = 0, maxerr = 0;
+    for (int m = 0; m < 256; ++m) {
+      double rm = 0, em = 0;
+      for (int n = 0; n < 256; ++n) { rm = std::fmax(rm, std::fabs(ref2[(size_t)m * 256 + n])); em = std::fmax(em, std::fabs(got2[(size_t)m * 256 + n] - ref2[(size_t)m * 256 + n])); }
+      maxref = std::fmax(maxref, rm); maxerr = std::fmax(maxerr, em);
+      if (em > 1e-5 * rm) { if (rows_off < 6) printf("  row %d: max err %.3e vs max ref %.3e\n", m, em, rm); ++rows_off; }
+    }
+    for (int n = 0; n < 256; ++n) {
+      double rm = 0, em = 0;
+      for (int m = 0; m < 256; ++m) { rm = std::fmax(rm, std::fabs(ref2[(size_t)m * 256 + n])); em = std::fmax(em, std::fabs(got2[(size_t)m * 256 + n] - ref2[(size_t)m * 256 + n])); }
+      if (em > 1e-5 * rm) ++cols_off;
+    }
+    printf("max|ref| = %.6e max|err| = %.6e; %d of 256 rows, %d of 256 columns off; %s\n", maxref, maxerr, rows_off, cols_off,
+           rows_off == 0 ? "PROBE OK" : "PROBE MISMATCH");
+    rc_total |= rows_off != 0;
   }
   long long t[2];
   cudaMemcpy(t, dt, 16, cudaMemcpyDeviceToHost);
