@@ -198,13 +198,13 @@ CLASR_API int clasr_debug_mma_rate(int N, int pattern, int iters, long long* out
 
 /* ------------------------------------------------------------------------------------------
  * 4. Fused joint + transducer loss — replaces the fused branch of RNNTJoint.forward
- *    (modules/rnnt.py:1403-1561): joint_after_projection (:1587-1665) + RNNTLoss, without ever
- *    writing the [B,T,U1,Vp] logits to HBM.
+ *    (modules/rnnt.py:1403-1561): joint_after_projection (:1587-1665) + RNNTLoss, without the padded
+ *    [B,T,U1,Vp] logits tensor (a forward-only call stores no logits at all; see `stash` below).
  *      f [B,T,H] = enc projection, g [B,U1,H] = pred projection (fp32)
  *      z[b,t,u,:] = W_out . act(f[b,t,:] + g[b,u,:]) + b_out,  W_out [Vp,H] (nn.Linear layout)
  *    Pass 1 (tcgen05 GEMM, epilogue = online log-sum-exp + gather) fills the same lattice workspace
- *    as clasr_rnnt_loss_fwd and runs the alpha/beta wavefront; pass 2 recomputes logits tile-wise
- *    and contracts the softmax-fused gradient into d_f, d_g, dW_out, db_out.
+ *    as clasr_rnnt_loss_fwd and runs the alpha/beta wavefront; pass 2 forms the softmax-fused gradient (from the
+ *    stashed logits, or by recomputing them tile-wise) and contracts it into d_f, d_g, dW_out, db_out.
  *    dropout_p > 0 applies the joint's Dropout (modules/rnnt.py:1699-1709: act -> Dropout(p) -> Linear) inside the
  *    kernels: a counter-based mask keyed by (dropout_seed, compact cell row, feature pair) that the recompute pass and
  *    the d_f / d_g reduction regenerate; kept activations are scaled by 1 / (1 - p).  The backward calls must be given
