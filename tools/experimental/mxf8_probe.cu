@@ -6,12 +6,14 @@
 //   nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I indic_cl_asr_b200/csrc \
 //        tools/experimental/mxf8_probe.cu -o tools/experimental/mxf8_probe -lcuda && tools/experimental/mxf8_probe
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "tc_common.cuh"
@@ -91,12 +93,13 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* __restrict__ 
       asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(t_sfa), "l"(make_desc_sf(tc::smem_u32(sfa_s))));
       asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(t_sfb), "l"(make_desc_sf(tc::smem_u32(sfb_s))));
       if (mixed) {
-        const uint32_t id16 = tc::make_idesc_bf16(kM, kN);
+        // mixed == 3: A holds fp16 bits, B bf16 (a_format [7,10) = 0, b_format [10,13) = 1), nothing else accumulated
+        const uint32_t id16 = mixed == 3 ? (tc::make_idesc_bf16(kM, kN) & ~(7u << 7)) : tc::make_idesc_bf16(kM, kN);
         for (int kk = 0; kk < 4; ++kk)
           tc::umma_ss(tmem, tc::make_desc_kmajor_sw128(tc::smem_u32(a16_s) + kk * 32),
                       tc::make_desc_kmajor_sw128(tc::smem_u32(b16_s) + kk * 32), id16, kk > 0);
       }
-      for (int kb = 0; kb < kK / 32; ++kb) {
+      for (int kb = 0; kb < (mixed == 3 ? 0 : kK / 32); ++kb) {
         const uint64_t da = tc::make_desc_kmajor_sw128(tc::smem_u32(a_s) + kb * 32);
         // MN-major: 32 K rows per MMA = four 1024-byte atoms; one 128-element MN block, so LBO is never used
         const uint64_t db = mixed == 2 ? tc::make_desc_mnmajor_sw128(tc::smem_u32(bt_s) + kb * 4096, 16384)
@@ -263,7 +266,8 @@ static void quantise(const std::vector<float>& x, int rows, std::vector<uint8_t>
     }
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const bool try_mixed_formats = argc > 1 && std::string(argv[1]) == "--mixed-formats";
   std::vector<float> A((size_t)kM * kK), B((size_t)kN * kK);
   srand(1);
   for (auto& v : A) v = (rand() / (float)RAND_MAX * 2 - 1) * std::ldexp(1.f, rand() % 24 - 20);   // wide dynamic range
@@ -390,8 +394,32 @@ int main() {
            rows_off == 0 ? "PROBE OK" : "PROBE MISMATCH");
     rc_total |= rows_off != 0;
   }
-  long long t[2];
-  cudaMemcpy(t, dt, 16, cudaMemcpyDeviceToHost);
+  // ---- kind::f16 with an fp16 A operand and a bf16 B operand.  MEASURED on B200: "an illegal instruction was
+  // encountered" — the two 16-bit formats of one kind::f16 MMA must match.  Run with --mixed-formats to reproduce (it
+  // kills the context, so it is last and optional).
+  if (try_mixed_formats) {
+    printf("---- kind::f16, A = fp16, B = bf16, K = 64 (expected: illegal instruction)\n");
+    std::vector<__half> Ah((size_t)kM * 64);
+    for (auto& v : Ah) v = __float2half(rand() / (float)RAND_MAX * 2 - 1);
+    cudaMemcpy(da16, Ah.data(), Ah.size() * 2, cudaMemcpyHostToDevice);
+    probe_kernel<<<1, 128, smem>>>(da, db, dsa, dsb, da16, db16, 3, dc, nullptr);
+    cudaError_t e3 = cudaDeviceSynchronize();
+    if (e3 != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e3)); return 1; }
+    std::vector<float> got3((size_t)kM * kN);
+    cudaMemcpy(got3.data(), dc, got3.size() * 4, cudaMemcpyDeviceToHost);
+    double maxref = 0, maxerr = 0;
+    for (int m = 0; m < kM; ++m)
+      for (int n = 0; n < kN; ++n) {
+        double acc = 0;
+        for (int k = 0; k < 64; ++k) acc += (double)__half2float(Ah[m * 64 + k]) * __bfloat162float(B16[n * 64 + k]);
+        maxref = std::fmax(maxref, std::fabs(acc));
+        maxerr = std::fmax(maxerr, std::fabs(acc - got3[(size_t)m * kN + n]));
+      }
+    printf("max|ref| = %.6e max|err| = %.6e; %s\n", maxref, maxerr, maxerr < 1e-5 * maxref ? "PROBE OK" : "PROBE MISMATCH");
+    rc_total |= !(maxerr < 1e-5 * maxref);
+  }
+  long long t[2] = {0, 0};
+  if (!try_mixed_formats) cudaMemcpy(t, dt, 16, cudaMemcpyDeviceToHost);
   printf("issue rate, M=128 N=128, 256 MMAs each: kind::f16 (K=16) %.1f cycles/MMA, kind::mxf8f6f4 (K=32) %.1f cycles/MMA\n",
          t[0] / 256.0, t[1] / 256.0);
   return rc_total;
