@@ -100,3 +100,26 @@ def test_constructor_errors_match_reference():
                                       "pred.bias", "pred.weight"]
     jm = RNNTJoint(jointnet=dict(jn, dropout=0.2), num_classes=8, multilingual=True, language_keys=["hi", "bn"])
     assert "joint_net.2.hi.weight" in jm.state_dict() and jm.joint_net[2]["bn"].out_features == 5
+
+
+def test_joint_stash_size_and_limit(monkeypatch):
+    """The stash a differentiated forward call keeps: 4*pad32(Vp) bytes of logits + 2 (bf16) or 4 (bf16 hi/lo) bytes
+    per hidden feature, per padded lattice row; the CLASR_JOINT_STASH switch / limit is host logic."""
+    from indic_cl_asr_b200 import fused
+
+    l = _lib.lib()
+    B, T, U1, H, Vp = 32, 250, 101, 640, 1025
+    rows = B * ((T * U1 + 127) // 128) * 128
+    x3 = l.clasr_joint_stash_bytes(B, T, U1, H, Vp, _lib.PREC["bf16x3"])
+    x1 = l.clasr_joint_stash_bytes(B, T, U1, H, Vp, _lib.PREC["bf16"])
+    assert x3 >= rows * (1056 * 4 + 2 * H * 2) and x3 < rows * (1056 * 4 + 2 * H * 2) + 4096
+    assert x3 - x1 >= rows * H * 2 and x3 - x1 < rows * H * 2 + 4096
+    assert l.clasr_joint_stash_bytes(0, T, U1, H, Vp, _lib.PREC["bf16x3"]) == 0
+    monkeypatch.delenv("CLASR_JOINT_STASH", raising=False)
+    assert fused._stash_limit_bytes() == 48 << 30
+    monkeypatch.setenv("CLASR_JOINT_STASH", "0")
+    assert fused._stash_limit_bytes() == 0
+    monkeypatch.setenv("CLASR_JOINT_STASH", "1.5")
+    assert fused._stash_limit_bytes() == 3 << 29
+    # no gradient wanted -> nothing is kept, whatever the limit
+    assert fused._stash(torch.empty(1), B, T, U1, H, Vp, _lib.PREC["bf16x3"], False) == (None, 0)
