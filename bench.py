@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="tcgen05", choices=["tcgen05", "materialised"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp16x3", "bf16"])
     ap.add_argument("--activation", default="tanh", choices=["tanh", "relu", "sigmoid"])
     ap.add_argument("--ragged", type=int, default=0)
     ap.add_argument("--dropout", type=float, default=0.0, help="joint dropout (the shipped checkpoint trains with 0.2)")
@@ -361,14 +361,14 @@ def main_b200(args):
                     # stash mode (profiles/r01k_ncu_stash_mode.md): 0.032 GB read + 5.460 GB written — the algorithmic
                     # output is the kept logits and hidden activations, 4*pad32(V+1) + 4*H bytes per cell = 5.48 GB.
                     # recompute mode (r01bcd, r01g capture): 31.5 MB read, ~0 written (outputs 20 B per cell).
-                    "traffic": (None if (args.precision != "bf16x3" or args.ragged or args.dropout > 0)
+                    "traffic": (None if (args.precision not in ("bf16x3", "fp16x3") or args.ragged or args.dropout > 0)
                                 else 31.5e6 if os.environ.get("CLASR_JOINT_STASH", "") == "0" else 5.492e9),
                     "backward_mode": "recompute" if os.environ.get("CLASR_JOINT_STASH", "") == "0" else "stash",
                     "peak_source": pk["source"] + " bf16 sustained",
                     "algorithmic_flops_per_launch": gemm_flops, "ms": kern["joint_fwd"],
-                    "mma_issue_multiplier": 3 if args.precision == "bf16x3" else 1,
+                    "mma_issue_multiplier": 3 if args.precision in ("bf16x3", "fp16x3") else 1,
                     # the same launch counted in MMA issues (what the tensor pipe actually executes)
-                    "frac_of_mma_issue_rate": (3 if args.precision == "bf16x3" else 1) * ach / pk["tf_sustained"]}
+                    "frac_of_mma_issue_rate": (3 if args.precision in ("bf16x3", "fp16x3") else 1) * ach / pk["tf_sustained"]}
         tensor_ms = sum(kern.get(k, 0.0) for k in ("joint_fwd", "joint_bwd_dz", "gemm_dhid", "gemm_dw"))
         ach_all = 3.0 * gemm_flops / (tensor_ms * 1e-3) / 1e12
         extra_roof["joint_fwd_bwd"] = {"bound": "tensor", "achieved": ach_all, "peak": pk["tf_sustained"],
@@ -379,7 +379,7 @@ def main_b200(args):
         if "joint_dz_sweep" in kern:
             # dZ from the kept logits: reads z fp32 [cells, round_up(Vp,32)], writes dZ bf16 hi+lo [cells, round_up(Vp,16)]
             vp = c["V"] + 1
-            terms = 2 if args.precision == "bf16x3" else 1
+            terms = 2 if args.precision in ("bf16x3", "fp16x3") else 1
             by = cells * (4.0 * ((vp + 31) // 32 * 32) + 2.0 * terms * ((vp + 15) // 16 * 16))
             ach_dz = by / (kern["joint_dz_sweep"] * 1e-3) / 1e9
             extra_roof["joint_dz_sweep"] = {"bound": "hbm", "achieved": ach_dz, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -428,8 +428,8 @@ def main_b200(args):
             "metric": "RNNT+CTC+EWC fwd/bwd utts/s (B32,T250,U100,V1024)", "value": value, "unit": "utts/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (joint GEMM: bf16 hi/lo split x3 on tcgen05, fp32 accumulate)" if args.precision == "bf16x3"
-                     else "bf16 joint GEMM, fp32 elsewhere",
+            "dtype": (f"f32 (joint GEMM: {args.precision[:4]} hi/lo split x3 on tcgen05, fp32 accumulate)"
+                      if args.precision in ("bf16x3", "fp16x3") else "bf16 joint GEMM, fp32 elsewhere"),
             "data": "synthetic",
             "config": {"workload": "configs[1]: standalone RNNT+CTC(+EWC) loss fwd/bwd, B=32 T=250 U=100 V=1024 H=640 "
                                    "per GPU, full-length utterances" + (" (ragged)" if args.ragged else ""),

@@ -15,6 +15,9 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 void prof_begin(const char* name, cudaStream_t s);
 void prof_end(const char* name, cudaStream_t s);
+static inline bool prec_ok(int p) { return p == CLASR_PREC_BF16 || p == CLASR_PREC_BF16X3 || p == CLASR_PREC_FP16X3; }
+static inline bool prec_x3(int p) { return p == CLASR_PREC_BF16X3 || p == CLASR_PREC_FP16X3; }   // hi/lo split, 3 MMAs
+static inline bool prec_f16(int p) { return p == CLASR_PREC_FP16X3; }                             // operands are fp16
 
 #define CLASR_CHECK_ARG(cond, ...)              \
   do {                                          \

@@ -63,26 +63,33 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 // fp32 [rows, cols] -> bf16 hi (and lo) [rows, cols_pad], cols_pad multiple of 8, pad zero-filled
 // ------------------------------------------------------------------------------------------------
 __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t src_ld,
-                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int cols_pad) {
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int cols_pad,
+                                  int f16) {
   const int64_t n = rows * (int64_t)cols_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols_pad;
     const int c = (int)(i - r * cols_pad);
     const float x = c < cols ? src[r * src_ld + c] : 0.f;
-    __nv_bfloat16 h, l;
-    tc::split_bf16(x, h, l);
-    hi[i] = h;
-    if (lo) lo[i] = l;
+    if (f16) {   // the same 2-byte slots hold fp16 (CLASR_PREC_FP16X3)
+      const __half h = __float2half_rn(x);
+      reinterpret_cast<__half*>(hi)[i] = h;
+      if (lo) reinterpret_cast<__half*>(lo)[i] = __float2half_rn(x - __half2float(h));
+    } else {
+      __nv_bfloat16 h, l;
+      tc::split_bf16(x, h, l);
+      hi[i] = h;
+      if (lo) lo[i] = l;
+    }
   }
 }
 
 int launch_split_bf16(const float* src, int64_t rows, int cols, int64_t src_ld, void* hi, void* lo, int cols_pad,
-                      cudaStream_t s) {
+                      cudaStream_t s, int f16) {
   const int64_t n = rows * (int64_t)cols_pad;
   int grid = (int)((n + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   if (grid < 1) grid = 1;
-  split_bf16_kernel<<<grid, 256, 0, s>>>(src, rows, cols, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, cols_pad);
+  split_bf16_kernel<<<grid, 256, 0, s>>>(src, rows, cols, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, cols_pad, f16);
   CLASR_CHECK_LAUNCH("split_bf16");
   return CLASR_STATUS_SUCCESS;
 }
@@ -117,6 +124,7 @@ struct GemmParams {
   const float* bias; // optional [N]: C = acc + bias[n] (non-atomic epilogue only)
   int group_n;       // pair kernel, no split-K: walk all N tiles of a row block back to back
   int b_keep;        // pair kernel: B is small and re-read by every row block -> TMA loads carry L2 evict_last
+  int f16;           // operands are fp16 instead of bf16 (CLASR_PREC_FP16X3)
 };
 
 template <int kTerms>
@@ -201,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp loops, one elected lane issues) =================
-    const uint32_t idesc = tc::make_idesc_bf16(kBM, kBN, p.a_mn, p.b_mn);
+    const uint32_t idesc = tc::make_idesc_16(kBM, kBN, p.a_mn, p.b_mn, p.f16);
     const uint32_t smem_base = tc::smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;
@@ -451,7 +459,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const uint32_t acc_phase = (it >> 1) & 1;
       const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
       const int nw = n_width((mn % n_tiles) * kBN);
-      const uint32_t idesc = tc::make_idesc_bf16(kPM, nw, p.a_mn, p.b_mn);
+      const uint32_t idesc = tc::make_idesc_16(kPM, nw, p.a_mn, p.b_mn, p.f16);
       const int kb_begin = ks * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
       tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc::tc_fence_after();
@@ -562,7 +570,7 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
                    int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias) {
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
-  const bool x3 = precision == CLASR_PREC_BF16X3;
+  const bool x3 = prec_x3(precision);
   // CTA pairs (256-row tiles) pay off once there are enough rows; CLASR_GEMM_PAIR=0/1 forces the choice (tests)
   static const int force_pair = [] { const char* e = getenv("CLASR_GEMM_PAIR"); return e ? atoi(e) : -1; }();
   const bool use_pair = force_pair >= 0 ? force_pair != 0 : (M >= 4 * kBM);
@@ -607,7 +615,8 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
   const char* ge = getenv("CLASR_GEMM_GROUP");
   GemmParams p{M, N, K, C, ldc, atomic_add, k_splits, a_mn, b_mn, m_dev, k_dev, atomic_add ? nullptr : bias,
                ge ? atoi(ge) : 0,
-               /*b_keep*/ ((size_t)N * K * 2 * (x3 ? 2 : 1) <= ((size_t)16 << 20) && (int64_t)M >= 8 * (int64_t)N) ? 1 : 0};
+               /*b_keep*/ ((size_t)N * K * 2 * (x3 ? 2 : 1) <= ((size_t)16 << 20) && (int64_t)M >= 8 * (int64_t)N) ? 1 : 0,
+               prec_f16(precision) ? 1 : 0};
   if (use_pair) {
     const int tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN) * k_splits;
     int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
@@ -643,7 +652,7 @@ static inline int pad8(int k) { return (k + 7) / 8 * 8; }
 
 extern "C" size_t clasr_gemm_workspace_bytes(int M, int N, int K, int precision) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  const size_t parts = precision == CLASR_PREC_BF16X3 ? 2 : 1;
+  const size_t parts = prec_x3(precision) ? 2 : 1;
   // either orientation of either operand fits: rows x pad8(cols)
   size_t a = ((size_t)pad8(M) * pad8(K) * 2 + 255) / 256 * 256, b = ((size_t)pad8(N) * pad8(K) * 2 + 255) / 256 * 256;
   return parts * (a + b);
@@ -653,11 +662,11 @@ extern "C" int clasr_gemm_ex(const float* A, const float* B, float* C, int M, in
                              int k_splits, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   CLASR_CHECK_ARG(A && B && C && workspace, "gemm: null pointer");
   CLASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: non-positive dimension");
-  CLASR_CHECK_ARG(precision == CLASR_PREC_BF16 || precision == CLASR_PREC_BF16X3, "gemm: bad precision");
+  CLASR_CHECK_ARG(prec_ok(precision), "gemm: bad precision");
   CLASR_CHECK_ARG(workspace_bytes >= clasr_gemm_workspace_bytes(M, N, K, precision), "gemm: workspace too small");
   CLASR_CHECK_ARG((((uintptr_t)workspace) & 255) == 0, "gemm: workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  const bool x3 = precision == CLASR_PREC_BF16X3;
+  const bool x3 = prec_x3(precision);
   const size_t a_sz = ((size_t)pad8(M) * pad8(K) * 2 + 255) / 256 * 256;
   const size_t b_sz = ((size_t)pad8(N) * pad8(K) * 2 + 255) / 256 * 256;
   char* w = (char*)workspace;
@@ -669,8 +678,8 @@ extern "C" int clasr_gemm_ex(const float* A, const float* B, float* C, int M, in
   const int a_rows = a_trans ? K : M, a_cols = a_trans ? M : K;
   const int b_rows = b_trans ? K : N, b_cols = b_trans ? N : K;
   int rc;
-  if ((rc = launch_split_bf16(A, a_rows, a_cols, a_cols, a_hi, a_lo, pad8(a_cols), s))) return rc;
-  if ((rc = launch_split_bf16(B, b_rows, b_cols, b_cols, b_hi, b_lo, pad8(b_cols), s))) return rc;
+  if ((rc = launch_split_bf16(A, a_rows, a_cols, a_cols, a_hi, a_lo, pad8(a_cols), s, prec_f16(precision)))) return rc;
+  if ((rc = launch_split_bf16(B, b_rows, b_cols, b_cols, b_hi, b_lo, pad8(b_cols), s, prec_f16(precision)))) return rc;
   if (k_splits > 1) {
     cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     CLASR_CHECK_ARG(e == cudaSuccess, "gemm: memset failed");
@@ -715,7 +724,7 @@ __global__ void colsum_kernel(const float* __restrict__ dy, int64_t M, int N, in
 
 static size_t linear_ws_bytes(int M, int N, int K, int precision) {
   // operands of the three GEMMs are split one pair at a time: max over (x,w), (dy,w), (dy,x)
-  const size_t parts = precision == CLASR_PREC_BF16X3 ? 2 : 1;
+  const size_t parts = prec_x3(precision) ? 2 : 1;
   auto sz = [&](int64_t r, int64_t c) { return ((size_t)pad8((int)r) * pad8((int)c) * 2 + 255) / 256 * 256; };
   const size_t x = sz(M, K), w = sz(N, K), dy = sz(M, N);
   return parts * (x + w + dy);
@@ -728,7 +737,7 @@ extern "C" size_t clasr_linear_workspace_bytes(int M, int N, int K, int precisio
 
 struct LinearWs { void *x_hi, *x_lo, *w_hi, *w_lo, *dy_hi, *dy_lo; };
 static LinearWs linear_ws_carve(void* base, int M, int N, int K, int precision) {
-  const bool x3 = precision == CLASR_PREC_BF16X3;
+  const bool x3 = prec_x3(precision);
   auto sz = [&](int64_t r, int64_t c) { return ((size_t)pad8((int)r) * pad8((int)c) * 2 + 255) / 256 * 256; };
   char* p = (char*)base;
   LinearWs w;
@@ -742,14 +751,14 @@ extern "C" int clasr_linear_fwd(const float* x, const float* w, const float* bia
                                 int precision, void* workspace, size_t workspace_bytes, void* stream) {
   CLASR_CHECK_ARG(x && w && y && workspace, "linear_fwd: null pointer");
   CLASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear_fwd: non-positive dimension");
-  CLASR_CHECK_ARG(precision == CLASR_PREC_BF16 || precision == CLASR_PREC_BF16X3, "linear_fwd: bad precision");
+  CLASR_CHECK_ARG(prec_ok(precision), "linear_fwd: bad precision");
   CLASR_CHECK_ARG(workspace_bytes >= linear_ws_bytes(M, N, K, precision), "linear_fwd: workspace too small");
   CLASR_CHECK_ARG((((uintptr_t)workspace) & 255) == 0, "linear_fwd: workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   LinearWs ws = linear_ws_carve(workspace, M, N, K, precision);
   int rc;
-  if ((rc = launch_split_bf16(x, M, K, K, ws.x_hi, ws.x_lo, pad8(K), s))) return rc;
-  if ((rc = launch_split_bf16(w, N, K, K, ws.w_hi, ws.w_lo, pad8(K), s))) return rc;
+  if ((rc = launch_split_bf16(x, M, K, K, ws.x_hi, ws.x_lo, pad8(K), s, prec_f16(precision)))) return rc;
+  if ((rc = launch_split_bf16(w, N, K, K, ws.w_hi, ws.w_lo, pad8(K), s, prec_f16(precision)))) return rc;
   prof_begin("linear_fwd", s);
   rc = launch_gemm_tc(ws.x_hi, ws.x_lo, pad8(K), 0, ws.w_hi, ws.w_lo, pad8(K), 0, M, N, K, y, N, precision, 0, 1, s,
                       nullptr, nullptr, bias);
@@ -763,13 +772,13 @@ extern "C" int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db
                                 void* workspace, size_t workspace_bytes, void* stream) {
   CLASR_CHECK_ARG(dy && workspace, "linear_bwd: null pointer");
   CLASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear_bwd: non-positive dimension");
-  CLASR_CHECK_ARG(precision == CLASR_PREC_BF16 || precision == CLASR_PREC_BF16X3, "linear_bwd: bad precision");
+  CLASR_CHECK_ARG(prec_ok(precision), "linear_bwd: bad precision");
   CLASR_CHECK_ARG(workspace_bytes >= linear_ws_bytes(M, N, K, precision), "linear_bwd: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
   LinearWs ws = linear_ws_carve(workspace, M, N, K, precision);
   int rc;
   if (dx || dw)
-    if ((rc = launch_split_bf16(dy, M, N, N, ws.dy_hi, ws.dy_lo, pad8(N), s))) return rc;
+    if ((rc = launch_split_bf16(dy, M, N, N, ws.dy_hi, ws.dy_lo, pad8(N), s, prec_f16(precision)))) return rc;
   prof_begin("linear_bwd", s);
   if (dx) {  // A = dy [M, N] K-major (K_gemm = N); B = W given as [K_gemm = N rows, N_gemm = K cols] (MN-major)
     if ((rc = launch_gemm_tc(ws.dy_hi, ws.dy_lo, pad8(N), 0, ws.w_hi, ws.w_lo, pad8(K), 1, M, K, N, dx, K, precision, 0, 1,

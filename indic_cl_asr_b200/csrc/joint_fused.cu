@@ -25,7 +25,7 @@
 namespace clasr {
 
 int launch_split_bf16(const float* src, int64_t rows, int cols, int64_t src_ld, void* hi, void* lo, int cols_pad,
-                      cudaStream_t s);
+                      cudaStream_t s, int f16);
 
 constexpr int kJM = 128;            // rows (lattice cells) per tile
 constexpr int kJK = 64;             // K block (one 128-byte swizzle span of bf16)
@@ -87,6 +87,7 @@ struct JointFwdParams {
   float* db_acc;              // [Vp] bias gradient: column sums of dZ, accumulated by the pass-2 epilogue (zeroed first)
   int* rows_pad_dev;          // [1] total_tiles * 128 (written by the tile-offset kernel)
   // ---- kMode 3 (forward that keeps the logits for the backward): z = logits + bias, fp32, compact tile-row order
+  int f16;                    // 16-bit operands are fp16 instead of bf16 (CLASR_PREC_FP16X3)
   float* zbuf;                // [rows_pad, ldzf]
   int ldzf;                   // round_up(Vp, 32): whole 32-column epilogue pieces
 };
@@ -337,8 +338,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     }
   } else if (warp == 1 && leader) {
     // ============================ MMA issuer (whole warp loops, one elected lane issues; pair: leader CTA) ====
-    const uint32_t idesc_full = tc::make_idesc_bf16(kPair ? 2 * kJM : kJM, C::kBN);
-    const uint32_t idesc_last = tc::make_idesc_bf16(kPair ? 2 * kJM : kJM, n_last);
+    const uint32_t idesc_full = tc::make_idesc_16(kPair ? 2 * kJM : kJM, C::kBN, 0, 0, p.f16);
+    const uint32_t idesc_last = tc::make_idesc_16(kPair ? 2 * kJM : kJM, n_last, 0, 0, p.f16);
     const uint32_t a_base = tc::smem_u32(a_smem);
     const uint32_t b_base = tc::smem_u32(b_ring);
     int stage = 0;
@@ -630,11 +631,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               uint32_t ph[8], pl[8];
 #pragma unroll
               for (int j2 = 0; j2 < 8; ++j2) {
-                const float g0 = gr[2 * j2], g1 = gr[2 * j2 + 1];
-                __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
-                __nv_bfloat162 ll = __floats2bfloat162_rn(g0 - __low2float(hh), g1 - __high2float(hh));
-                ph[j2] = *reinterpret_cast<uint32_t*>(&hh);
-                pl[j2] = *reinterpret_cast<uint32_t*>(&ll);
+                tc::pack_hi_lo(gr[2 * j2], gr[2 * j2 + 1], p.f16, ph[j2], pl[j2]);
               }
               st_global_256(p.dz_hi + grow * p.ldz + col0, ph);
               if (kTerms > 1) st_global_256(p.dz_lo + grow * p.ldz + col0, pl);
@@ -752,10 +749,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             h0 = (x & 0xffffu) >= p.drop_thresh ? h0 * p.drop_scale : 0.f;
             h1 = (x >> 16) >= p.drop_thresh ? h1 * p.drop_scale : 0.f;
           }
-          __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
-          __nv_bfloat162 ll = __floats2bfloat162_rn(h0 - __low2float(hh), h1 - __high2float(hh));
-          const uint32_t hw = *reinterpret_cast<uint32_t*>(&hh);
-          const uint32_t lw = *reinterpret_cast<uint32_t*>(&ll);
+          uint32_t hw, lw;
+          tc::pack_hi_lo(h0, h1, p.f16, hw, lw);
           const int rimm = (i & 3) + 8 * (i >> 2);  // compile-time part of the row index
           tc::st_shared_u32(ablk + aoff[i & 3] + rimm * 128, hw);
           if (kTerms > 1) tc::st_shared_u32(stg + soff[i & 3] + 8 * (i >> 2) * 64, lw);
@@ -980,11 +975,7 @@ __global__ void __maxnreg__(CLASR_DZ_REGS) joint_dz_kernel(JointFwdParams p, int
           uint32_t* plw = reinterpret_cast<uint32_t*>(&pl);
 #pragma unroll
           for (int j2 = 0; j2 < 4; ++j2) {
-            const float g0 = gr[2 * j2], g1 = gr[2 * j2 + 1];
-            __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
-            __nv_bfloat162 ll = __floats2bfloat162_rn(g0 - __low2float(hh), g1 - __high2float(hh));
-            phw[j2] = *reinterpret_cast<uint32_t*>(&hh);
-            plw[j2] = *reinterpret_cast<uint32_t*>(&ll);
+            tc::pack_hi_lo(gr[2 * j2], gr[2 * j2 + 1], p.f16, phw[j2], plw[j2]);
           }
           *reinterpret_cast<uint4*>(p.dz_hi + grow * p.ldz + col0) = ph;
           if (kTerms > 1) *reinterpret_cast<uint4*>(p.dz_lo + grow * p.ldz + col0) = pl;
@@ -1220,7 +1211,7 @@ struct JointBwdScratch {
 
 static inline JointBwdScratch joint_bwd_scratch_carve(void* base, int B, int T, int U1, int H, int Vp, int precision) {
   JointBwdScratch sc;
-  const bool x3 = precision == CLASR_PREC_BF16X3;
+  const bool x3 = prec_x3(precision);
   sc.rows_cap = (int64_t)B * ((((int64_t)T * U1) + kJM - 1) / kJM) * kJM;
   sc.ldz = (Vp + 15) / 16 * 16;
   sc.ldh = H;
@@ -1249,7 +1240,7 @@ struct JointStash {
 
 static inline JointStash joint_stash_carve(void* base, int B, int T, int U1, int H, int Vp, int precision) {
   JointStash st;
-  const bool x3 = precision == CLASR_PREC_BF16X3;
+  const bool x3 = prec_x3(precision);
   st.rows_cap = (int64_t)B * ((((int64_t)T * U1) + kJM - 1) / kJM) * kJM;
   st.ldzf = (Vp + 31) / 32 * 32;
   char* p = (char*)base;
@@ -1271,7 +1262,7 @@ static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, in
   j.vp_pad = (Vp + 15) / 16 * 16;
   const size_t wbytes = ((size_t)j.vp_pad * H * 2 + 255) / 256 * 256;
   j.w_hi = p + off; off += wbytes;
-  j.w_lo = p + off; off += (precision == CLASR_PREC_BF16X3) ? wbytes : 0;
+  j.w_lo = p + off; off += prec_x3(precision) ? wbytes : 0;
   j.tile_offsets = (int*)(p + off);
   off += ((size_t)(B + 2) * sizeof(int) + 255) / 256 * 256;
   j.bias_pad = (float*)(p + off);
@@ -1385,8 +1376,7 @@ static int check_joint_args(const char* who, const void* f, const void* g, const
   CLASR_CHECK_ARG(blank >= 0 && blank < Vp, "%s: blank %d outside [0,%d)", who, blank, Vp);
   CLASR_CHECK_ARG(activation >= CLASR_ACT_RELU && activation <= CLASR_ACT_TANH, "%s: unknown activation %d", who,
                   activation);
-  CLASR_CHECK_ARG(precision == CLASR_PREC_BF16 || precision == CLASR_PREC_BF16X3, "%s: unknown precision %d", who,
-                  precision);
+  CLASR_CHECK_ARG(prec_ok(precision), "%s: unknown precision %d", who, precision);
   CLASR_CHECK_ARG(ws_bytes >= clasr_joint_workspace_bytes(B, T, U1, H, Vp, precision), "%s: workspace too small", who);
   CLASR_CHECK_ARG((((uintptr_t)ws) & 255) == 0, "%s: workspace must be 256-byte aligned", who);
   CLASR_CHECK_ARG((((uintptr_t)f) & 15) == 0 && (((uintptr_t)g) & 15) == 0, "%s: f/g must be 16-byte aligned", who);
@@ -1409,9 +1399,9 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   }
   cudaStream_t s = (cudaStream_t)stream;
   JointWs jw = joint_ws_carve(workspace, B, T, U1, H, Vp, precision);
-  const bool x3 = precision == CLASR_PREC_BF16X3;
+  const bool x3 = prec_x3(precision);
   // W_out [Vp,H] fp32 -> bf16 hi[,lo] (rows beyond Vp are never read: TMA zero-fills out-of-bounds rows)
-  if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s))) return rc;
+  if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s, prec_f16(precision)))) return rc;
   joint_tile_offsets_kernel<<<1, 256, 0, s>>>(act_lens, label_lens, B, jw.tile_offsets, jw.tile_offsets + B + 1,
                                               b_out, Vp, jw.bias_pad);
   CLASR_CHECK_LAUNCH("joint_tile_offsets");
@@ -1421,6 +1411,7 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   p.bias = b_out; p.bias_pad = jw.bias_pad; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
   p.tile_offsets = jw.tile_offsets;
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
+  p.f16 = prec_f16(precision) ? 1 : 0;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.sumsq = sumsq;
   if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;
@@ -1487,7 +1478,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
     CLASR_CHECK_ARG((((uintptr_t)stash) & 255) == 0, "joint_rnnt_bwd: stash must be 256-byte aligned");
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const bool x3 = precision == CLASR_PREC_BF16X3;
+  const bool x3 = prec_x3(precision);
   JointWs jw = joint_ws_carve(workspace, B, T, U1, H, Vp, precision);   // filled by the forward call
   JointBwdScratch sc = joint_bwd_scratch_carve(scratch, B, T, U1, H, Vp, precision);
   CLASR_CHECK_ARG(sc.rows_cap < 2147483647LL, "joint_rnnt_bwd: too many lattice cells");
@@ -1501,6 +1492,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   p.bias = b_out; p.bias_pad = jw.bias_pad; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
   p.tile_offsets = jw.tile_offsets;
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
+  p.f16 = prec_f16(precision) ? 1 : 0;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.grad_out = grad_out; p.grad_cells = grad_cells; p.fastemit_lambda = fastemit_lambda; p.clamp = clamp;
   if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -319,6 +320,26 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr, 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_mn_major & 1) << 15) | ((uint32_t)(b_mn_major & 1) << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// the same for either 16-bit format: a_format = b_format = 1 (BF16) or 0 (F16) — they must match (a mixed pair is an
+// illegal instruction, tools/experimental/mxf8_probe.cu)
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int a_mn_major, int b_mn_major, int f16) {
+  return f16 ? (make_idesc_bf16(M, N, a_mn_major, b_mn_major) & ~((7u << 7) | (7u << 10)))
+             : make_idesc_bf16(M, N, a_mn_major, b_mn_major);
+}
+// (a, b) -> packed 16-bit pairs hi = rn(x), lo = rn(x - hi), in bf16 or fp16
+__device__ __forceinline__ void pack_hi_lo(float a, float b, int f16, uint32_t& hi, uint32_t& lo) {
+  if (f16) {
+    const __half2 hh = __floats2half2_rn(a, b);
+    const __half2 ll = __floats2half2_rn(a - __low2float(hh), b - __high2float(hh));
+    hi = *reinterpret_cast<const uint32_t*>(&hh);
+    lo = *reinterpret_cast<const uint32_t*>(&ll);
+  } else {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(a - __low2float(hh), b - __high2float(hh));
+    hi = *reinterpret_cast<const uint32_t*>(&hh);
+    lo = *reinterpret_cast<const uint32_t*>(&ll);
+  }
 }
 
 // Byte offset of element (row, k) inside a K-major SWIZZLE_128B tile whose rows are 64 bf16 (128 B) wide and

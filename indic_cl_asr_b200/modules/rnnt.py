@@ -98,6 +98,9 @@ class RNNTJoint(torch.nn.Module):
             raise ValueError("fused_impl must be 'tcgen05' or 'materialised'")
         if precision not in _lib.PREC:
             raise ValueError(f"precision must be one of {sorted(_lib.PREC)}")
+        if precision == "fp16x3" and str(jointnet.get("activation", "relu")).lower() == "relu":
+            raise ValueError("precision='fp16x3' needs a bounded joint activation (tanh / sigmoid): hidden values are "
+                             "split into fp16 halves")
         self.fused_impl = fused_impl
         self.precision = precision
 

@@ -25,7 +25,7 @@ def gemm_nt(A, B, precision):
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 640), (300, 520, 200), (1000, 1025, 640), (37, 19, 13),
                                    (4096, 640, 1040)])
-@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("bf16x3", 2e-5)])
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("bf16x3", 2e-5), ("fp16x3", 5e-6)])
 def test_gemm_nt(M, N, K, precision, tol):
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g)
@@ -51,7 +51,7 @@ def gemm_ex(A, B, M, N, K, a_trans, b_trans, k_splits, precision):
 
 @pytest.mark.parametrize("a_trans,b_trans", [(0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K,splits", [(128, 256, 64, 1), (200, 300, 500, 1), (1025, 648, 4000, 7), (640, 1025, 256, 1)])
-@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("bf16x3", 2e-5)])
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("bf16x3", 2e-5), ("fp16x3", 5e-6)])
 def test_gemm_transposed_operands_and_split_k(M, N, K, splits, a_trans, b_trans, precision, tol):
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g)
