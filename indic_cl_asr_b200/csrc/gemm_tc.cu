@@ -125,6 +125,7 @@ struct GemmParams {
   int group_n;       // pair kernel, no split-K: walk all N tiles of a row block back to back
   int b_keep;        // pair kernel: B is small and re-read by every row block -> TMA loads carry L2 evict_last
   int f16;           // operands are fp16 instead of bf16 (CLASR_PREC_FP16X3)
+  const float* alpha_dev;  // optional device scalar: the atomic epilogue adds alpha * acc (undoes an operand pre-scale)
 };
 
 template <int kTerms>
@@ -272,6 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int row = m0 + q * 32 + lane;
       float* crow = p.C + (int64_t)row * p.ldc;
       const bool vec_ok = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+      const float alpha = (p.atomic_add && p.alpha_dev) ? __ldg(p.alpha_dev) : 1.f;
       const bool vec32_ok = ((p.ldc & 7) == 0) && ((((uintptr_t)p.C) & 31) == 0);
 #pragma unroll 1
       for (int c = 0; c < kBN / 32; ++c) {
@@ -282,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (row < Mdyn && col0 < p.N) {
           if (p.atomic_add) {
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(crow + col0 + j, __uint_as_float(r[j]));
+              if (col0 + j < p.N) atomicAdd(crow + col0 + j, alpha * __uint_as_float(r[j]));
           } else if (vec_ok && col0 + 32 <= p.N) {
             if (p.bias) {
 #pragma unroll
@@ -513,6 +515,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int row = m0 + q * 32 + lane;
       float* crow = p.C + (int64_t)row * p.ldc;
       const bool vec_ok = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+      const float alpha = (p.atomic_add && p.alpha_dev) ? __ldg(p.alpha_dev) : 1.f;
       const bool vec32_ok = ((p.ldc & 7) == 0) && ((((uintptr_t)p.C) & 31) == 0);
 #pragma unroll 1
       for (int c = 0; c < nw / 32; ++c) {
@@ -523,7 +526,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         if (row < Mdyn && col0 < p.N) {
           if (p.atomic_add) {
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(crow + col0 + j, __uint_as_float(r[j]));
+              if (col0 + j < p.N) atomicAdd(crow + col0 + j, alpha * __uint_as_float(r[j]));
           } else if (vec_ok && col0 + 32 <= p.N) {
             if (p.bias) {
 #pragma unroll
@@ -567,7 +570,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 // lda / ldb in elements (multiples of 8).  k_splits > 1 requires atomic_add and a zero-initialised C.
 int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
                    int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
-                   int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias) {
+                   int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias,
+                   const float* alpha_dev) {
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   const bool x3 = prec_x3(precision);
@@ -616,7 +620,7 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
   GemmParams p{M, N, K, C, ldc, atomic_add, k_splits, a_mn, b_mn, m_dev, k_dev, atomic_add ? nullptr : bias,
                ge ? atoi(ge) : 0,
                /*b_keep*/ ((size_t)N * K * 2 * (x3 ? 2 : 1) <= ((size_t)16 << 20) && (int64_t)M >= 8 * (int64_t)N) ? 1 : 0,
-               prec_f16(precision) ? 1 : 0};
+               prec_f16(precision) ? 1 : 0, alpha_dev};
   if (use_pair) {
     const int tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN) * k_splits;
     int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
@@ -685,7 +689,7 @@ extern "C" int clasr_gemm_ex(const float* A, const float* B, float* C, int M, in
     CLASR_CHECK_ARG(e == cudaSuccess, "gemm: memset failed");
   }
   return launch_gemm_tc(a_hi, a_lo, pad8(a_cols), a_trans, b_hi, b_lo, pad8(b_cols), b_trans, M, N, K, C, N, precision,
-                        k_splits > 1, k_splits, s, nullptr, nullptr, nullptr);
+                        k_splits > 1, k_splits, s, nullptr, nullptr, nullptr, nullptr);
 }
 
 extern "C" int clasr_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int precision,
@@ -761,7 +765,7 @@ extern "C" int clasr_linear_fwd(const float* x, const float* w, const float* bia
   if ((rc = launch_split_bf16(w, N, K, K, ws.w_hi, ws.w_lo, pad8(K), s, prec_f16(precision)))) return rc;
   prof_begin("linear_fwd", s);
   rc = launch_gemm_tc(ws.x_hi, ws.x_lo, pad8(K), 0, ws.w_hi, ws.w_lo, pad8(K), 0, M, N, K, y, N, precision, 0, 1, s,
-                      nullptr, nullptr, bias);
+                      nullptr, nullptr, bias, nullptr);
   prof_end("linear_fwd", s);
   return rc;
 }
@@ -782,7 +786,7 @@ extern "C" int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db
   prof_begin("linear_bwd", s);
   if (dx) {  // A = dy [M, N] K-major (K_gemm = N); B = W given as [K_gemm = N rows, N_gemm = K cols] (MN-major)
     if ((rc = launch_gemm_tc(ws.dy_hi, ws.dy_lo, pad8(N), 0, ws.w_hi, ws.w_lo, pad8(K), 1, M, K, N, dx, K, precision, 0, 1,
-                             s, nullptr, nullptr, nullptr)))
+                             s, nullptr, nullptr, nullptr, nullptr)))
       return rc;
   }
   if (dw) {  // A = dy given as [K_gemm = M rows, M_gemm = N cols]; B = x given as [K_gemm = M rows, N_gemm = K cols]
@@ -796,7 +800,7 @@ extern "C" int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db
       CLASR_CHECK_ARG(e == cudaSuccess, "linear_bwd: memset failed");
     }
     if ((rc = launch_gemm_tc(ws.dy_hi, ws.dy_lo, pad8(N), 1, ws.x_hi, ws.x_lo, pad8(K), 1, N, K, M, dw, K, precision,
-                             splits > 1, splits, s, nullptr, nullptr, nullptr)))
+                             splits > 1, splits, s, nullptr, nullptr, nullptr, nullptr)))
       return rc;
   }
   if (db) {

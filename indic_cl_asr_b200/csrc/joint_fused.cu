@@ -88,6 +88,7 @@ struct JointFwdParams {
   int* rows_pad_dev;          // [1] total_tiles * 128 (written by the tile-offset kernel)
   // ---- kMode 3 (forward that keeps the logits for the backward): z = logits + bias, fp32, compact tile-row order
   int f16;                    // 16-bit operands are fp16 instead of bf16 (CLASR_PREC_FP16X3)
+  const float* gscale;        // fp16 only: [2] = {S, 1/S}, the power-of-two pre-scale of dZ (joint_gscale_kernel), or null
   float* zbuf;                // [rows_pad, ldzf]
   int ldzf;                   // round_up(Vp, 32): whole 32-column epilogue pieces
 };
@@ -142,6 +143,7 @@ __device__ __forceinline__ RowGrad joint_row_grad(const JointFwdParams& p, int b
     if (t < Tb - 1) rg.blank_sub += expf((float)(a + beta_t1 - ll + (double)lpair.x));
     rg.label_sub = has_label ? expf(log1pf(p.fastemit_lambda) + (float)(a + beta_u1 - ll + (double)lpair.y)) : 0.f;
   }
+  if (p.gscale) rg.go *= __ldg(p.gscale);   // dZ leaves pre-scaled by S (fp16 operands); every consumer multiplies by 1/S
   return rg;
 }
 
@@ -205,6 +207,32 @@ __global__ void joint_tile_offsets_kernel(const int64_t* __restrict__ act_lens, 
       tile_offsets[b + 1] = acc;
     }
     rows_pad_dev[0] = acc * kJM;
+  }
+}
+
+// fp16 operands (CLASR_PREC_FP16X3): dZ = upstream x (softmax terms) is split into fp16 halves, whose relative accuracy
+// degrades below 6e-5 — exactly where small upstream gradients (mean reductions, loss weights) put it.  dZ is therefore
+// produced pre-scaled by the power of two S that brings max|upstream| * headroom to ~1, and dHid / dW / db / the blank
+// terms are multiplied by 1/S where they are consumed (exact: powers of two).  out[0] = S, out[1] = 1/S.
+__global__ void joint_gscale_kernel(const float* __restrict__ g, int64_t n, float headroom, float* __restrict__ out) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(g[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0) {
+      int e = 0;
+      if (m > 0.f && isfinite(m)) {
+        frexpf(m * headroom, &e);                 // m * headroom = f * 2^e, f in [0.5, 1)
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+      }
+      out[0] = ldexpf(1.f, -e);
+      out[1] = ldexpf(1.f, e);
+    }
   }
 }
 
@@ -650,7 +678,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               }
             }
             gr[0] += __shfl_xor_sync(0xffffffffu, gr[0], 1);
-            if ((lane & 1) == 0 && col0 + (lane >> 1) < p.Vp) atomicAdd(p.db_acc + col0 + (lane >> 1), gr[0]);
+            if ((lane & 1) == 0 && col0 + (lane >> 1) < p.Vp)
+              atomicAdd(p.db_acc + col0 + (lane >> 1), p.gscale ? gr[0] * __ldg(p.gscale + 1) : gr[0]);
           }
         }
         tc::tc_fence_before();
@@ -985,9 +1014,10 @@ __global__ void __maxnreg__(CLASR_DZ_REGS) joint_dz_kernel(JointFwdParams p, int
     __syncthreads();  // the next chunk's scalars are complete; this chunk's are no longer read
   }
   if (col_ok) {
+    const float inv_s = p.gscale ? __ldg(p.gscale + 1) : 1.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (col0 + j < p.Vp) atomicAdd(p.db_acc + col0 + j, db[j]);
+      if (col0 + j < p.Vp) atomicAdd(p.db_acc + col0 + j, db[j] * inv_s);
   }
 }
 
@@ -1085,7 +1115,8 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
                                                               float* __restrict__ d_f, float* __restrict__ d_g,
                                                               const float* __restrict__ dzb,
                                                               float* __restrict__ d_w_blank,
-                                                              const float* __restrict__ w_blank, uint32_t drop_thresh,
+                                                              const float* __restrict__ w_blank,
+                                                              const float* __restrict__ gscale, uint32_t drop_thresh,
                                                               uint32_t drop_seed_a, uint32_t drop_seed_b,
                                                               float drop_scale) {
   extern __shared__ float sm_dfg[];
@@ -1131,6 +1162,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
   float wb = 0.f;
   // ... and the blank column of the dHid GEMM (K = V instead of V+1): dHid[cell, k] += dZ[cell, blank] * W[blank, k]
   const float wbk = (dzb && live) ? __ldg(w_blank + k0 + lane) : 0.f;
+  const float inv_s = gscale ? __ldg(gscale + 1) : 1.f;   // dHid and dzb arrive pre-scaled by S (fp16 operands)
   for (int t = t_begin + warp; t < t_end; t += nw) {
     float df = 0.f;
     if (t < Tb) {
@@ -1151,7 +1183,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
           float h, dh;
           act_pair(fv, eg_s[(u + j) * 32 + lane], h, dh);
           if (drop_thresh) drop(r0 + u + j, h, dh);
-          const float pv = (dzb ? fmaf(zb[j], wbk, d[j]) : d[j]) * dh;
+          const float pv = (dzb ? fmaf(zb[j], wbk, d[j]) : d[j]) * (dh * inv_s);
           df += pv;
           atomicAdd(dg_s + (u + j) * 32 + lane, pv);
           if (dzb) wb = fmaf(zb[j], h, wb);
@@ -1162,7 +1194,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
         act_pair(fv, eg_s[u * 32 + lane], h, dh);
         if (drop_thresh) drop(r0 + u, h, dh);
         const float zb1 = dzb ? __ldg(dzb + r0 + u) : 0.f;
-        const float pv = fmaf(zb1, wbk, ld_stream1(dp + (int64_t)u * H)) * dh;
+        const float pv = fmaf(zb1, wbk, ld_stream1(dp + (int64_t)u * H)) * (dh * inv_s);
         df += pv;
         atomicAdd(dg_s + u * 32 + lane, pv);
         if (dzb) wb = fmaf(zb1, h, wb);
@@ -1170,7 +1202,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
     }
     d_f[((int64_t)b * T + t) * H + k0 + lane] = df;
   }
-  if (dzb && live) atomicAdd(d_w_blank + k0 + lane, wb);
+  if (dzb && live) atomicAdd(d_w_blank + k0 + lane, wb * inv_s);
   if (live) {
     __syncthreads();
     for (int i = threadIdx.x; i < Ub1 * 32; i += blockDim.x)
@@ -1180,7 +1212,8 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
 
 int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
                    int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
-                   int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias = nullptr);
+                   int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias = nullptr,
+                   const float* alpha_dev = nullptr);
 
 // ------------------------------------------------------------------------------------------------
 // workspace layout of the fused path
@@ -1190,6 +1223,7 @@ struct JointWs {
   void* w_hi;
   void* w_lo;
   int* tile_offsets;   // [B+1], then [1] rows_pad
+  float* gscale;       // [2] fp16 operands: power-of-two pre-scale of dZ and its inverse
   float* bias_pad;     // [round_up(Vp,32)+32]
   float* ef;           // [B,T,H]  scaled pre-activation c*f (tanh / sigmoid; relu reads f directly)
   float* eg;           // [B,U1,H]
@@ -1265,6 +1299,8 @@ static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, in
   j.w_lo = p + off; off += prec_x3(precision) ? wbytes : 0;
   j.tile_offsets = (int*)(p + off);
   off += ((size_t)(B + 2) * sizeof(int) + 255) / 256 * 256;
+  j.gscale = (float*)(p + off);
+  off += 256;
   j.bias_pad = (float*)(p + off);
   off += ((size_t)((Vp + 31) / 32 * 32 + 32) * sizeof(float) + 255) / 256 * 256;
   j.ef = (float*)(p + off);
@@ -1504,6 +1540,12 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
                            (size_t)2 * U1 * 32 * sizeof(float) <= 200 * 1024;
   p.dzb = blank_split ? sc.dzb : nullptr;
   p.db_acc = d_b_out;
+  if (p.f16 && (mode == 2 || grad_out)) {   // fp16 operands: pre-scale dZ to O(1) (see joint_gscale_kernel)
+    if (mode == 1) joint_gscale_kernel<<<1, 256, 0, s>>>(grad_out, B, 1.f + fastemit_lambda, jw.gscale);
+    else joint_gscale_kernel<<<1, 1024, 0, s>>>(grad_cells, (int64_t)B * T * U1, 128.f, jw.gscale);
+    CLASR_CHECK_LAUNCH("joint_gscale");
+    p.gscale = jw.gscale;
+  }
   {  // d_b accumulates in the pass-2a epilogue, d_W in the split-K GEMM: both start from zero
     cudaError_t e1 = cudaMemsetAsync(d_b_out, 0, (size_t)Vp * sizeof(float), s);
     cudaError_t e2 = cudaMemsetAsync(d_w_out, 0, (size_t)Vp * H * sizeof(float), s);
@@ -1556,7 +1598,8 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   // ---- pass 2c: dW[Vp, H] = dZ^T . Hid       (both operands MN-major, split-K over the rows, fp32 atomics)
   prof_begin("gemm_dw", s);
   if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, hid_hi, hid_lo, sc.ldh, 1, blank_split ? Vp - 1 : Vp, H,
-                           (int)sc.rows_cap, d_w_out, H, precision, 1, /*auto split-K*/ 0, s, nullptr, rows_pad_dev)))
+                           (int)sc.rows_cap, d_w_out, H, precision, 1, /*auto split-K*/ 0, s, nullptr, rows_pad_dev,
+                           nullptr, p.gscale ? p.gscale + 1 : nullptr)))
     return rc;
   prof_end("gemm_dw", s);
   // ---- pass 2d: through the activation and the broadcast add: d_f = sum_u, d_g = sum_t of dHid * act'(f+g)
@@ -1575,7 +1618,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
     joint_dfg_fused_kernel<ACT><<<grid, 256, smem, s>>>(sc.dhid, ef_, eg_, act_lens, label_lens, jw.tile_offsets,  \
                                                         T, U1, H, d_f, d_g, blank_split ? sc.dzb : nullptr,        \
                                                         d_w_out + (size_t)blank * H, w_out + (size_t)blank * H,    \
-                                                        p.drop_thresh, p.drop_seed_a,                              \
+                                                        p.gscale, p.drop_thresh, p.drop_seed_a,                    \
                                                         p.drop_seed_b, p.drop_scale);                              \
   } while (0)
       if (activation == CLASR_ACT_RELU) CLASR_LAUNCH_DFG(CLASR_ACT_RELU);
@@ -1585,6 +1628,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
       CLASR_CHECK_LAUNCH("joint_dfg_fused");
     } else {  // very long label sequences: the two-pass kernel (reads dHid twice, no shared-memory partials)
       CLASR_CHECK_ARG(p.drop_thresh == 0, "joint_rnnt_bwd: in-kernel dropout needs U+1 <= 800 (single-pass d_f/d_g kernel)");
+      CLASR_CHECK_ARG(!p.gscale, "joint_rnnt_bwd: fp16x3 needs U+1 <= 800 (single-pass d_f/d_g kernel)");
       joint_dfg_kernel<<<dim3(T, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
                                                  activation, 0, d_f);
       CLASR_CHECK_LAUNCH("joint_df");

@@ -177,7 +177,8 @@ class RNNTJoint(torch.nn.Module):
         f+g flips relu' for ~80x more elements than fp32 rounding does, which alone costs 3e-4 of gradient parity."""
         if x.is_cuda and str(self.activation).lower() != "relu":
             from ..linear import linear_x3
-            return linear_x3(x, lin.weight, lin.bias, self.precision)
+            # the projections' upstream gradients are not pre-scaled: they keep the range-safe bf16 split
+            return linear_x3(x, lin.weight, lin.bias, "bf16x3" if self.precision == "fp16x3" else self.precision)
         return lin(x)
 
     def project_encoder(self, encoder_output: torch.Tensor) -> torch.Tensor:

@@ -112,3 +112,28 @@ def test_degenerate_shapes():
         assert rel_err(costs.detach().cpu().numpy(), oc.detach().numpy()) <= 1e-5, (B, T, U)
         for name, got, ref in zip(["d_f", "d_g", "d_W", "d_b"], (fd, gd, Wd, bd), leaves):
             assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy()) <= 1e-4, (B, T, U, name)
+
+
+@pytest.mark.parametrize("scale", [1e-5, 1.0, 3e4])
+@pytest.mark.parametrize("stash", ["", "0"], ids=["stash", "recompute"])
+def test_fp16x3_gradient_scale_invariance(scale, stash, monkeypatch):
+    """fp16 operands lose relative accuracy below 6e-5, so dZ is produced pre-scaled by a power of two derived from the
+    upstream gradient (joint_gscale_kernel) and un-scaled where it is consumed: parity must not depend on the size of
+    the upstream gradient (mean reductions / loss weights make it tiny, a loss scale makes it huge)."""
+    monkeypatch.setenv("CLASR_JOINT_STASH", stash)
+    B, T, U, V, H = 3, 33, 12, 300, 128
+    f, g, W, b, lab, al, ll = make(B, T, U, V, H, seed=41)
+    fd, gd, Wd, bd = [x.to(DEV).requires_grad_(True) for x in (f, g, W, b)]
+    costs = fused_joint_rnnt_loss(fd, gd, Wd, bd, lab.to(DEV), al.to(DEV), ll.to(DEV), V, "tanh", "fp16x3",
+                                  fastemit_lambda=0.01)
+    wts = torch.linspace(0.5, 1.5, B) * scale
+    (costs * wts.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    f64, g64 = f.double().requires_grad_(True), g.double().requires_grad_(True)
+    W64, b64 = W.double().requires_grad_(True), b.double().requires_grad_(True)
+    z = torch.nn.functional.linear(torch.tanh(f64.unsqueeze(2) + g64.unsqueeze(1)), W64, b64)
+    oc = joint_oracle.rnnt_loss(z, lab, al, ll, V, fastemit_lambda=0.01)
+    (oc * wts.double()).sum().backward()
+    for name, got, ref in zip(["d_f", "d_g", "d_W", "d_b"], (fd, gd, Wd, bd), (f64, g64, W64, b64)):
+        assert torch.isfinite(got.grad).all(), name
+        assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy()) <= 2e-5, (name, scale)
