@@ -64,12 +64,13 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 // ------------------------------------------------------------------------------------------------
 __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t src_ld,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int cols_pad,
-                                  int f16) {
+                                  int f16, const float* __restrict__ scale_dev) {
+  const float scale = scale_dev ? __ldg(scale_dev) : 1.f;   // power of two (exact)
   const int64_t n = rows * (int64_t)cols_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols_pad;
     const int c = (int)(i - r * cols_pad);
-    const float x = c < cols ? src[r * src_ld + c] : 0.f;
+    const float x = c < cols ? src[r * src_ld + c] * scale : 0.f;
     if (f16) {   // the same 2-byte slots hold fp16 (CLASR_PREC_FP16X3)
       const __half h = __float2half_rn(x);
       reinterpret_cast<__half*>(hi)[i] = h;
@@ -84,12 +85,12 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t rows, i
 }
 
 int launch_split_bf16(const float* src, int64_t rows, int cols, int64_t src_ld, void* hi, void* lo, int cols_pad,
-                      cudaStream_t s, int f16) {
+                      cudaStream_t s, int f16, const float* scale_dev) {
   const int64_t n = rows * (int64_t)cols_pad;
   int grid = (int)((n + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   if (grid < 1) grid = 1;
-  split_bf16_kernel<<<grid, 256, 0, s>>>(src, rows, cols, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, cols_pad, f16);
+  split_bf16_kernel<<<grid, 256, 0, s>>>(src, rows, cols, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, cols_pad, f16, scale_dev);
   CLASR_CHECK_LAUNCH("split_bf16");
   return CLASR_STATUS_SUCCESS;
 }
@@ -682,8 +683,8 @@ extern "C" int clasr_gemm_ex(const float* A, const float* B, float* C, int M, in
   const int a_rows = a_trans ? K : M, a_cols = a_trans ? M : K;
   const int b_rows = b_trans ? K : N, b_cols = b_trans ? N : K;
   int rc;
-  if ((rc = launch_split_bf16(A, a_rows, a_cols, a_cols, a_hi, a_lo, pad8(a_cols), s, prec_f16(precision)))) return rc;
-  if ((rc = launch_split_bf16(B, b_rows, b_cols, b_cols, b_hi, b_lo, pad8(b_cols), s, prec_f16(precision)))) return rc;
+  if ((rc = launch_split_bf16(A, a_rows, a_cols, a_cols, a_hi, a_lo, pad8(a_cols), s, prec_f16(precision), nullptr))) return rc;
+  if ((rc = launch_split_bf16(B, b_rows, b_cols, b_cols, b_hi, b_lo, pad8(b_cols), s, prec_f16(precision), nullptr))) return rc;
   if (k_splits > 1) {
     cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     CLASR_CHECK_ARG(e == cudaSuccess, "gemm: memset failed");
@@ -761,8 +762,8 @@ extern "C" int clasr_linear_fwd(const float* x, const float* w, const float* bia
   cudaStream_t s = (cudaStream_t)stream;
   LinearWs ws = linear_ws_carve(workspace, M, N, K, precision);
   int rc;
-  if ((rc = launch_split_bf16(x, M, K, K, ws.x_hi, ws.x_lo, pad8(K), s, prec_f16(precision)))) return rc;
-  if ((rc = launch_split_bf16(w, N, K, K, ws.w_hi, ws.w_lo, pad8(K), s, prec_f16(precision)))) return rc;
+  if ((rc = launch_split_bf16(x, M, K, K, ws.x_hi, ws.x_lo, pad8(K), s, prec_f16(precision), nullptr))) return rc;
+  if ((rc = launch_split_bf16(w, N, K, K, ws.w_hi, ws.w_lo, pad8(K), s, prec_f16(precision), nullptr))) return rc;
   prof_begin("linear_fwd", s);
   rc = launch_gemm_tc(ws.x_hi, ws.x_lo, pad8(K), 0, ws.w_hi, ws.w_lo, pad8(K), 0, M, N, K, y, N, precision, 0, 1, s,
                       nullptr, nullptr, bias, nullptr);
@@ -782,7 +783,7 @@ extern "C" int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db
   LinearWs ws = linear_ws_carve(workspace, M, N, K, precision);
   int rc;
   if (dx || dw)
-    if ((rc = launch_split_bf16(dy, M, N, N, ws.dy_hi, ws.dy_lo, pad8(N), s, prec_f16(precision)))) return rc;
+    if ((rc = launch_split_bf16(dy, M, N, N, ws.dy_hi, ws.dy_lo, pad8(N), s, prec_f16(precision), nullptr))) return rc;
   prof_begin("linear_bwd", s);
   if (dx) {  // A = dy [M, N] K-major (K_gemm = N); B = W given as [K_gemm = N rows, N_gemm = K cols] (MN-major)
     if ((rc = launch_gemm_tc(ws.dy_hi, ws.dy_lo, pad8(N), 0, ws.w_hi, ws.w_lo, pad8(K), 1, M, K, N, dx, K, precision, 0, 1,

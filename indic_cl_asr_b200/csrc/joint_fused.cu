@@ -25,7 +25,7 @@
 namespace clasr {
 
 int launch_split_bf16(const float* src, int64_t rows, int cols, int64_t src_ld, void* hi, void* lo, int cols_pad,
-                      cudaStream_t s, int f16);
+                      cudaStream_t s, int f16, const float* scale_dev);
 
 constexpr int kJM = 128;            // rows (lattice cells) per tile
 constexpr int kJK = 64;             // K block (one 128-byte swizzle span of bf16)
@@ -89,6 +89,7 @@ struct JointFwdParams {
   // ---- kMode 3 (forward that keeps the logits for the backward): z = logits + bias, fp32, compact tile-row order
   int f16;                    // 16-bit operands are fp16 instead of bf16 (CLASR_PREC_FP16X3)
   const float* gscale;        // fp16 only: [2] = {S, 1/S}, the power-of-two pre-scale of dZ (joint_gscale_kernel), or null
+  const float* wscale;        // fp16 only: [2] = {Sw, 1/Sw}, the pre-scale of W_out (max|W| Sw ~ 1); logits = acc / Sw + b
   float* zbuf;                // [rows_pad, ldzf]
   int ldzf;                   // round_up(Vp, 32): whole 32-column epilogue pieces
 };
@@ -471,6 +472,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     const int egrp = (warp - 4) >> 2;   // kWide: this warpgroup serves accumulator buffer `egrp` only
     const uint64_t pol_stream = tc::l2_policy_evict_first();
     (void)pol_stream;
+    const float inv_w = p.wscale ? __ldg(p.wscale + 1) : 1.f;   // 1.0: fmaf(acc, 1, b) == acc + b exactly
     const int row = q * 32 + lane;
     int acc_it = 0;
     for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
@@ -515,10 +517,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             float z[32];
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              z[4 * j4 + 0] = __uint_as_float(rr[4 * j4 + 0]) + bv[j4].x;
-              z[4 * j4 + 1] = __uint_as_float(rr[4 * j4 + 1]) + bv[j4].y;
-              z[4 * j4 + 2] = __uint_as_float(rr[4 * j4 + 2]) + bv[j4].z;
-              z[4 * j4 + 3] = __uint_as_float(rr[4 * j4 + 3]) + bv[j4].w;
+              z[4 * j4 + 0] = fmaf(__uint_as_float(rr[4 * j4 + 0]), inv_w, bv[j4].x);
+              z[4 * j4 + 1] = fmaf(__uint_as_float(rr[4 * j4 + 1]), inv_w, bv[j4].y);
+              z[4 * j4 + 2] = fmaf(__uint_as_float(rr[4 * j4 + 2]), inv_w, bv[j4].z);
+              z[4 * j4 + 3] = fmaf(__uint_as_float(rr[4 * j4 + 3]), inv_w, bv[j4].w);
             }
             const bool tail = col0 + 32 > p.Vp;
             if (p.sumsq) {
@@ -610,10 +612,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             tc::tmem_ld_wait();
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              gr[4 * j4 + 0] = __uint_as_float(rr[4 * j4 + 0]) + bv[j4].x;
-              gr[4 * j4 + 1] = __uint_as_float(rr[4 * j4 + 1]) + bv[j4].y;
-              gr[4 * j4 + 2] = __uint_as_float(rr[4 * j4 + 2]) + bv[j4].z;
-              gr[4 * j4 + 3] = __uint_as_float(rr[4 * j4 + 3]) + bv[j4].w;
+              gr[4 * j4 + 0] = fmaf(__uint_as_float(rr[4 * j4 + 0]), inv_w, bv[j4].x);
+              gr[4 * j4 + 1] = fmaf(__uint_as_float(rr[4 * j4 + 1]), inv_w, bv[j4].y);
+              gr[4 * j4 + 2] = fmaf(__uint_as_float(rr[4 * j4 + 2]), inv_w, bv[j4].z);
+              gr[4 * j4 + 3] = fmaf(__uint_as_float(rr[4 * j4 + 3]), inv_w, bv[j4].w);
             }
             if (kMode == 2) {
               // MAS importance objective: dZ = 2 z * upstream (go); nothing else to do per logit
@@ -1116,7 +1118,8 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
                                                               const float* __restrict__ dzb,
                                                               float* __restrict__ d_w_blank,
                                                               const float* __restrict__ w_blank,
-                                                              const float* __restrict__ gscale, uint32_t drop_thresh,
+                                                              const float* __restrict__ gscale,
+                                                              const float* __restrict__ wscale, uint32_t drop_thresh,
                                                               uint32_t drop_seed_a, uint32_t drop_seed_b,
                                                               float drop_scale) {
   extern __shared__ float sm_dfg[];
@@ -1161,8 +1164,11 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
   // that would cost a whole extra 256-row tile in the dW GEMM; here it is one FMA per element on data already in flight
   float wb = 0.f;
   // ... and the blank column of the dHid GEMM (K = V instead of V+1): dHid[cell, k] += dZ[cell, blank] * W[blank, k]
-  const float wbk = (dzb && live) ? __ldg(w_blank + k0 + lane) : 0.f;
-  const float inv_s = gscale ? __ldg(gscale + 1) : 1.f;   // dHid and dzb arrive pre-scaled by S (fp16 operands)
+  // fp16 operands: dZ (hence dzb) arrives pre-scaled by S, dHid by S * Sw (W_out is split pre-scaled by Sw)
+  const float s_w = wscale ? __ldg(wscale) : 1.f;
+  const float wbk = (dzb && live) ? __ldg(w_blank + k0 + lane) * s_w : 0.f;
+  const float inv_s = gscale ? __ldg(gscale + 1) : 1.f;
+  const float inv_sw = inv_s * (wscale ? __ldg(wscale + 1) : 1.f);
   for (int t = t_begin + warp; t < t_end; t += nw) {
     float df = 0.f;
     if (t < Tb) {
@@ -1183,7 +1189,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
           float h, dh;
           act_pair(fv, eg_s[(u + j) * 32 + lane], h, dh);
           if (drop_thresh) drop(r0 + u + j, h, dh);
-          const float pv = (dzb ? fmaf(zb[j], wbk, d[j]) : d[j]) * (dh * inv_s);
+          const float pv = (dzb ? fmaf(zb[j], wbk, d[j]) : d[j]) * (dh * inv_sw);
           df += pv;
           atomicAdd(dg_s + (u + j) * 32 + lane, pv);
           if (dzb) wb = fmaf(zb[j], h, wb);
@@ -1194,7 +1200,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
         act_pair(fv, eg_s[u * 32 + lane], h, dh);
         if (drop_thresh) drop(r0 + u, h, dh);
         const float zb1 = dzb ? __ldg(dzb + r0 + u) : 0.f;
-        const float pv = fmaf(zb1, wbk, ld_stream1(dp + (int64_t)u * H)) * (dh * inv_s);
+        const float pv = fmaf(zb1, wbk, ld_stream1(dp + (int64_t)u * H)) * (dh * inv_sw);
         df += pv;
         atomicAdd(dg_s + u * 32 + lane, pv);
         if (dzb) wb = fmaf(zb1, h, wb);
@@ -1437,7 +1443,14 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   JointWs jw = joint_ws_carve(workspace, B, T, U1, H, Vp, precision);
   const bool x3 = prec_x3(precision);
   // W_out [Vp,H] fp32 -> bf16 hi[,lo] (rows beyond Vp are never read: TMA zero-fills out-of-bounds rows)
-  if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s, prec_f16(precision)))) return rc;
+  const float* wscale = nullptr;
+  if (prec_f16(precision)) {   // fp16 operands: W_out is split after a power-of-two scale that brings max|W| to ~1
+    joint_gscale_kernel<<<1, 1024, 0, s>>>(w_out, (int64_t)Vp * H, 1.f, jw.gscale + 2);
+    CLASR_CHECK_LAUNCH("joint_wscale");
+    wscale = jw.gscale + 2;
+  }
+  if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s, prec_f16(precision), wscale)))
+    return rc;
   joint_tile_offsets_kernel<<<1, 256, 0, s>>>(act_lens, label_lens, B, jw.tile_offsets, jw.tile_offsets + B + 1,
                                               b_out, Vp, jw.bias_pad);
   CLASR_CHECK_LAUNCH("joint_tile_offsets");
@@ -1448,6 +1461,7 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   p.tile_offsets = jw.tile_offsets;
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.f16 = prec_f16(precision) ? 1 : 0;
+  p.wscale = p.f16 ? jw.gscale + 2 : nullptr;   // written by the forward call
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.sumsq = sumsq;
   if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;
@@ -1529,6 +1543,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   p.tile_offsets = jw.tile_offsets;
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.f16 = prec_f16(precision) ? 1 : 0;
+  p.wscale = p.f16 ? jw.gscale + 2 : nullptr;   // written by the forward call
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.grad_out = grad_out; p.grad_cells = grad_cells; p.fastemit_lambda = fastemit_lambda; p.clamp = clamp;
   if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;
@@ -1618,7 +1633,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
     joint_dfg_fused_kernel<ACT><<<grid, 256, smem, s>>>(sc.dhid, ef_, eg_, act_lens, label_lens, jw.tile_offsets,  \
                                                         T, U1, H, d_f, d_g, blank_split ? sc.dzb : nullptr,        \
                                                         d_w_out + (size_t)blank * H, w_out + (size_t)blank * H,    \
-                                                        p.gscale, p.drop_thresh, p.drop_seed_a,                    \
+                                                        p.gscale, p.wscale, p.drop_thresh, p.drop_seed_a,          \
                                                         p.drop_seed_b, p.drop_scale);                              \
   } while (0)
       if (activation == CLASR_ACT_RELU) CLASR_LAUNCH_DFG(CLASR_ACT_RELU);
@@ -1628,7 +1643,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
       CLASR_CHECK_LAUNCH("joint_dfg_fused");
     } else {  // very long label sequences: the two-pass kernel (reads dHid twice, no shared-memory partials)
       CLASR_CHECK_ARG(p.drop_thresh == 0, "joint_rnnt_bwd: in-kernel dropout needs U+1 <= 800 (single-pass d_f/d_g kernel)");
-      CLASR_CHECK_ARG(!p.gscale, "joint_rnnt_bwd: fp16x3 needs U+1 <= 800 (single-pass d_f/d_g kernel)");
+      CLASR_CHECK_ARG(!p.f16, "joint_rnnt_bwd: fp16x3 needs U+1 <= 800 (single-pass d_f/d_g kernel)");
       joint_dfg_kernel<<<dim3(T, B), 160, 0, s>>>(sc.dhid, f, g, act_lens, label_lens, jw.tile_offsets, T, U1, H,
                                                  activation, 0, d_f);
       CLASR_CHECK_LAUNCH("joint_df");

@@ -137,3 +137,21 @@ def test_fp16x3_gradient_scale_invariance(scale, stash, monkeypatch):
     for name, got, ref in zip(["d_f", "d_g", "d_W", "d_b"], (fd, gd, Wd, bd), (f64, g64, W64, b64)):
         assert torch.isfinite(got.grad).all(), name
         assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy()) <= 2e-5, (name, scale)
+
+
+@pytest.mark.parametrize("w_mult", [1e-4, 30.0])
+def test_fp16x3_weight_scale_invariance(w_mult):
+    """W_out is split into fp16 halves after a power-of-two scale that brings max|W| to ~1 (tiny weights would sit in
+    fp16's subnormal range otherwise); logits and gradients are un-scaled where they are consumed."""
+    B, T, U, V, H = 2, 21, 9, 300, 128
+    f, g, W, b, lab, al, ll = make(B, T, U, V, H, seed=43)
+    W = W * w_mult
+    fd, gd, Wd, bd = [x.to(DEV).requires_grad_(True) for x in (f, g, W, b)]
+    costs = fused_joint_rnnt_loss(fd, gd, Wd, bd, lab.to(DEV), al.to(DEV), ll.to(DEV), V, "tanh", "fp16x3")
+    costs.sum().backward()
+    torch.cuda.synchronize()
+    oc, _, leaves = oracle(f, g, W, b, lab, al, ll, V, "tanh")
+    oc.sum().backward()
+    assert rel_err(costs.detach().cpu().numpy(), oc.detach().numpy()) <= 1e-5
+    for name, got, ref in zip(["d_f", "d_g", "d_W", "d_b"], (fd, gd, Wd, bd), leaves):
+        assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy()) <= 2e-5, (name, w_mult)
