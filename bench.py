@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="tcgen05", choices=["tcgen05", "materialised"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp16x3", "bf16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "fp16x3", "bf16"],
+                    help="auto = the module default: fp16x3 for tanh / sigmoid joints, bf16x3 for relu")
     ap.add_argument("--activation", default="tanh", choices=["tanh", "relu", "sigmoid"])
     ap.add_argument("--ragged", type=int, default=0)
     ap.add_argument("--dropout", type=float, default=0.0, help="joint dropout (the shipped checkpoint trains with 0.2)")
@@ -242,6 +243,7 @@ def main_b200(args):
                                     activation=args.activation, dropout=args.dropout),
                       num_classes=c["V"], fuse_loss_wer=True, fused_batch_size=4, fused_impl=args.mode,
                       precision=args.precision).to(dev)
+    args.precision = joint.precision   # 'auto' resolved by the module
     joint.set_loss(RNNTLoss(num_classes=c["V"]))
     joint.set_wer(object())
     head = ConvASRDecoder(feat_in=c["D_enc"], num_classes=c["V"]).to(dev)
