@@ -222,10 +222,14 @@ __global__ void joint_tile_offsets_kernel(const int64_t* __restrict__ act_lens, 
 #define CLASR_SCALE_HEADROOM 1.f
 #endif
 constexpr float kScaleHeadroom = CLASR_SCALE_HEADROOM;
-__global__ void joint_gscale_kernel(const float* __restrict__ g, int64_t n, float headroom, float* __restrict__ out) {
+// scratch[0] = running maximum (bit pattern of a non-negative float: ordered like an unsigned), scratch[1] = blocks done;
+// both zeroed by the launcher.  The last block to finish converts the maximum into the scale.
+__global__ void joint_gscale_kernel(const float* __restrict__ g, int64_t n, float headroom, float* __restrict__ out,
+                                    unsigned int* __restrict__ scratch) {
   __shared__ float red[32];
   float m = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(g[i]));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(g[i]));
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -233,15 +237,34 @@ __global__ void joint_gscale_kernel(const float* __restrict__ g, int64_t n, floa
     m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     m = warp_max(m);
     if (threadIdx.x == 0) {
-      int e = 0;
-      if (m > 0.f && isfinite(m)) {
-        frexpf(m * headroom, &e);                 // m * headroom = f * 2^e, f in [0.5, 1)
-        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+      if (isfinite(m)) atomicMax(scratch, __float_as_uint(m));
+      __threadfence();
+      if (atomicAdd(scratch + 1, 1u) == gridDim.x - 1) {
+        m = __uint_as_float(atomicMax(scratch, 0u));
+        int e = 0;
+        if (m > 0.f) {
+          frexpf(m * headroom, &e);                 // m * headroom = f * 2^e, f in [0.5, 1)
+          e = e > 100 ? 100 : (e < -100 ? -100 : e);
+        }
+        out[0] = ldexpf(1.f, -e);
+        out[1] = ldexpf(1.f, e);
       }
-      out[0] = ldexpf(1.f, -e);
-      out[1] = ldexpf(1.f, e);
     }
   }
+}
+
+static int launch_joint_gscale(const float* g, int64_t n, float headroom, float* out, cudaStream_t s) {
+  unsigned int* scratch = reinterpret_cast<unsigned int*>(out) + 8;   // same 256-byte workspace slot
+  if (cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned int), s) != cudaSuccess) {
+    set_error("joint_gscale: memset failed");
+    return CLASR_STATUS_CUDA_ERROR;
+  }
+  int64_t blocks = (n + 4095) / 4096;
+  if (blocks > kNumSMs) blocks = kNumSMs;
+  if (blocks < 1) blocks = 1;
+  joint_gscale_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, n, headroom, out, scratch);
+  CLASR_CHECK_LAUNCH("joint_gscale");
+  return CLASR_STATUS_SUCCESS;
 }
 
 __device__ __forceinline__ int find_utterance(const int* __restrict__ offs, int B, int tile) {
@@ -1452,8 +1475,7 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   // W_out [Vp,H] fp32 -> bf16 hi[,lo] (rows beyond Vp are never read: TMA zero-fills out-of-bounds rows)
   const float* wscale = nullptr;
   if (prec_f16(precision)) {   // fp16 operands: W_out is split after a power-of-two scale that brings max|W| to ~1
-    joint_gscale_kernel<<<1, 1024, 0, s>>>(w_out, (int64_t)Vp * H, kScaleHeadroom, jw.gscale + 2);
-    CLASR_CHECK_LAUNCH("joint_wscale");
+    if ((rc = launch_joint_gscale(w_out, (int64_t)Vp * H, kScaleHeadroom, jw.gscale + 2, s))) return rc;
     wscale = jw.gscale + 2;
   }
   if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s, prec_f16(precision), wscale)))
@@ -1563,9 +1585,9 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   p.dzb = blank_split ? sc.dzb : nullptr;
   p.db_acc = d_b_out;
   if (p.f16 && (mode == 2 || grad_out)) {   // fp16 operands: pre-scale dZ to O(1) (see joint_gscale_kernel)
-    if (mode == 1) joint_gscale_kernel<<<1, 256, 0, s>>>(grad_out, B, (1.f + fastemit_lambda) * kScaleHeadroom, jw.gscale);
-    else joint_gscale_kernel<<<1, 1024, 0, s>>>(grad_cells, (int64_t)B * T * U1, 128.f, jw.gscale);
-    CLASR_CHECK_LAUNCH("joint_gscale");
+    rc = mode == 1 ? launch_joint_gscale(grad_out, B, (1.f + fastemit_lambda) * kScaleHeadroom, jw.gscale, s)
+                   : launch_joint_gscale(grad_cells, (int64_t)B * T * U1, 128.f, jw.gscale, s);
+    if (rc) return rc;
     p.gscale = jw.gscale;
   }
   {  // d_b accumulates in the pass-2a epilogue, d_W in the split-K GEMM: both start from zero
