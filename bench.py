@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="tcgen05", choices=["tcgen05", "materialised"])
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16x3", "fp16x3", "bf16"],
-                    help="auto = the module default: fp16x3 for tanh / sigmoid joints, bf16x3 for relu")
+                    help="auto = the module default (fp16x3)")
     ap.add_argument("--activation", default="tanh", choices=["tanh", "relu", "sigmoid"])
     ap.add_argument("--ragged", type=int, default=0)
     ap.add_argument("--dropout", type=float, default=0.0, help="joint dropout (the shipped checkpoint trains with 0.2)")

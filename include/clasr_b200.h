@@ -46,9 +46,9 @@ extern "C" {
 #define CLASR_PREC_BF16 0   /* single bf16 pass (config 5, "bf16 joint GEMM") */
 #define CLASR_PREC_BF16X3 1 /* hi/lo bf16 split, 3 MMAs per product: fp32-grade accuracy (config 2, "fp32") */
 #define CLASR_PREC_FP16X3 2 /* the same split in fp16 (2^-22 operands instead of 2^-17, less tensor energy).  The fused
-                             joint brings W_out and dZ to O(1) with exact power-of-two scales it undoes itself; the
-                             hidden activations must be bounded (tanh / sigmoid).  Plain GEMM / linear entries apply
-                             no scaling: their operands must fit fp16's range. */
+                             joint brings W_out, ReLU hidden values and dZ to O(1) with exact power-of-two scales it
+                             undoes itself.  Plain GEMM / linear entries apply no scaling: their operands must fit
+                             fp16's range. */
 
 CLASR_API int clasr_version(void);
 CLASR_API const char* clasr_last_error(void);

@@ -127,6 +127,7 @@ struct GemmParams {
   int b_keep;        // pair kernel: B is small and re-read by every row block -> TMA loads carry L2 evict_last
   int f16;           // operands are fp16 instead of bf16 (CLASR_PREC_FP16X3)
   const float* alpha_dev;  // optional device scalar: the atomic epilogue adds alpha * acc (undoes an operand pre-scale)
+  const float* alpha_dev2; // optional second factor of alpha
 };
 
 template <int kTerms>
@@ -274,7 +275,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int row = m0 + q * 32 + lane;
       float* crow = p.C + (int64_t)row * p.ldc;
       const bool vec_ok = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
-      const float alpha = (p.atomic_add && p.alpha_dev) ? __ldg(p.alpha_dev) : 1.f;
+      const float alpha = p.atomic_add ? (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f) * (p.alpha_dev2 ? __ldg(p.alpha_dev2) : 1.f) : 1.f;
       const bool vec32_ok = ((p.ldc & 7) == 0) && ((((uintptr_t)p.C) & 31) == 0);
 #pragma unroll 1
       for (int c = 0; c < kBN / 32; ++c) {
@@ -516,7 +517,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int row = m0 + q * 32 + lane;
       float* crow = p.C + (int64_t)row * p.ldc;
       const bool vec_ok = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
-      const float alpha = (p.atomic_add && p.alpha_dev) ? __ldg(p.alpha_dev) : 1.f;
+      const float alpha = p.atomic_add ? (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f) * (p.alpha_dev2 ? __ldg(p.alpha_dev2) : 1.f) : 1.f;
       const bool vec32_ok = ((p.ldc & 7) == 0) && ((((uintptr_t)p.C) & 31) == 0);
 #pragma unroll 1
       for (int c = 0; c < nw / 32; ++c) {
@@ -572,7 +573,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
                    int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
                    int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias,
-                   const float* alpha_dev) {
+                   const float* alpha_dev, const float* alpha_dev2) {
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   const bool x3 = prec_x3(precision);
@@ -621,7 +622,7 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
   GemmParams p{M, N, K, C, ldc, atomic_add, k_splits, a_mn, b_mn, m_dev, k_dev, atomic_add ? nullptr : bias,
                ge ? atoi(ge) : 0,
                /*b_keep*/ ((size_t)N * K * 2 * (x3 ? 2 : 1) <= ((size_t)16 << 20) && (int64_t)M >= 8 * (int64_t)N) ? 1 : 0,
-               prec_f16(precision) ? 1 : 0, alpha_dev};
+               prec_f16(precision) ? 1 : 0, alpha_dev, alpha_dev2};
   if (use_pair) {
     const int tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN) * k_splits;
     int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
@@ -690,7 +691,7 @@ extern "C" int clasr_gemm_ex(const float* A, const float* B, float* C, int M, in
     CLASR_CHECK_ARG(e == cudaSuccess, "gemm: memset failed");
   }
   return launch_gemm_tc(a_hi, a_lo, pad8(a_cols), a_trans, b_hi, b_lo, pad8(b_cols), b_trans, M, N, K, C, N, precision,
-                        k_splits > 1, k_splits, s, nullptr, nullptr, nullptr, nullptr);
+                        k_splits > 1, k_splits, s, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 extern "C" int clasr_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int precision,
@@ -766,7 +767,7 @@ extern "C" int clasr_linear_fwd(const float* x, const float* w, const float* bia
   if ((rc = launch_split_bf16(w, N, K, K, ws.w_hi, ws.w_lo, pad8(K), s, prec_f16(precision), nullptr))) return rc;
   prof_begin("linear_fwd", s);
   rc = launch_gemm_tc(ws.x_hi, ws.x_lo, pad8(K), 0, ws.w_hi, ws.w_lo, pad8(K), 0, M, N, K, y, N, precision, 0, 1, s,
-                      nullptr, nullptr, bias, nullptr);
+                      nullptr, nullptr, bias, nullptr, nullptr);
   prof_end("linear_fwd", s);
   return rc;
 }
@@ -787,7 +788,7 @@ extern "C" int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db
   prof_begin("linear_bwd", s);
   if (dx) {  // A = dy [M, N] K-major (K_gemm = N); B = W given as [K_gemm = N rows, N_gemm = K cols] (MN-major)
     if ((rc = launch_gemm_tc(ws.dy_hi, ws.dy_lo, pad8(N), 0, ws.w_hi, ws.w_lo, pad8(K), 1, M, K, N, dx, K, precision, 0, 1,
-                             s, nullptr, nullptr, nullptr, nullptr)))
+                             s, nullptr, nullptr, nullptr, nullptr, nullptr)))
       return rc;
   }
   if (dw) {  // A = dy given as [K_gemm = M rows, M_gemm = N cols]; B = x given as [K_gemm = M rows, N_gemm = K cols]
@@ -801,7 +802,7 @@ extern "C" int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db
       CLASR_CHECK_ARG(e == cudaSuccess, "linear_bwd: memset failed");
     }
     if ((rc = launch_gemm_tc(ws.dy_hi, ws.dy_lo, pad8(N), 1, ws.x_hi, ws.x_lo, pad8(K), 1, N, K, M, dw, K, precision,
-                             splits > 1, splits, s, nullptr, nullptr, nullptr, nullptr)))
+                             splits > 1, splits, s, nullptr, nullptr, nullptr, nullptr, nullptr)))
       return rc;
   }
   if (db) {

@@ -89,7 +89,9 @@ struct JointFwdParams {
   // ---- kMode 3 (forward that keeps the logits for the backward): z = logits + bias, fp32, compact tile-row order
   int f16;                    // 16-bit operands are fp16 instead of bf16 (CLASR_PREC_FP16X3)
   const float* gscale;        // fp16 only: [2] = {S, 1/S}, the power-of-two pre-scale of dZ (joint_gscale_kernel), or null
-  const float* wscale;        // fp16 only: [2] = {Sw, 1/Sw}, the pre-scale of W_out (max|W| Sw ~ 1); logits = acc / Sw + b
+  const float* wscale;        // fp16 only: {Sw, 1/Sw, Sa, 1/Sa, 1/(Sw Sa)}: pre-scales of W_out (max|W| Sw ~ 1) and of the
+                              // hidden activations (ReLU only, else 1); logits = acc / (Sw Sa) + b
+  const float* ascale;        // fp16 + ReLU: &Sa for the A producers, else null
   float* zbuf;                // [rows_pad, ldzf]
   int ldzf;                   // round_up(Vp, 32): whole 32-column epilogue pieces
 };
@@ -265,6 +267,15 @@ static int launch_joint_gscale(const float* g, int64_t n, float headroom, float*
   joint_gscale_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, n, headroom, out, scratch);
   CLASR_CHECK_LAUNCH("joint_gscale");
   return CLASR_STATUS_SUCCESS;
+}
+
+// fp16 operands: gs[2..3] = {Sw, 1/Sw} (written before); ReLU: gs[16..17], gs[18..19] = scales of max|f|, max|g| ->
+// hidden values relu(f + g) <= max|f| + max|g| <= 2 max(1/Sf, 1/Sg): Sa = min(Sf, Sg) / 2.  Writes gs[4..6].
+__global__ void joint_ascale_kernel(float* __restrict__ gs, int relu) {
+  const float sa = relu ? 0.5f * fminf(gs[16], gs[18]) : 1.f;
+  gs[4] = sa;
+  gs[5] = 1.f / sa;          // exact: power of two
+  gs[6] = gs[3] * gs[5];
 }
 
 __device__ __forceinline__ int find_utterance(const int* __restrict__ offs, int B, int tile) {
@@ -502,7 +513,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     const int egrp = (warp - 4) >> 2;   // kWide: this warpgroup serves accumulator buffer `egrp` only
     const uint64_t pol_stream = tc::l2_policy_evict_first();
     (void)pol_stream;
-    const float inv_w = p.wscale ? __ldg(p.wscale + 1) : 1.f;   // 1.0: fmaf(acc, 1, b) == acc + b exactly
+    const float inv_w = p.wscale ? __ldg(p.wscale + 4) : 1.f;   // 1 / (Sw Sa); 1.0: fmaf(acc, 1, b) == acc + b exactly
     const int row = q * 32 + lane;
     int acc_it = 0;
     for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
@@ -779,6 +790,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       }
       __syncwarp();
       float2 fa[kBatch], ga[kBatch], fb[kBatch], gb[kBatch];
+      const float s_a = (kAct == CLASR_ACT_RELU && p.ascale) ? __ldg(p.ascale) : 1.f;
       const float* __restrict__ ef_lane = p.ef + half * 32 + 2 * c;   // this lane's two features of a row
       const float* __restrict__ eg_lane = p.eg + half * 32 + 2 * c;
       auto load_batch = [&](int kb, int batch, float2 (&fo)[kBatch], float2 (&go_)[kBatch]) {
@@ -803,6 +815,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           const int i = batch * kBatch + j;
           float h0 = joint_combine<kAct>(fi[j].x, gi[j].x);
           float h1 = joint_combine<kAct>(fi[j].y, gi[j].y);
+          if (kAct == CLASR_ACT_RELU) {  // fp16 operands: unbounded ReLU values are brought to <= 1 (s_a = 1 otherwise)
+            h0 *= s_a;
+            h1 *= s_a;
+          }
           if (p.drop_thresh) {  // warp-uniform
             const uint32_t crow = (uint32_t)tile * kJM + q * 32 + ((i & 3) + 8 * (i >> 2)) + 4 * hs;
             const uint32_t x = drop_hash(crow * (uint32_t)(p.H >> 1) + (uint32_t)((kb * kJK + half * 32) >> 1) + c,
@@ -1249,7 +1265,7 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
 int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
                    int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
                    int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias = nullptr,
-                   const float* alpha_dev = nullptr);
+                   const float* alpha_dev = nullptr, const float* alpha_dev2 = nullptr);
 
 // ------------------------------------------------------------------------------------------------
 // workspace layout of the fused path
@@ -1476,6 +1492,13 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   const float* wscale = nullptr;
   if (prec_f16(precision)) {   // fp16 operands: W_out is split after a power-of-two scale that brings max|W| to ~1
     if ((rc = launch_joint_gscale(w_out, (int64_t)Vp * H, kScaleHeadroom, jw.gscale + 2, s))) return rc;
+    const int relu = activation == CLASR_ACT_RELU;
+    if (relu) {
+      if ((rc = launch_joint_gscale(f, (int64_t)B * T * H, 1.f, jw.gscale + 16, s))) return rc;
+      if ((rc = launch_joint_gscale(g, (int64_t)B * U1 * H, 1.f, jw.gscale + 18, s))) return rc;
+    }
+    joint_ascale_kernel<<<1, 1, 0, s>>>(jw.gscale, relu);
+    CLASR_CHECK_LAUNCH("joint_ascale");
     wscale = jw.gscale + 2;
   }
   if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s, prec_f16(precision), wscale)))
@@ -1491,6 +1514,7 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.f16 = prec_f16(precision) ? 1 : 0;
   p.wscale = p.f16 ? jw.gscale + 2 : nullptr;   // written by the forward call
+  p.ascale = (p.f16 && activation == CLASR_ACT_RELU) ? jw.gscale + 4 : nullptr;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.sumsq = sumsq;
   if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;
@@ -1573,6 +1597,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.f16 = prec_f16(precision) ? 1 : 0;
   p.wscale = p.f16 ? jw.gscale + 2 : nullptr;   // written by the forward call
+  p.ascale = (p.f16 && activation == CLASR_ACT_RELU) ? jw.gscale + 4 : nullptr;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.grad_out = grad_out; p.grad_cells = grad_cells; p.fastemit_lambda = fastemit_lambda; p.clamp = clamp;
   if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;
@@ -1643,7 +1668,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   prof_begin("gemm_dw", s);
   if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, hid_hi, hid_lo, sc.ldh, 1, blank_split ? Vp - 1 : Vp, H,
                            (int)sc.rows_cap, d_w_out, H, precision, 1, /*auto split-K*/ 0, s, nullptr, rows_pad_dev,
-                           nullptr, p.gscale ? p.gscale + 1 : nullptr)))
+                           nullptr, p.gscale ? p.gscale + 1 : nullptr, p.ascale ? p.ascale + 1 : nullptr)))
     return rc;
   prof_end("gemm_dw", s);
   // ---- pass 2d: through the activation and the broadcast add: d_f = sum_u, d_g = sum_t of dHid * act'(f+g)

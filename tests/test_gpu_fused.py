@@ -155,3 +155,23 @@ def test_fp16x3_weight_scale_invariance(w_mult):
     assert rel_err(costs.detach().cpu().numpy(), oc.detach().numpy()) <= 1e-5
     for name, got, ref in zip(["d_f", "d_g", "d_W", "d_b"], (fd, gd, Wd, bd), leaves):
         assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy()) <= 2e-5, (name, w_mult)
+
+
+@pytest.mark.parametrize("mult", [1e-3, 300.0])
+def test_fp16x3_relu_hidden_scale(mult):
+    """ReLU hidden values are unbounded: with fp16 operands the A producers scale them by a power of two derived from
+    max|f| + max|g|, and the logits / dW are un-scaled where they are consumed."""
+    B, T, U, V, H = 2, 21, 9, 300, 128
+    f, g, W, b, lab, al, ll = make(B, T, U, V, H, seed=47)
+    f, g = f * mult, g * mult
+    W = W / max(mult, 1.0)      # keep the logits O(1) so that the softmax stays informative
+    fd, gd, Wd, bd = [x.to(DEV).requires_grad_(True) for x in (f, g, W, b)]
+    costs = fused_joint_rnnt_loss(fd, gd, Wd, bd, lab.to(DEV), al.to(DEV), ll.to(DEV), V, "relu", "fp16x3")
+    costs.sum().backward()
+    torch.cuda.synchronize()
+    oc, _, leaves = oracle(f, g, W, b, lab, al, ll, V, "relu")
+    oc.sum().backward()
+    assert rel_err(costs.detach().cpu().numpy(), oc.detach().numpy()) <= 1e-5
+    for name, got, ref in zip(["d_f", "d_g", "d_W", "d_b"], (fd, gd, Wd, bd), leaves):
+        assert torch.isfinite(got.grad).all(), name
+        assert rel_err(got.grad.cpu().numpy(), ref.grad.numpy()) <= 2e-5, (name, mult)
