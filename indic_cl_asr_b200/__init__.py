@@ -10,9 +10,10 @@ include/clasr_b200.h).  There is no CPU path and no fallback: a missing library 
 """
 from . import _lib
 from .losses import CTCLoss, RNNTLoss, RNNTLossNumba, rnnt_loss
-from .modules import ConvASRDecoder, RNNTJoint
-from .hybrid import HybridRNNTCTCLoss
+from .modules import ConvASRDecoder, RNNTDecoder, RNNTJoint
+from .hybrid import EncDecHybridRNNTCTCStep, HybridRNNTCTCLoss
 
-__all__ = ["CTCLoss", "RNNTLoss", "RNNTLossNumba", "rnnt_loss", "ConvASRDecoder", "RNNTJoint", "HybridRNNTCTCLoss",
+__all__ = ["CTCLoss", "RNNTLoss", "RNNTLossNumba", "rnnt_loss", "ConvASRDecoder", "RNNTJoint", "RNNTDecoder", "HybridRNNTCTCLoss",
+           "EncDecHybridRNNTCTCStep",
            "_lib"]
 __version__ = "0.1.0"

@@ -148,8 +148,9 @@ class FlatParams:
         """theta* <- theta (get_params_clone, utils.py:284-293) in one kernel."""
         self.ensure_theta_views()
         out = _alloc(self.layout, self.device, zero=False)
-        st = _lib.lib().clasr_cl_snapshot(out.data_ptr(), self.theta.data_ptr(), self.layout.total,
-                                          _lib.stream_ptr(self.device))
+        with torch.cuda.device(self.device):
+            st = _lib.lib().clasr_cl_snapshot(out.data_ptr(), self.theta.data_ptr(), self.layout.total,
+                                              _lib.stream_ptr(self.device))
         _lib.check(st, "cl_snapshot")
         return FlatDict(self.layout, out)
 

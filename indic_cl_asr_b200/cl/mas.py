@@ -49,10 +49,16 @@ def penalty(model, main_importance, prev_params) -> torch.Tensor:
     return _MasPenaltyFn.apply(fp, omega.flat, star.flat, *fp.params)
 
 
-def penalty_into_grads(model, main_importance, prev_params, mas_lambda: float) -> torch.Tensor:
-    """Fast path: returns the penalty value (device fp64 scalar) and ADDS mas_lambda * d(penalty)/d(theta)
-    straight into the model's flat gradient buffer in the same sweep (what cl_baseline_mas.py:231-240 does
-    through autograd)."""
+def penalty_into_grads(model, main_importance, prev_params, mas_lambda: float, grad_scale: float = 1.0) -> torch.Tensor:
+    """Fast path: returns the penalty value (device fp64 scalar) and ADDS ``grad_scale * mas_lambda *
+    d(penalty)/d(theta)`` straight into the model's flat gradient buffer in the same sweep.
+
+    The reference gets this gradient through autograd (cl_baseline_mas.py:231-240: ``loss += mas_lambda * penalty``
+    then ``backward()``).  Writing into ``.grad`` directly bypasses autograd, so anything that multiplies the loss
+    before ``backward()`` must be passed as ``grad_scale``: under ``config.mixed_precision`` the reference calls
+    ``scaler.scale(loss).backward()``, i.e. every gradient carries the GradScaler's factor until ``unscale_`` —
+    pass ``grad_scale=scaler.get_scale()`` (a host float; that read is the scaler's own sync) or use ``penalty()``,
+    the autograd path, which needs no such care."""
     fp = flat_params(model)
     omega = as_flat(main_importance, fp.layout)
     star = as_flat(prev_params, fp.layout)
@@ -63,8 +69,8 @@ def penalty_into_grads(model, main_importance, prev_params, mas_lambda: float) -
     fp.ensure_theta_views()
     with torch.cuda.device(fp.device):
         _lib.check(_lib.lib().clasr_cl_penalty_value_grad(
-            fp.theta.data_ptr(), star.flat.data_ptr(), omega.flat.data_ptr(), fp.layout.total, float(mas_lambda),
-            value.data_ptr(), fp.grad.data_ptr(), _lib.stream_ptr(fp.device)), "cl_penalty_value_grad")
+            fp.theta.data_ptr(), star.flat.data_ptr(), omega.flat.data_ptr(), fp.layout.total,
+            float(mas_lambda) * float(grad_scale), value.data_ptr(), fp.grad.data_ptr(), _lib.stream_ptr(fp.device)), "cl_penalty_value_grad")
     return value
 
 

@@ -37,10 +37,16 @@ def get_params_clone(model) -> FlatDict:
 
 
 def get_zero_params(model, device=None) -> FlatDict:
-    """utils.py:295-302."""
+    """utils.py:295-302: zeros_like(param.data).to(device) per trainable tensor.  The flat buffer lives on the model's
+    device (where the sweeps run); asking for another device gets a flat copy there, as the reference's ``.to(device)``
+    would, and the hooks re-home it (``as_flat``) when it meets the model again."""
     fd = flat_params(model).zeros()
-    if device is not None and torch.device(device) != fd.flat.device:
-        raise ValueError("get_zero_params: regulariser state lives on the model's device")
+    if device is not None:
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else dev
+        if dev != fd.flat.device:
+            return FlatDict(fd.layout, fd.flat.to(dev))
     return fd
 
 

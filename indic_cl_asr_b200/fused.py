@@ -17,21 +17,29 @@ __all__ = ["fused_joint_rnnt_loss", "fused_joint_forward_stats", "fused_joint_su
            "dropout_mask_reference"]
 
 
-def _stash_limit_bytes() -> int:
-    """CLASR_JOINT_STASH: "0" = never keep the logits (the backward pass recomputes them), a number = the largest
-    stash in GiB that a forward call may allocate (default 48 GiB of the B200's 180)."""
+def _stash_limit_bytes(stash_gib=None) -> int:
+    """Largest logits stash (bytes) a differentiated forward call may allocate.
+
+    Default 0: the logits are NEVER written to HBM and the backward pass recomputes them tile-wise on the tensor cores
+    (BASELINE.json north_star (1)).  ``stash_gib`` > 0 (``RNNTJoint(backward_mode="stash")``) opts into the faster
+    mode that keeps the valid cells' logits and hidden activations between forward and backward (about 15 % less step
+    time at B32/T250/U100/V1024 for 4 (V+1+H) bytes per lattice cell).  The environment variable CLASR_JOINT_STASH
+    (GiB; "0" = recompute) overrides both — it exists for A/B measurements."""
     v = os.environ.get("CLASR_JOINT_STASH", "")
-    gib = 48.0 if v == "" else float(v)
+    gib = float(v) if v != "" else (0.0 if stash_gib is None else float(stash_gib))
     return int(gib * (1 << 30))
 
 
-def _stash(f, B, T, U1, H, Vp, prec, needs_grad):
+def _stash(f, B, T, U1, H, Vp, prec, needs_grad, stash_gib=None):
     """(tensor | None, nbytes): the logits / hidden-activation stash a differentiated forward call leaves for its
     backward call (include/clasr_b200.h: clasr_joint_stash_bytes)."""
     if not needs_grad:
         return None, 0
+    limit = _stash_limit_bytes(stash_gib)
+    if limit <= 0:
+        return None, 0
     nbytes = _lib.lib().clasr_joint_stash_bytes(B, T, U1, H, Vp, prec)
-    if nbytes == 0 or nbytes > _stash_limit_bytes():
+    if nbytes == 0 or nbytes > limit:
         return None, 0
     return torch.empty(nbytes, dtype=torch.uint8, device=f.device), nbytes
 
@@ -45,7 +53,7 @@ def _ws(f, B, T, U1, H, Vp, prec):
 class _FusedJointRNNT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision, fastemit_lambda,
-                clamp, want_sumsq, dropout_p=0.0, dropout_seed=0):
+                clamp, want_sumsq, dropout_p=0.0, dropout_seed=0, stash_gib=None):
         _lib.require_cuda(f, "f")
         if clamp < 0:
             raise ValueError("`clamp` must be 0.0 or positive float value.")
@@ -68,7 +76,7 @@ class _FusedJointRNNT(torch.autograd.Function):
             labels = labels[:, : U1 - 1].contiguous()
         prec = _lib.PREC[precision]
         ws, nbytes = _ws(f, B, T, U1, H, Vp, prec)
-        stash, stash_bytes = _stash(f, B, T, U1, H, Vp, prec, needs_grad)
+        stash, stash_bytes = _stash(f, B, T, U1, H, Vp, prec, needs_grad, stash_gib)
         costs = torch.empty(B, dtype=torch.float32, device=f.device)
         sumsq = torch.zeros(B, T, U1, dtype=torch.float32, device=f.device) if want_sumsq else None
         L = _lib.lib()
@@ -113,15 +121,17 @@ class _FusedJointRNNT(torch.autograd.Function):
                 _lib.stream_ptr(f.device))
         ctx.stash = (None, 0)   # the logits are dead once dZ exists
         _lib.check(st, "joint_rnnt_bwd")
-        return (d_f, d_g, d_w, d_b) + (None,) * 11
+        return (d_f, d_g, d_w, d_b) + (None,) * 12
 
 
 def fused_joint_rnnt_loss(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh",
-                          precision="bf16x3", fastemit_lambda=0.0, clamp=0.0, dropout_p=0.0, dropout_seed=0):
+                          precision="fp16x3", fastemit_lambda=0.0, clamp=0.0, dropout_p=0.0, dropout_seed=0,
+                          stash_gib=None):
     """Per-sample transducer costs [B].  ``dropout_p`` > 0 applies the joint's Dropout between the activation and the
-    output layer inside the kernels (mask keyed by ``dropout_seed``; see ``dropout_mask_reference``)."""
+    output layer inside the kernels (mask keyed by ``dropout_seed``; see ``dropout_mask_reference``).  ``stash_gib``:
+    see ``_stash_limit_bytes`` (default: the logits never reach HBM, the backward pass recomputes them)."""
     return _FusedJointRNNT.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision,
-                                 fastemit_lambda, clamp, False, dropout_p, dropout_seed)
+                                 fastemit_lambda, clamp, False, dropout_p, dropout_seed, stash_gib)
 
 
 def dropout_mask_reference(act_lens, label_lens, T, U1, H, dropout_p, dropout_seed):
@@ -156,7 +166,7 @@ def dropout_mask_reference(act_lens, label_lens, T, U1, H, dropout_p, dropout_se
 
 
 def fused_joint_forward_stats(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh",
-                              precision="bf16x3"):
+                              precision="fp16x3"):
     """(costs [B], sum_v z^2 [B,T,U+1]) — the second is what MAS needs from the joint logits."""
     return _FusedJointRNNT.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision, 0.0,
                                  0.0, True, 0.0, 0)
@@ -168,7 +178,7 @@ class _FusedJointSumsq(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision, dropout_p=0.0,
-                dropout_seed=0):
+                dropout_seed=0, stash_gib=None):
         _lib.require_cuda(f, "f")
         needs_grad = any(ctx.needs_input_grad[:4])
         f = f.contiguous().float()
@@ -183,7 +193,7 @@ class _FusedJointSumsq(torch.autograd.Function):
         label_lens = label_lens.contiguous().long()
         prec = _lib.PREC[precision]
         ws, nbytes = _ws(f, B, T, U1, H, Vp, prec)
-        stash, stash_bytes = _stash(f, B, T, U1, H, Vp, prec, needs_grad)
+        stash, stash_bytes = _stash(f, B, T, U1, H, Vp, prec, needs_grad, stash_gib)
         costs = torch.empty(B, dtype=torch.float32, device=f.device)  # by-product of the same pass; not used here
         sumsq = torch.zeros(B, T, U1, dtype=torch.float32, device=f.device)
         L = _lib.lib()
@@ -221,14 +231,14 @@ class _FusedJointSumsq(torch.autograd.Function):
                 scratch.data_ptr(), sbytes, _lib.ptr(stash), stash_bytes, _lib.stream_ptr(f.device))
         ctx.stash = (None, 0)
         _lib.check(st, "joint_sumsq_bwd")
-        return (d_f, d_g, d_w, d_b) + (None,) * 8
+        return (d_f, d_g, d_w, d_b) + (None,) * 9
 
 
-def fused_joint_sumsq(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh", precision="bf16x3",
-                      dropout_p=0.0, dropout_seed=0):
+def fused_joint_sumsq(f, g, weight, bias, labels, act_lens, label_lens, blank, activation="tanh", precision="fp16x3",
+                      dropout_p=0.0, dropout_seed=0, stash_gib=None):
     """[B,T,U+1] tensor of sum_v z^2 (zero outside the cells selected by the lengths), with autograd."""
     return _FusedJointSumsq.apply(f, g, weight, bias, labels, act_lens, label_lens, blank, activation, precision,
-                                  dropout_p, dropout_seed)
+                                  dropout_p, dropout_seed, stash_gib)
 
 
 class LazySubLogits:

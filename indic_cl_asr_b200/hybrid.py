@@ -17,7 +17,16 @@ import torch
 
 from . import cl
 
-__all__ = ["HybridRNNTCTCLoss", "ewc_backward", "mas_importance_backward"]
+__all__ = ["HybridRNNTCTCLoss", "EncDecHybridRNNTCTCStep", "ewc_backward", "mas_importance_backward", "silence_side_stream_grad_warning"]
+
+
+def silence_side_stream_grad_warning() -> None:
+    """With ``overlap_ctc`` the CTC head's gradients are accumulated on the side stream; torch (>= 2.9) warns about
+    that once per parameter although the autograd engine synchronises the streams correctly.  The switch is
+    PROCESS-WIDE, so it is the application's call (bench.py makes it), not a side effect of building a module."""
+    warn_off = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+    if warn_off is not None:
+        warn_off(False)
 
 
 class HybridRNNTCTCLoss(torch.nn.Module):
@@ -28,13 +37,8 @@ class HybridRNNTCTCLoss(torch.nn.Module):
         self.ctc_loss = ctc_loss
         self.ctc_loss_weight = float(ctc_loss_weight)   # cfg.aux_ctc.ctc_loss_weight (:233)
         self.overlap_ctc = overlap_ctc
+        self.return_log_probs = False   # also hand the CTC log-probs back in the monitor (training_step's return_probs)
         self._side: Dict[torch.device, torch.cuda.Stream] = {}
-        if overlap_ctc:
-            # parameters shared by both branches (none here) or created earlier accumulate on their own stream;
-            # the engine synchronises correctly, the warning is only about graph capture
-            warn_off = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
-            if warn_off is not None:
-                warn_off(False)
 
     def _side_stream(self, device) -> torch.cuda.Stream:
         if device not in self._side:
@@ -51,8 +55,12 @@ class HybridRNNTCTCLoss(torch.nn.Module):
         cur = torch.cuda.current_stream(encoded.device)
         kw = {} if language_ids is None else {"language_ids": language_ids}
 
+        kept = {}
+
         def ctc_branch():
             log_probs = self.ctc_decoder(encoder_output=encoded, **kw)                                  # :894
+            if self.return_log_probs:
+                kept["log_probs"] = log_probs
             return self.ctc_loss(log_probs=log_probs, targets=transcript, input_lengths=encoded_len,
                                  target_lengths=transcript_len)                                         # :896-898
 
@@ -76,7 +84,104 @@ class HybridRNNTCTCLoss(torch.nn.Module):
         loss = (1 - w) * loss_rnnt + w * loss_ctc                                                       # :902
         monitor = {"train_rnnt_loss": loss_rnnt.detach(), "train_ctc_loss": loss_ctc.detach(),
                    "train_loss": loss.detach(), "training_batch_wer": wer}
+        monitor.update(kept)
         return loss, monitor
+
+
+class EncDecHybridRNNTCTCStep(torch.nn.Module):
+    """``EncDecHybridRNNTCTCModel.training_step(batch, lang_ids, return_probs=False)`` work-alike
+    (reference hybrid_rnnt_ctc_models.py:859-930) over the B200 modules.
+
+    Same attribute contract as the reference model — ``encoder``, ``decoder``, ``joint``, ``ctc_decoder``, ``loss``,
+    ``ctc_loss``, ``wer``, ``ctc_wer``, ``ctc_loss_weight`` (so ``utils.freeze_layer`` and the drivers' hook flags
+    ``model.joint.store_sub_logits`` / ``model.ctc_decoder.return_logits_`` work unchanged) — same call signature, same
+    return value ``(loss, monitor[, log_probs])`` and the same five monitor keys.  What is NOT reproduced is the
+    reference's per-step overhead: six ``gc.collect(); torch.cuda.empty_cache()`` pairs (:862-924) and four separate
+    ``.item()`` host syncs (:899,900,912,920).  With ``monitor_host=True`` (default, the reference's python floats) all
+    monitor scalars cross to the host in ONE copy at the end of the step; with ``monitor_host=False`` they stay 0-d
+    device tensors and the step never synchronises.
+
+    ``encoder`` is any module mapping ``(input_signal=, input_signal_length=) -> (encoded [B,D,T'], encoded_len)`` — the
+    preprocessor + SpecAugment + Conformer stack is upstream of the path this library accelerates.
+    ``wer`` / ``ctc_wer`` (torchmetrics-style ``update / compute / reset``) are called like the reference does
+    (``compute_wer = True``, :875, :903-911) when given; pass ``None`` to keep greedy decoding off the training step.
+    """
+
+    def __init__(self, encoder, decoder, joint, ctc_decoder, loss, ctc_loss, wer=None, ctc_wer=None,
+                 ctc_loss_weight: float = 0.3, overlap_ctc: bool = True, monitor_host: bool = True):
+        super().__init__()
+        self.encoder = encoder
+        self.decoder = decoder
+        self.joint = joint
+        self.ctc_decoder = ctc_decoder
+        self.loss = loss
+        self.ctc_loss = ctc_loss
+        self.wer = wer
+        self.ctc_wer = ctc_wer
+        self.ctc_loss_weight = float(ctc_loss_weight)
+        self.monitor_host = monitor_host
+        # EncDecRNNTModel.__init__ (rnnt_models.py:120-124): the fused joint owns the loss and the WER metric
+        if self.joint.fuse_loss_wer:
+            self.joint.set_loss(self.loss)
+            self.joint.set_wer(self.wer if self.wer is not None else _NoWer())
+        self._step = HybridRNNTCTCLoss(joint, ctc_decoder, ctc_loss, ctc_loss_weight=ctc_loss_weight,
+                                       overlap_ctc=overlap_ctc)
+
+    def forward(self, input_signal=None, input_signal_length=None):
+        """Encoder-only forward, as EncDecRNNTModel.forward (rnnt_models.py:606-655)."""
+        return self.encoder(input_signal=input_signal, input_signal_length=input_signal_length)
+
+    def training_step(self, batch, lang_ids, return_probs: bool = False):
+        signal, signal_len, transcript, transcript_len = batch
+        language_ids = lang_ids
+        encoded, encoded_len = self.forward(input_signal=signal, input_signal_length=signal_len)          # :866
+        decoder, _, _ = self.decoder(targets=transcript, target_length=transcript_len)                    # :871
+        compute_wer = self.wer is not None                                                                # :875
+        self._step.return_log_probs = return_probs or self.ctc_wer is not None
+        loss_value, mon = self._step(encoded, encoded_len, decoder, transcript, transcript_len,
+                                     language_ids=language_ids, compute_wer=compute_wer)                  # :880-902
+        log_probs = mon.pop("log_probs", None)
+        ctc_wer = None
+        if self.ctc_wer is not None:                                                                      # :903-911
+            kw = {} if language_ids is None else {"lang_ids": language_ids}
+            self.ctc_wer.update(predictions=log_probs.detach(), targets=transcript, targets_lengths=transcript_len,
+                                predictions_lengths=encoded_len, **kw)
+            ctc_wer, _, _ = self.ctc_wer.compute()
+            self.ctc_wer.reset()
+        monitor = {"training_batch_wer": mon["training_batch_wer"], "train_rnnt_loss": mon["train_rnnt_loss"],
+                   "train_ctc_loss": mon["train_ctc_loss"], "training_batch_wer_ctc": ctc_wer,
+                   "train_loss": mon["train_loss"]}
+        if self.monitor_host:
+            monitor = _monitor_to_host(monitor)
+        if return_probs:
+            return loss_value, monitor, log_probs
+        return loss_value, monitor
+
+
+class _NoWer:
+    """Stands in for the WER metric when none is attached (the fused joint insists on one, modules/rnnt.py:1407-1410);
+    only ever reached if a caller passes ``compute_wer=True`` by hand."""
+
+    def update(self, **kw):
+        pass
+
+    def compute(self):
+        return None, None, None
+
+    def reset(self):
+        pass
+
+
+def _monitor_to_host(monitor):
+    """The reference's monitor holds python floats (``.item()`` per key); here: ONE device->host copy for all keys."""
+    keys = [k for k, v in monitor.items() if isinstance(v, torch.Tensor) and v.is_cuda and v.numel() == 1]
+    if keys:
+        vals = torch.stack([monitor[k].detach().reshape(()).to(torch.float32) for k in keys]).tolist()
+        monitor = dict(monitor)
+        for k, v in zip(keys, vals):
+            if k in ("train_rnnt_loss", "train_ctc_loss", "train_loss", "training_batch_wer_ctc"):
+                monitor[k] = v               # floats in the reference (:899,900,912,920)
+    return monitor
 
 
 def ewc_backward(model, loss: torch.Tensor, config, main_fish, checkpoint) -> Optional[torch.Tensor]:

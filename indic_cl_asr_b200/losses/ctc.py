@@ -23,6 +23,9 @@ class _CTCLossB200(torch.autograd.Function):
             raise ValueError("log_probs must be 3D [B, T, D]")
         if log_probs.dtype != torch.float32:
             raise TypeError("log_probs must be torch.float32")
+        # decided BEFORE .contiguous(): inside Function.forward grad mode is off, so the contiguous copy of a narrowed /
+        # transposed input would report requires_grad = False and the beta pass would be skipped
+        need_beta = 1 if ctx.needs_input_grad[0] else 0
         log_probs = log_probs.contiguous()
         targets = targets.contiguous()
         B, T, Vp = log_probs.shape
@@ -35,7 +38,6 @@ class _CTCLossB200(torch.autograd.Function):
         ws_bytes = L.clasr_ctc_workspace_bytes(B, T, maxU)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=log_probs.device)
         nll = torch.empty(B, dtype=torch.float32, device=log_probs.device)
-        need_beta = 1 if log_probs.requires_grad else 0
         with torch.cuda.device(log_probs.device):
             st = L.clasr_ctc_loss_fwd(
                 log_probs.data_ptr(), _lib.ptr(targets) if maxU > 0 else 0, int(targets.stride(0)) if maxU > 0 else 0,

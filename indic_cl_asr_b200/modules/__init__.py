@@ -1,4 +1,5 @@
 from .conv_asr import ConvASRDecoder
 from .rnnt import RNNTJoint
+from .rnnt_decoder import RNNTDecoder
 
-__all__ = ["ConvASRDecoder", "RNNTJoint"]
+__all__ = ["ConvASRDecoder", "RNNTJoint", "RNNTDecoder"]

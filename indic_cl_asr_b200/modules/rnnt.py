@@ -53,6 +53,8 @@ class RNNTJoint(torch.nn.Module):
         offset_token_ids_by_token_id=None,
         fused_impl: str = "tcgen05",
         precision: str = "auto",
+        backward_mode: str = "recompute",
+        stash_gib: float = 48.0,
     ):
         super().__init__()
         self.vocabulary = vocabulary
@@ -103,8 +105,16 @@ class RNNTJoint(torch.nn.Module):
             precision = "fp16x3"
         if precision not in _lib.PREC:
             raise ValueError(f"precision must be 'auto' or one of {sorted(_lib.PREC)}")
+        if backward_mode not in ("recompute", "stash"):
+            raise ValueError("backward_mode must be 'recompute' or 'stash'")
         self.fused_impl = fused_impl
         self.precision = precision
+        # "recompute" (default): the [B,T,U+1,V+1] logits never reach HBM in either direction — the backward pass
+        # recomputes them tile-wise on the tensor cores.  "stash": the forward pass keeps the VALID cells' logits and
+        # hidden activations (compact rows, up to stash_gib GiB) for a cheaper backward pass (~15 % less step time at
+        # the benchmark shape) — an explicit trade of HBM for time that the caller has to ask for.
+        self.backward_mode = backward_mode
+        self.stash_gib = float(stash_gib)
 
     # ------------------------------------------------------------------ construction (:1667-1710)
     def _joint_net_modules(self, num_classes, pred_n_hidden, enc_n_hidden, joint_n_hidden, activation, dropout):
@@ -264,16 +274,44 @@ class RNNTJoint(torch.nn.Module):
             and self._tcgen05_supported(language_ids)
         )
         if use_tcgen05:
-            losses = self._forward_fused_tcgen05(encoder_outputs, decoder_outputs, encoder_lengths, transcripts,
-                                                 transcript_lengths, language_ids)
+            # ONE projection and ONE dropout draw per forward call, shared by the loss pass and (MAS importance pass)
+            # the stored-logits pass — the reference stores the logits of the same joint call (:1480-1496, 1649-1650)
+            f = self.project_encoder(encoder_outputs)   # [B,T,H]  (tcgen05 GEMM)
+            g = self.project_prednet(decoder_outputs)   # [B,U1,H]
+            drop = self._dropout_args()
+            losses = self._forward_fused_tcgen05(f, g, drop, encoder_lengths, transcripts, transcript_lengths,
+                                                 language_ids)
             if self.store_sub_logits:
-                self.store_list = self._lazy_store_list(encoder_outputs, decoder_outputs, encoder_lengths,
-                                                        transcripts, transcript_lengths, language_ids)
+                self.store_list = self._lazy_store_list(f, g, drop, encoder_outputs, decoder_outputs,
+                                                        encoder_lengths, transcripts, transcript_lengths,
+                                                        language_ids)
             wer, wer_num, wer_denom = self._wer_pass(encoder_outputs, encoder_lengths, transcripts,
                                                      transcript_lengths, language_ids) if compute_wer else (None,) * 3
             return losses, wer, wer_num, wer_denom
+        if self.fused_impl == "tcgen05" and decoder_outputs is not None:
+            self._warn_fallback(needs_tensors, language_ids)
         return self._forward_fused_materialised(encoder_outputs, decoder_outputs, encoder_lengths, transcripts,
                                                 transcript_lengths, compute_wer, language_ids)
+
+    def _warn_fallback(self, needs_tensors, language_ids):
+        """Say (once per reason) why a tcgen05 joint is running the materialised sub-batch strategy: that path holds
+        the [b,T,U+1,V+1] logits in HBM and multiplies through cuBLAS — correct, but not the kernel this module is for."""
+        if needs_tensors:
+            why = "store_sub_enc / store_sub_logits with detach_sub_enc=True hand logits tensors back to the caller"
+        elif self.temperature != 1.0 or self.log_softmax:
+            why = "log_softmax=True / temperature != 1 are not implemented in the fused epilogue"
+        elif self.joint_hidden % 64 != 0 or self.joint_hidden > 640:
+            why = f"joint_hidden={self.joint_hidden} is not a multiple of 64 in [64, 640]"
+        elif isinstance(self.joint_net[-1], torch.nn.ModuleDict):
+            why = "the batch mixes languages (or language_ids is None) on a multilingual joint"
+        else:
+            why = "dropout >= 1"
+        seen = self.__dict__.setdefault("_fallback_warned", set())
+        if why not in seen:
+            seen.add(why)
+            import warnings
+            warnings.warn(f"RNNTJoint(fused_impl='tcgen05') falls back to the materialised strategy: {why}",
+                          RuntimeWarning, stacklevel=3)
 
     # -- the reference's structure: sub-batch loop over materialised logits ------------------------
     def _sub_batches(self, batch_size):
@@ -361,7 +399,7 @@ class RNNTJoint(torch.nn.Module):
             return self._dropout_p, int(torch.randint(0, 2 ** 62, (1,)).item())
         return 0.0, 0
 
-    def _lazy_store_list(self, enc, dec, enc_lens, transcripts, transcript_lens, language_ids):
+    def _lazy_store_list(self, f, g, drop, enc, dec, enc_lens, transcripts, transcript_lens, language_ids):
         """``store_list`` for ``store_sub_logits`` on the fused path (reference modules/rnnt.py:1480-1496, 1649-1650).
 
         One extra fused forward over the PADDED sub-batch boxes (every utterance of a sub-batch takes the sub-batch's
@@ -378,11 +416,10 @@ class RNNTJoint(torch.nn.Module):
             mt, mu = int(enc_lens[begin:end].max()), int(transcript_lens[begin:end].max())
             box_t[begin:end], box_u[begin:end] = mt, mu
             boxes.append((begin, end, mt, mu))
-        f, g = self.project_encoder(enc), self.project_prednet(dec)
-        p_drop, seed = self._dropout_args()
+        p_drop, seed = drop
         sumsq = fused_joint_sumsq(f, g, lin.weight, lin.bias, transcripts, box_t, box_u, blank=self.loss._blank,
                                   activation=self.activation, precision=self.precision, dropout_p=p_drop,
-                                  dropout_seed=seed)
+                                  dropout_seed=seed, stash_gib=self.stash_gib if self.backward_mode == "stash" else None)
         vp = int(lin.weight.shape[0])
         out = []
         for begin, end, mt, mu in boxes:
@@ -396,17 +433,16 @@ class RNNTJoint(torch.nn.Module):
             out.append(LazySubLogits(sumsq[begin:end, :mt, : mu + 1], vp, mat))
         return out
 
-    def _forward_fused_tcgen05(self, enc, dec, enc_lens, transcripts, transcript_lens, language_ids):
+    def _forward_fused_tcgen05(self, f, g, drop, enc_lens, transcripts, transcript_lens, language_ids):
         from ..fused import fused_joint_rnnt_loss
 
         lin = self._final_linear(language_ids)
-        f = self.project_encoder(enc)   # [B,T,H]  (tcgen05 GEMM)
-        g = self.project_prednet(dec)   # [B,U1,H]
         loss_mod = self.loss
-        p_drop, seed = self._dropout_args()
+        p_drop, seed = drop
         per_sample = fused_joint_rnnt_loss(
             f, g, lin.weight, lin.bias, transcripts, enc_lens, transcript_lens,
             blank=loss_mod._blank, activation=self.activation, precision=self.precision,
             fastemit_lambda=float(getattr(loss_mod, "fastemit_lambda", 0.0)),
-            clamp=float(getattr(loss_mod, "clamp", 0.0)), dropout_p=p_drop, dropout_seed=seed)
+            clamp=float(getattr(loss_mod, "clamp", 0.0)), dropout_p=p_drop, dropout_seed=seed,
+            stash_gib=self.stash_gib if self.backward_mode == "stash" else None)
         return loss_mod.reduce(per_sample, transcript_lens.long())

@@ -74,13 +74,19 @@ def gen_rnnt():
     np.savez(os.path.join(OUT, "ref_rnnt.npz"), **out)
 
 
-def _joint_case(activation, seed, B, T, U, De, Dp, H, V, fbs, reduction, ragged=True):
+def _joint_case(activation, seed, B, T, U, De, Dp, H, V, fbs, reduction, ragged=True, loss_kwargs=None,
+                language_keys=None, language_ids=None):
+    """One run of the reference's RNNTJoint (fused branch) + RNNTLoss facade.  ``language_keys``: the multilingual
+    ("multisoftmax") joint, V classes PER LANGUAGE: num_classes = V * n_lang, one Linear(H, V+1) per language
+    (modules/rnnt.py:1694-1703), loss blank = V (hybrid_rnnt_ctc_bpe_models.py:112-116)."""
     J = R.load_joint_class()
     L = R.load_rnnt_loss_facade()
     torch.manual_seed(seed)
+    multi = language_keys is not None
     j = J(jointnet=dict(encoder_hidden=De, pred_hidden=Dp, joint_hidden=H, activation=activation, dropout=0.0),
-          num_classes=V, fuse_loss_wer=True, fused_batch_size=fbs)
-    loss = L(num_classes=V, reduction=reduction)
+          num_classes=V * len(language_keys) if multi else V, fuse_loss_wer=True, fused_batch_size=fbs,
+          multilingual=multi, language_keys=language_keys)
+    loss = L(num_classes=V, reduction=reduction, loss_kwargs=loss_kwargs)
     j.set_loss(loss)
     j.set_wer(object())
     enc = torch.randn(B, De, T, requires_grad=True)
@@ -95,12 +101,12 @@ def _joint_case(activation, seed, B, T, U, De, Dp, H, V, fbs, reduction, ragged=
     tr = torch.randint(0, V, (B, U), generator=g)
     # non-fused logits (fuse flag off -> plain joint), reference forward :1394-1401
     j._fuse_loss_wer = False
-    logits = j(encoder_outputs=enc, decoder_outputs=dec).detach().clone()
+    logits = j(encoder_outputs=enc, decoder_outputs=dec, language_ids=language_ids).detach().clone()
     j._fuse_loss_wer = True
     j.store_sub_logits = True
     j.detach_sub_enc = True
     val, _, _, _ = j(encoder_outputs=enc, decoder_outputs=dec, encoder_lengths=el, transcripts=tr,
-                     transcript_lengths=tl, compute_wer=False)
+                     transcript_lengths=tl, compute_wer=False, language_ids=language_ids)
     sub_shapes = np.asarray([list(s.shape) for s in j.store_list], dtype=np.int64)
     val.backward()
     out = dict(
@@ -109,11 +115,23 @@ def _joint_case(activation, seed, B, T, U, De, Dp, H, V, fbs, reduction, ragged=
         d_enc=enc.grad.numpy(), d_dec=dec.grad.numpy(), sub_shapes=sub_shapes,
         cfg=np.asarray([B, T, U, De, Dp, H, V, fbs], dtype=np.int64),
     )
-    names = {"enc.weight": j.enc.weight, "enc.bias": j.enc.bias, "pred.weight": j.pred.weight,
-             "pred.bias": j.pred.bias, "out.weight": j.joint_net[-1].weight, "out.bias": j.joint_net[-1].bias}
+    names = {"enc.weight": j.enc.weight, "enc.bias": j.enc.bias, "pred.weight": j.pred.weight, "pred.bias": j.pred.bias}
+    if multi:
+        for lang in language_keys:
+            names[f"out.{lang}.weight"] = j.joint_net[-1][lang].weight
+            names[f"out.{lang}.bias"] = j.joint_net[-1][lang].bias
+        out["language_keys"] = np.asarray(language_keys)
+        out["language_ids"] = np.asarray(language_ids)
+    else:
+        names.update({"out.weight": j.joint_net[-1].weight, "out.bias": j.joint_net[-1].bias})
     for k, p in names.items():
         out["p." + k] = p.detach().numpy()
-        out["g." + k] = p.grad.numpy()
+        # a head no utterance of the batch used keeps grad None in the reference (utils.py:308-310 skips it)
+        out["g." + k] = p.grad.numpy() if p.grad is not None else np.zeros_like(p.detach().numpy())
+    fe = (loss_kwargs or {}).get("fastemit_lambda", 0.0)
+    cl = (loss_kwargs or {}).get("clamp", -1.0)
+    out["fastemit_lambda"] = np.float64(fe)
+    out["clamp"] = np.float64(cl)
     return out
 
 
@@ -131,6 +149,40 @@ def gen_joint():
         out[f"{name}__activation"] = np.asarray(kw["activation"])
         out[f"{name}__reduction"] = np.asarray(kw["reduction"])
     np.savez(os.path.join(OUT, "ref_joint.npz"), **out)
+
+
+def gen_joint_fused():
+    """Reference runs whose joint_hidden is a multiple of 64, i.e. shapes the fused tcgen05 kernel accepts: the shipped
+    checkpoint's ReLU, the multilingual per-language head with language_ids (one language per batch = the drivers'
+    case, and a mixed batch = the per-sample loop :1635-1639), FastEmit, and every NeMo-side reduction."""
+    out = {}
+    langs = ["hi", "bn", "ta"]
+    for name, kw in {
+        "relu_h64": dict(activation="relu", seed=51, B=5, T=11, U=6, De=20, Dp=12, H=64, V=29, fbs=2,
+                         reduction="mean_batch"),
+        "relu_h128_fastemit": dict(activation="relu", seed=52, B=4, T=9, U=5, De=16, Dp=24, H=128, V=33, fbs=4,
+                                   reduction="mean_batch", loss_kwargs=dict(fastemit_lambda=0.01)),
+        "tanh_h128_mean_volume": dict(activation="tanh", seed=53, B=6, T=10, U=7, De=12, Dp=12, H=128, V=21, fbs=4,
+                                      reduction="mean_volume"),
+        "sigmoid_h64_mean": dict(activation="sigmoid", seed=54, B=3, T=8, U=4, De=8, Dp=8, H=64, V=12, fbs=2,
+                                 reduction="mean", ragged=False),
+        # no clamp case here: on CPU the reference joint log-softmaxes its output (:1651-1655) and RNNTLossNumba then
+        # clamps the gradient w.r.t. those LOG-PROBS behind a second log_softmax (rnnt_pytorch.py:428-433), which is not
+        # what its CUDA path (clamp on the softmax-fused logits gradient, gpu_rnnt_kernel.py:396) computes; clamp is
+        # pinned at the loss level instead (ref_kat.npz rnnt_clamp_*, ref_rnnt.npz fastemit_clamp)
+        "tanh_h64_fastemit_sum": dict(activation="tanh", seed=55, B=3, T=8, U=5, De=8, Dp=8, H=64, V=15, fbs=3,
+                                      reduction="sum", loss_kwargs=dict(fastemit_lambda=0.1)),
+        "multilingual_relu": dict(activation="relu", seed=56, B=5, T=9, U=5, De=16, Dp=16, H=64, V=12, fbs=2,
+                                  reduction="mean_batch", language_keys=langs, language_ids=["bn"] * 5),
+        "multilingual_mixed": dict(activation="tanh", seed=57, B=4, T=7, U=4, De=12, Dp=12, H=64, V=10, fbs=4,
+                                   reduction="mean_batch", language_keys=langs,
+                                   language_ids=["hi", "ta", "ta", "bn"]),
+    }.items():
+        for k, v in _joint_case(**kw).items():
+            out[f"{name}__{k}"] = v
+        out[f"{name}__activation"] = np.asarray(kw["activation"])
+        out[f"{name}__reduction"] = np.asarray(kw["reduction"])
+    np.savez(os.path.join(OUT, "ref_joint_fused.npz"), **out)
 
 
 def gen_ctc():
@@ -224,14 +276,46 @@ def gen_conv_asr():
              log_probs=lp.detach().numpy(), logits=m.decoder_logits.detach().numpy())
 
 
+def gen_decoder():
+    """Reference RNNTDecoder runs (embedding -> zero SOS step -> LSTM): outputs and parameter gradients for a given
+    state_dict, so that the work-alike can be checked after load_state_dict (initialisation RNG order is not pinned)."""
+    D = R.load_decoder_class()
+    out = {}
+    for name, (seed, B, U, V, H, L, kw) in {
+        "one_layer": (61, 3, 5, 11, 16, 1, {}),
+        "two_layers_fgb": (62, 2, 7, 9, 24, 2, dict(forget_gate_bias=0.5, weights_init_scale=0.7,
+                                                    hidden_hidden_bias_scale=0.3)),
+    }.items():
+        torch.manual_seed(seed)
+        m = D(prednet=dict(pred_hidden=H, pred_rnn_layers=L, dropout=0.0, **kw), vocab_size=V)
+        tg = torch.randint(0, V, (B, U))
+        tg[-1, U - 2:] = V          # blank-as-pad positions embed to zero (padding_idx)
+        tl = torch.full((B,), U)
+        g, tl_out, states = m(targets=tg, target_length=tl)
+        w = torch.randn_like(g)
+        (g * w).sum().backward()
+        out[f"{name}__targets"] = tg.numpy()
+        out[f"{name}__g"] = g.detach().numpy()
+        out[f"{name}__w"] = w.numpy()
+        out[f"{name}__h"] = states[0].detach().numpy()
+        out[f"{name}__c"] = states[1].detach().numpy()
+        out[f"{name}__cfg"] = np.asarray([B, U, V, H, L], dtype=np.int64)
+        for k, p in m.named_parameters():
+            out[f"{name}__p.{k}"] = p.detach().numpy()
+            out[f"{name}__g.{k}"] = p.grad.numpy()
+    np.savez(os.path.join(OUT, "ref_decoder.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gen_kat()
     gen_rnnt()
     gen_joint()
+    gen_joint_fused()
     gen_ctc()
     gen_cl()
     gen_conv_asr()
+    gen_decoder()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

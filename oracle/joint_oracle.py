@@ -47,12 +47,19 @@ def rnnt_loss(logits, labels, act_lens, label_lens, blank, fastemit_lambda=0.0, 
     return _RNNTLossFn.apply(logits, labels.long(), act_lens.long(), label_lens.long(), blank, fastemit_lambda, clamp)
 
 
-def joint_logits(enc_out, pred_out, p: Dict[str, torch.Tensor], activation: str):
-    """enc_out [B,T,D_enc], pred_out [B,U1,D_pred] (already transposed as in forward :1388-1391)."""
+def joint_logits(enc_out, pred_out, p: Dict[str, torch.Tensor], activation: str, language_ids=None):
+    """enc_out [B,T,D_enc], pred_out [B,U1,D_pred] (already transposed as in forward :1388-1391).
+
+    ``language_ids`` (one key per utterance) selects the multilingual head (:1627-1639): ``p`` then holds
+    ``out.<lang>.weight / .bias`` per language; a batch of one language takes that head for the whole batch, a mixed
+    batch goes utterance by utterance — numerically the same thing, so one code path serves both."""
     f = torch.nn.functional.linear(enc_out, p["enc.weight"], p["enc.bias"])
     g = torch.nn.functional.linear(pred_out, p["pred.weight"], p["pred.bias"])
     inp = _ACTS[activation](f.unsqueeze(2) + g.unsqueeze(1))
-    return torch.nn.functional.linear(inp, p["out.weight"], p["out.bias"])
+    if language_ids is None:
+        return torch.nn.functional.linear(inp, p["out.weight"], p["out.bias"])
+    return torch.stack([torch.nn.functional.linear(x, p[f"out.{lang}.weight"], p[f"out.{lang}.bias"])
+                        for x, lang in zip(inp, language_ids)])
 
 
 def reduce_losses(losses, target_lengths, reduction):
@@ -81,6 +88,7 @@ def fused_joint_loss(
     fastemit_lambda: float = 0.0,
     clamp: float = 0.0,
     return_sub_logits: bool = False,
+    language_ids=None,
 ):
     enc = encoder_outputs.transpose(1, 2)
     dec = decoder_outputs.transpose(1, 2)
@@ -91,7 +99,8 @@ def fused_joint_loss(
         sl = slice(begin, end)
         el, tl = encoder_lengths[sl], transcript_lengths[sl]
         mt, mu = int(el.max()), int(tl.max())
-        z = joint_logits(enc[sl, :mt], dec[sl, : mu + 1], p, activation)
+        z = joint_logits(enc[sl, :mt], dec[sl, : mu + 1], p, activation,
+                         None if language_ids is None else list(language_ids[begin:end]))
         if return_sub_logits:
             subs.append(z)
         # blank = num_classes (RNNTLoss._blank, losses/rnnt.py:416)

@@ -164,6 +164,40 @@ def load_joint_class():
     return _build_class("RNNTJoint", meths, (_Base,), ns)
 
 
+def load_decoder_class():
+    """The reference's RNNTDecoder (modules/rnnt.py:524-1173: __init__, forward, predict, _predict_modules,
+    initialize_state) on top of the real ``nemo.collections.common.parts.rnn`` module (imports only torch, numpy and
+    nemo.utils), with AbstractRNNTDecoder's three attribute assignments (rnnt_abstract.py:128-137) as the base."""
+    _require()
+    import importlib.util
+
+    import torch
+
+    _stub_namespaces()
+    spec = importlib.util.spec_from_file_location(
+        "_ref_common_parts_rnn", os.path.join(NEMO_ROOT, "nemo", "collections", "common", "parts", "rnn.py"))
+    rnn_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rnn_mod)
+    meths = _class_methods(os.path.join(ASR, "modules", "rnnt.py"), "RNNTDecoder",
+                           ["__init__", "forward", "predict", "_predict_modules", "initialize_state"])
+
+    class _Base(torch.nn.Module):
+        def __init__(self, vocab_size, blank_idx, blank_as_pad):
+            super().__init__()
+            self.vocab_size = vocab_size
+            self.blank_idx = blank_idx
+            self.blank_as_pad = blank_as_pad
+            if blank_idx not in [0, vocab_size]:
+                raise ValueError("`blank_idx` must be either 0 or the final token of the vocabulary")
+
+        def is_adapter_available(self):
+            return False
+
+    ns = dict(torch=torch, Dict=Dict, Any=Any, Optional=Optional, List=List, Union=Union, Tuple=Tuple, rnn=rnn_mod,
+              logging=_Logging())
+    return _build_class("RNNTDecoder", meths, (_Base,), ns)
+
+
 def load_rnnt_loss_facade():
     """The reference's RNNTLoss facade (losses/rnnt.py:333-508), default loss = warprnnt_numba."""
     _require()

@@ -35,7 +35,7 @@ def joint_params(joint):
 
 
 def run_step_and_oracle(device="cuda:0", B=3, T=20, U=7, V=40, H=64, De=32, Dp=32, activation="tanh", seed=0,
-                        fused_impl="tcgen05", precision="bf16x3", ctc_weight=0.3, e_lambda=10.0):
+                        fused_impl="tcgen05", precision="auto", ctc_weight=0.3, e_lambda=10.0, backward_mode="recompute"):
     """One training step of the hot path on `device` (joint -> RNNT loss, CTC head -> CTC loss, mixed loss
     backward, EWC penalty sweep) and the same step through the CPU oracle.  Returns error metrics."""
     from indic_cl_asr_b200 import CTCLoss, ConvASRDecoder, RNNTJoint, RNNTLoss
@@ -46,7 +46,7 @@ def run_step_and_oracle(device="cuda:0", B=3, T=20, U=7, V=40, H=64, De=32, Dp=3
     joint = RNNTJoint(jointnet=dict(encoder_hidden=De, pred_hidden=Dp, joint_hidden=H, activation=activation,
                                     dropout=0.0),
                       num_classes=V, fuse_loss_wer=True, fused_batch_size=4, fused_impl=fused_impl,
-                      precision=precision).to(device)
+                      precision=precision, backward_mode=backward_mode).to(device)
     joint.set_loss(RNNTLoss(num_classes=V))
     joint.set_wer(object())
     head = ConvASRDecoder(feat_in=De, num_classes=V).to(device)

@@ -116,7 +116,8 @@ def test_joint_stash_size_and_limit(monkeypatch):
     assert x3 - x1 >= rows * H * 2 and x3 - x1 < rows * H * 2 + 4096
     assert l.clasr_joint_stash_bytes(0, T, U1, H, Vp, _lib.PREC["bf16x3"]) == 0
     monkeypatch.delenv("CLASR_JOINT_STASH", raising=False)
-    assert fused._stash_limit_bytes() == 48 << 30
+    assert fused._stash_limit_bytes() == 0            # default: the logits never reach HBM (backward recomputes)
+    assert fused._stash_limit_bytes(48.0) == 48 << 30  # RNNTJoint(backward_mode="stash")
     monkeypatch.setenv("CLASR_JOINT_STASH", "0")
     assert fused._stash_limit_bytes() == 0
     monkeypatch.setenv("CLASR_JOINT_STASH", "1.5")

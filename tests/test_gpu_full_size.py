@@ -1,6 +1,7 @@
-"""BASELINE.json full size (T=250, U=100, V=1024, H=640): the fused tcgen05 path against the materialised path
-(torch fp32 joint -> our RNNT loss kernels, itself pinned to the fp64 oracle at this size by
-test_gpu_rnnt_loss.py::test_full_size_properties) and against size-independent properties of the transducer gradient."""
+"""BASELINE.json full size (T=250, U=100, V=1024, H=640): the fused tcgen05 path in its default precision against
+the fp64 oracle (two utterances), against the materialised path at B=32 (torch fp32 joint -> our RNNT loss kernels,
+itself pinned to the fp64 oracle at this size by test_gpu_rnnt_loss.py::test_full_size_properties) and against
+size-independent properties of the transducer gradient."""
 import pytest
 import torch
 
@@ -45,22 +46,25 @@ def _materialised_costs(f, g, W, b, lab, al, ll, sub=4):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
+# "fp16x3" is what RNNTJoint(precision="auto") resolves to, i.e. what bench.py measures
+@pytest.mark.parametrize("precision", ["fp16x3", "bf16x3"])
 @pytest.mark.parametrize("ragged", [False, True])
-def test_full_size_costs_fused_vs_materialised(ragged):
+def test_full_size_costs_fused_vs_materialised(ragged, precision):
     f, g, W, b, lab, al, ll = _inputs(32, 11, ragged)
     with torch.no_grad():
-        fused = fused_joint_rnnt_loss(f, g, W, b, lab, al, ll, V, "tanh", "bf16x3")
+        fused = fused_joint_rnnt_loss(f, g, W, b, lab, al, ll, V, "tanh", precision)
         ref = _materialised_costs(f, g, W, b, lab, al, ll)
     assert torch.isfinite(fused).all()
     assert ((fused - ref).abs() <= 1e-5 * ref.abs()).all(), ((fused - ref).abs() / ref.abs()).max().item()
 
 
-def test_full_size_gradients_and_properties():
+@pytest.mark.parametrize("precision,stash_gib", [("fp16x3", None), ("fp16x3", 48.0), ("bf16x3", None)])
+def test_full_size_gradients_and_properties(precision, stash_gib):
     B = 8
     f, g, W, b, lab, al, ll = _inputs(B, 5, True)
     wts = torch.linspace(0.5, 1.5, B, device=DEV)
     leaves = [x.clone().requires_grad_(True) for x in (f, g, W, b)]
-    (fused_joint_rnnt_loss(*leaves, lab, al, ll, V, "tanh", "bf16x3") * wts).sum().backward()
+    (fused_joint_rnnt_loss(*leaves, lab, al, ll, V, "tanh", precision, stash_gib=stash_gib) * wts).sum().backward()
     ref_leaves = [x.clone().requires_grad_(True) for x in (f, g, W, b)]
     (_materialised_costs(*ref_leaves, lab, al, ll) * wts).sum().backward()
     for name, got, ref in zip(["d_f", "d_g", "d_W", "d_b"], leaves, ref_leaves):
@@ -75,6 +79,39 @@ def test_full_size_gradients_and_properties():
     # blank mass: each alignment emits exactly T_b blanks => sum over cells of dZ[., blank] = sum_b w_b (E[#blank] - T_b)
     # with E[#blank] = sum of blank posteriors, which the softmax part reproduces; only sign/finite checks here
     assert torch.isfinite(d_W).all() and d_b[V].item() < 0.0
+
+
+@pytest.mark.parametrize("stash_gib", [None, 48.0], ids=["recompute", "stash"])
+@pytest.mark.parametrize("act", ["tanh", "relu"])
+def test_config2_default_precision_vs_fp64_oracle(act, stash_gib):
+    """BASELINE.json configs[1] shape (T=250, U=100, V=1024, H=640), the DEFAULT precision (fp16x3), both backward
+    modes, tanh and the shipped checkpoint's ReLU — against the fp64 ORACLE itself (oracle/joint_oracle.py +
+    rnnt_oracle.py), not against this repo's materialised path.  Two utterances (one full length, one ragged) keep the
+    fp64 joint (2 x 250 x 101 x 1025 logits) and the numpy lattice at a few seconds of CPU.
+    Tolerances are north_star's: relative 1e-5 on the loss, 1e-4 on every gradient tensor."""
+    from oracle import joint_oracle
+
+    g_ = torch.Generator().manual_seed(23)
+    B = 2
+    f = torch.randn(B, T, H, generator=g_) * 0.7
+    gg = torch.randn(B, U + 1, H, generator=g_) * 0.7
+    W = (torch.rand(V + 1, H, generator=g_) * 2 - 1) / H ** 0.5
+    b = (torch.rand(V + 1, generator=g_) * 2 - 1) / H ** 0.5
+    lab = torch.randint(0, V, (B, U), generator=g_)
+    al, ll = torch.tensor([T, 173]), torch.tensor([U, 61])
+    wts = torch.tensor([0.35, 0.65])          # mean_batch x loss weight: upstream gradients well below 1
+    leaves = [x.to(DEV).requires_grad_(True) for x in (f, gg, W, b)]
+    costs = fused_joint_rnnt_loss(*leaves, lab.to(DEV), al.to(DEV), ll.to(DEV), V, act, "fp16x3", stash_gib=stash_gib)
+    (costs * wts.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    ref_leaves = [x.double().requires_grad_(True) for x in (f, gg, W, b)]
+    z = torch.nn.functional.linear(joint_oracle._ACTS[act](ref_leaves[0].unsqueeze(2) + ref_leaves[1].unsqueeze(1)),
+                                   ref_leaves[2], ref_leaves[3])
+    oc = joint_oracle.rnnt_loss(z, lab, al, ll, V)
+    (oc * wts.double()).sum().backward()
+    assert rel_err(costs.detach().cpu().numpy(), oc.detach().numpy()) <= 1e-5
+    for nm, got, rf in zip(["d_f", "d_g", "d_W", "d_b"], leaves, ref_leaves):
+        assert rel_err(got.grad.cpu().numpy(), rf.grad.numpy()) <= 1e-4, (act, nm)
 
 
 def _generic_costs(f, g, W, b, lab, al, ll, V, act, sub=2):

@@ -11,18 +11,98 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def build_from_fixture(c, fused_impl, precision="bf16x3"):
+def build_from_fixture(c, fused_impl, precision="auto", backward_mode="recompute"):
+    """RNNTJoint + RNNTLoss configured and loaded like the reference run that produced fixture case ``c``
+    (oracle/gen_golden.py::_joint_case); ``precision='auto'`` is the module default that bench.py runs."""
     B, T, U, De, Dp, H, V, fbs = [int(x) for x in c["cfg"]]
+    multi = "language_keys" in c
+    keys = [str(k) for k in c["language_keys"]] if multi else None
     j = RNNTJoint(jointnet=dict(encoder_hidden=De, pred_hidden=Dp, joint_hidden=H, activation=str(c["activation"]),
                                 dropout=0.0),
-                  num_classes=V, fuse_loss_wer=True, fused_batch_size=fbs, fused_impl=fused_impl, precision=precision)
+                  num_classes=V * len(keys) if multi else V, fuse_loss_wer=True, fused_batch_size=fbs,
+                  fused_impl=fused_impl, precision=precision, backward_mode=backward_mode, multilingual=multi,
+                  language_keys=keys)
     sd = {"enc.weight": c["p.enc.weight"], "enc.bias": c["p.enc.bias"], "pred.weight": c["p.pred.weight"],
-          "pred.bias": c["p.pred.bias"], "joint_net.1.weight": c["p.out.weight"], "joint_net.1.bias": c["p.out.bias"]}
+          "pred.bias": c["p.pred.bias"]}
+    if multi:
+        for k in keys:
+            sd[f"joint_net.1.{k}.weight"] = c[f"p.out.{k}.weight"]
+            sd[f"joint_net.1.{k}.bias"] = c[f"p.out.{k}.bias"]
+    else:
+        sd.update({"joint_net.1.weight": c["p.out.weight"], "joint_net.1.bias": c["p.out.bias"]})
     j.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
     j = j.to(DEV)
-    j.set_loss(RNNTLoss(num_classes=V, reduction=str(c["reduction"])))
+    kw = {}
+    if "fastemit_lambda" in c and (float(c["fastemit_lambda"]) != 0.0 or float(c["clamp"]) > 0.0):
+        kw = {"loss_kwargs": dict(fastemit_lambda=float(c["fastemit_lambda"]), clamp=float(c["clamp"]))}
+    j.set_loss(RNNTLoss(num_classes=V, reduction=str(c["reduction"]), **kw))
     j.set_wer(object())
     return j
+
+
+def fixture_param_grads(j, c):
+    """{fixture key: parameter} for every parameter the fixture holds a gradient for."""
+    got = {"enc.weight": j.enc.weight, "enc.bias": j.enc.bias, "pred.weight": j.pred.weight, "pred.bias": j.pred.bias}
+    if "language_keys" in c:
+        for k in [str(x) for x in c["language_keys"]]:
+            got[f"out.{k}.weight"] = j.joint_net[1][k].weight
+            got[f"out.{k}.bias"] = j.joint_net[1][k].bias
+    else:
+        got.update({"out.weight": j.joint_net[1].weight, "out.bias": j.joint_net[1].bias})
+    return got
+
+
+def run_fixture(j, c):
+    enc = torch.tensor(c["enc"], device=DEV, requires_grad=True)
+    dec = torch.tensor(c["dec"], device=DEV, requires_grad=True)
+    kw = {"language_ids": [str(x) for x in c["language_ids"]]} if "language_ids" in c else {}
+    loss, _, _, _ = j(encoder_outputs=enc, decoder_outputs=dec, encoder_lengths=torch.tensor(c["enc_lens"], device=DEV),
+                      transcripts=torch.tensor(c["transcripts"], device=DEV),
+                      transcript_lengths=torch.tensor(c["transcript_lens"], device=DEV), compute_wer=False, **kw)
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss, enc, dec
+
+
+def assert_fixture_parity(j, c, loss, enc, dec):
+    assert abs(loss.item() - float(c["loss"])) <= 1e-5 * abs(float(c["loss"]))          # north_star: rel 1e-5 on loss
+    for k, p in fixture_param_grads(j, c).items():
+        ref = c["g." + k]
+        got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(ref)  # a head no utterance used: grad None
+        assert np.abs(got - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-6), k         # rel 1e-4 on gradients
+    assert rel_err(enc.grad.cpu().numpy(), c["d_enc"]) <= 1e-4
+    assert rel_err(dec.grad.cpu().numpy(), c["d_dec"]) <= 1e-4
+
+
+FUSED_CASES = ["relu_h64", "relu_h128_fastemit", "tanh_h128_mean_volume", "sigmoid_h64_mean", "tanh_h64_fastemit_sum",
+               "multilingual_relu", "multilingual_mixed"]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+@pytest.mark.parametrize("impl,precision,mode", [("tcgen05", "auto", "recompute"), ("tcgen05", "auto", "stash"),
+                                                 ("tcgen05", "bf16x3", "recompute"), ("materialised", "auto", "recompute")])
+def test_fused_shapes_vs_reference_run(golden, case, impl, precision, mode):
+    """ref_joint_fused.npz — the reference's own RNNTJoint + RNNTLoss run at joint_hidden in {64, 128}: ReLU (the
+    shipped checkpoint), the multilingual per-language head with language_ids (reference modules/rnnt.py:1627-1639,
+    1694-1703), FastEmit, mean / mean_volume / sum reductions — against the fused tcgen05 path in its default
+    precision (what bench.py runs) and both backward modes, and against the materialised strategy."""
+    c = split_cases(golden("ref_joint_fused.npz"))[case]
+    j = build_from_fixture(c, impl, precision, mode)
+    if impl == "tcgen05" and case != "multilingual_mixed":
+        lang = [str(x) for x in c["language_ids"]] if "language_ids" in c else None
+        assert j._tcgen05_supported(lang), "this fixture is meant to reach the fused kernel"
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)  # multilingual_mixed: documented fallback to the sub-batch loop
+        loss, enc, dec = run_fixture(j, c)
+    assert_fixture_parity(j, c, loss, enc, dec)
+
+
+def test_mixed_language_batch_warns_and_falls_back(golden):
+    c = split_cases(golden("ref_joint_fused.npz"))["multilingual_mixed"]
+    j = build_from_fixture(c, "tcgen05")
+    with pytest.warns(RuntimeWarning, match="falls back to the materialised strategy"):
+        run_fixture(j, c)
 
 
 @pytest.mark.parametrize("case", ["tanh", "relu", "sigmoid", "tanh_wide"])
@@ -74,7 +154,8 @@ def test_full_step_materialised_vs_oracle(activation):
     assert rep["penalty_avg_rel_err"] <= 1e-5, rep
 
 
-@pytest.mark.parametrize("activation,H,precision", [("tanh", 64, "bf16x3"), ("relu", 128, "bf16x3"), ("sigmoid", 64, "bf16x3")])
+@pytest.mark.parametrize("precision", ["auto", "bf16x3"])
+@pytest.mark.parametrize("activation,H", [("tanh", 64), ("relu", 128), ("sigmoid", 64)])
 def test_full_step_tcgen05_vs_oracle(activation, H, precision):
     """The B200 path: fused tcgen05 joint + wavefront + CTC + EWC sweep, one step, against the fp64 oracle."""
     rep = run_step_and_oracle(device=DEV, B=5, T=23, U=9, V=37, H=H, De=24, Dp=16, activation=activation, seed=5,
@@ -84,23 +165,13 @@ def test_full_step_tcgen05_vs_oracle(activation, H, precision):
     assert rep["d_enc_rel_err"] <= 1e-4 and rep["d_dec_rel_err"] <= 1e-4, rep
 
 
-def test_tcgen05_matches_reference_run_fixture(golden):
+@pytest.mark.parametrize("precision", ["auto", "bf16x3"])
+def test_tcgen05_matches_reference_run_fixture(golden, precision):
     """ref_joint.npz 'tanh_wide' (H=64): the reference's own RNNTJoint+RNNTLoss output vs the fused B200 path."""
     c = split_cases(golden("ref_joint.npz"))["tanh_wide"]
-    j = build_from_fixture(c, "tcgen05")
-    enc = torch.tensor(c["enc"], device=DEV, requires_grad=True)
-    dec = torch.tensor(c["dec"], device=DEV, requires_grad=True)
-    loss, _, _, _ = j(encoder_outputs=enc, decoder_outputs=dec, encoder_lengths=torch.tensor(c["enc_lens"], device=DEV),
-                      transcripts=torch.tensor(c["transcripts"], device=DEV),
-                      transcript_lengths=torch.tensor(c["transcript_lens"], device=DEV), compute_wer=False)
-    loss.backward()
-    assert abs(loss.item() - float(c["loss"])) <= 1e-5 * abs(float(c["loss"]))
-    got = {"enc.weight": j.enc.weight, "enc.bias": j.enc.bias, "pred.weight": j.pred.weight, "pred.bias": j.pred.bias,
-           "out.weight": j.joint_net[1].weight, "out.bias": j.joint_net[1].bias}
-    for k, p in got.items():
-        assert rel_err(p.grad.cpu().numpy(), c["g." + k]) <= 1e-4, k
-    assert rel_err(enc.grad.cpu().numpy(), c["d_enc"]) <= 1e-4
-    assert rel_err(dec.grad.cpu().numpy(), c["d_dec"]) <= 1e-4
+    j = build_from_fixture(c, "tcgen05", precision)
+    loss, enc, dec = run_fixture(j, c)
+    assert_fixture_parity(j, c, loss, enc, dec)
 
 
 def test_wer_hook_is_called_per_sub_batch():

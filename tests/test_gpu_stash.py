@@ -37,7 +37,7 @@ def test_loss_backward_modes_agree(B, T, U, V, H, act, kw, precision, monkeypatc
         c = fused_joint_rnnt_loss(fd, gd, Wd, bd, lab.to(DEV), al.to(DEV), ll.to(DEV), V, act, precision, **kw)
         return (c * wts).sum()
 
-    monkeypatch.setenv("CLASR_JOINT_STASH", "")
+    monkeypatch.setenv("CLASR_JOINT_STASH", "48")
     g_stash, c_stash = _grads(run, (f, g, W, b))
     monkeypatch.setenv("CLASR_JOINT_STASH", "0")
     g_rec, c_rec = _grads(run, (f, g, W, b))
@@ -55,7 +55,7 @@ def test_sumsq_backward_modes_agree(B, T, U, V, H, act, monkeypatch):
         s = fused_joint_sumsq(fd, gd, Wd, bd, lab.to(DEV), al.to(DEV), ll.to(DEV), V, act, "bf16x3")
         return (s * up).sum()
 
-    monkeypatch.setenv("CLASR_JOINT_STASH", "")
+    monkeypatch.setenv("CLASR_JOINT_STASH", "48")
     g_stash, v_stash = _grads(run, (f, g, W, b))
     monkeypatch.setenv("CLASR_JOINT_STASH", "0")
     g_rec, v_rec = _grads(run, (f, g, W, b))

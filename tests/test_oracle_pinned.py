@@ -127,6 +127,37 @@ def test_joint_vs_reference_run(golden, case):
     assert np.abs(dec.grad.numpy() - c["d_dec"]).max() <= 1e-4 * np.abs(c["d_dec"]).max()
 
 
+FUSED_CASES = ["relu_h64", "relu_h128_fastemit", "tanh_h128_mean_volume", "sigmoid_h64_mean", "tanh_h64_fastemit_sum",
+               "multilingual_relu", "multilingual_mixed"]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_joint_fused_shapes_vs_reference_run(golden, case):
+    """ref_joint_fused.npz: reference runs at joint_hidden in {64, 128} (the shapes the tcgen05 kernel accepts) —
+    ReLU, multilingual head with language_ids (single-language and mixed batches), FastEmit, all reductions."""
+    c = split_cases(golden("ref_joint_fused.npz"))[case]
+    B, T, U, De, Dp, H, V, fbs = [int(x) for x in c["cfg"]]
+    act, red = str(c["activation"]), str(c["reduction"])
+    lang = [str(x) for x in c["language_ids"]] if "language_ids" in c else None
+    p = {k[2:]: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in c.items() if k.startswith("p.")}
+    enc = torch.tensor(c["enc"], dtype=torch.float64, requires_grad=True)
+    dec = torch.tensor(c["dec"], dtype=torch.float64, requires_grad=True)
+    z = joint_oracle.joint_logits(enc.transpose(1, 2), dec.transpose(1, 2), p, act, lang)
+    assert np.allclose(z.log_softmax(-1).detach().numpy(), c["logits"], atol=2e-6)
+    loss = joint_oracle.fused_joint_loss(enc, dec, torch.tensor(c["enc_lens"]), torch.tensor(c["transcripts"]),
+                                         torch.tensor(c["transcript_lens"]), p, act, V, fbs, red,
+                                         fastemit_lambda=float(c["fastemit_lambda"]),
+                                         clamp=max(0.0, float(c["clamp"])), language_ids=lang)
+    assert np.allclose(loss.item(), c["loss"], rtol=1e-5)
+    loss.backward()
+    for k, t in p.items():
+        ref = c["g." + k]
+        got = t.grad.numpy() if t.grad is not None else np.zeros_like(ref)   # a head no utterance used
+        assert np.abs(got - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-3), k
+    assert np.abs(enc.grad.numpy() - c["d_enc"]).max() <= 1e-4 * np.abs(c["d_enc"]).max()
+    assert np.abs(dec.grad.numpy() - c["d_dec"]).max() <= 1e-4 * np.abs(c["d_dec"]).max()
+
+
 def test_cl_vs_reference_run(golden):
     c = golden("ref_cl.npz")
     names = [str(n) for n in c["names"]]
