@@ -103,13 +103,69 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
 //
 // Precision: at the named sizes the forward/backward variables reach magnitudes of ~2.4e3, where one fp32 ulp
 // (2.4e-4) already exceeds the 1e-4 gradient tolerance once exponentiated, and an fp32 log-space recursion
-// accumulates that rounding over T+U steps.  The wavefront therefore carries alpha/beta in fp64 but does all
-// transcendental work in fp32 on *differences* (|x| small): v = max + log1pf(expf(min - max)).  Per-step error
-// is then ~1e-7 absolute, independent of |alpha|.  Storage is fp64 too (18 MB at B=32,T=250,U=100: L2-resident).
+// accumulates that rounding over T+U steps (the reference's numba kernels and ATen's CTC do exactly that).  Here the
+// lattice variables live in a scaled linear domain (LatNum below): fp32 mantissa + int32 exponent, ~1e-7 RELATIVE
+// error per step wherever alpha sits.
+// A lattice value in the SCALED LINEAR domain: value = m * 2^e (m >= 0 fp32, not necessarily normalised; 0 <=> m == 0).
+// alpha / beta are stored like this (8 bytes per cell, like the fp64 log they replace) and decoded where they are
+// consumed (lat_log): the wavefront's dependent chain then carries no transcendental and no fp64 at all, and the
+// relative rounding error per step is 2^-24 wherever alpha sits.
+struct LatNum {
+  float m;
+  int e;
+};
+// The two transition probabilities of a lattice cell, split into mantissa and integer exponent by whoever produces the
+// log-probs (joint epilogue / rnnt_lse_gather), off the wavefront's dependent chain: exp(logp) = m * 2^e.
+struct __align__(16) LatProb {
+  float bm, lm;   // blank / label mantissa in [2^-0.5, 2^0.5] (0 for probability 0)
+  int be, le;     // exponents (kLatZeroExp for probability 0)
+};
+constexpr int kLatZeroExp = -(1 << 28);   // exponent of the representation of 0
+
+__device__ __forceinline__ float lat_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// exp(x) = pm * 2^pe with pm in [2^-0.5, 2^0.5]; x = -inf -> (0, kLatZeroExp); NaN propagates through pm.
+// log2(e) is applied as a compensated product so that the result is good to ~2^-22 relative for any |x|.
+__device__ __forceinline__ void lat_prob_split(float x, float& pm, int& pe) {
+  if (x < -1e30f) { pm = 0.f; pe = kLatZeroExp; return; }
+  const float kH = 1.44269502162933349609f, kL = 1.92596299112661746e-8f;   // log2(e) = kH + kL
+  const float yh = x * kH;
+  const float yl = fmaf(x, kH, -yh) + x * kL;
+  const float n = rintf(yh);
+  pm = lat_ex2((yh - n) + yl);
+  pe = (int)n;
+}
+__device__ __forceinline__ LatProb lat_make_prob(float logp_blank, float logp_label) {
+  LatProb r;
+  lat_prob_split(logp_blank, r.bm, r.be);
+  lat_prob_split(logp_label, r.lm, r.le);
+  return r;
+}
+// natural log of m * 2^e as fp64 (-inf for 0, NaN stays NaN)
+__device__ __forceinline__ double lat_log(float m, int e) {
+  if (!(m > 0.f)) return m == 0.f ? -(double)INFINITY : (double)m;
+  return ((double)e + (double)__log2f(m)) * 0.6931471805599453094;
+}
+__device__ __forceinline__ double lat_log(const LatNum& v) { return lat_log(v.m, v.e); }
+// inverse (generic fp64 log-space kernel -> stored form)
+__device__ __forceinline__ LatNum lat_from_log(double v) {
+  LatNum r;
+  if (!(v > -1e300)) { r.m = v != v ? (float)v : 0.f; r.e = kLatZeroExp; return r; }
+  const double y = v * 1.4426950408889634074;
+  const double n = floor(y);
+  r.m = (float)exp2(y - n);
+  r.e = (int)n;
+  return r;
+}
+
 struct LatticeWs {
   float2* lp;      // [B,ND,U1] (log P(blank|t,u), log P(label_u|t,u))
-  double* alpha;   // [B,ND,U1]
-  double* beta;    // [B,ND,U1]
+  LatProb* pp;     // [B,ND,U1] the same two probabilities, split for the wavefront
+  LatNum* alpha;   // [B,ND,U1]
+  LatNum* beta;    // [B,ND,U1]
   float* denom;    // [B,ND,U1] negative log-sum-exp of the logits row (reduce.py:186-248)
   double* ll_fwd;  // [B]
   double* ll_bwd;  // [B]
@@ -119,7 +175,7 @@ struct LatticeWs {
 inline size_t lattice_ws_bytes(int B, int T, int U1) {
   size_t nd = (size_t)(T + U1 - 1);
   size_t cells = (size_t)B * nd * (size_t)U1;
-  size_t bytes = cells * (sizeof(float2) + 2 * sizeof(double) + sizeof(float));
+  size_t bytes = cells * (sizeof(LatProb) + sizeof(float2) + 2 * sizeof(LatNum) + sizeof(float));
   bytes = (bytes + 15) / 16 * 16;
   bytes += 2 * (size_t)B * sizeof(double);
   return (bytes + 255) / 256 * 256;
@@ -130,9 +186,10 @@ inline LatticeWs lattice_ws_carve(void* ws, int B, int T, int U1) {
   size_t nd = (size_t)(T + U1 - 1);
   size_t cells = (size_t)B * nd * (size_t)U1;
   char* p = (char*)ws;
+  w.pp = (LatProb*)p;    p += cells * sizeof(LatProb);   // 16-byte elements first: the workspace is 16-byte aligned
   w.lp = (float2*)p;     p += cells * sizeof(float2);
-  w.alpha = (double*)p;  p += cells * sizeof(double);
-  w.beta = (double*)p;   p += cells * sizeof(double);
+  w.alpha = (LatNum*)p;  p += cells * sizeof(LatNum);
+  w.beta = (LatNum*)p;   p += cells * sizeof(LatNum);
   w.denom = (float*)p;   p += cells * sizeof(float);
   p = (char*)ws + ((size_t)(p - (char*)ws) + 15) / 16 * 16;
   w.ll_fwd = (double*)p; p += (size_t)B * sizeof(double);

@@ -130,13 +130,13 @@ __device__ __forceinline__ RowGrad joint_row_grad(const JointFwdParams& p, int b
   if (kMode == 2 && valid) rg.go = 2.f * p.grad_cells[((int64_t)b * p.T + t) * p.U1 + u];  // d(sum z^2)/dz = 2z
   if (kMode == 1 && valid) {
     const int64_t idx = ((int64_t)b * p.w.ND + t + u) * p.U1 + u;
-    const double a = p.w.alpha[idx], bt = p.w.beta[idx], ll = p.w.ll_fwd[b];
+    const double a = lat_log(p.w.alpha[idx]), bt = lat_log(p.w.beta[idx]), ll = p.w.ll_fwd[b];
     const float dn = p.w.denom[idx];
     const float2 lpair = p.w.lp[idx];
     rg.go = p.grad_out ? p.grad_out[b] : 1.f;
     const bool has_label = u < Ub1 - 1;
-    const double beta_t1 = (t < Tb - 1) ? p.w.beta[idx + p.U1] : 0.0;
-    const double beta_u1 = has_label ? p.w.beta[idx + p.U1 + 1] : 0.0;
+    const double beta_t1 = (t < Tb - 1) ? lat_log(p.w.beta[idx + p.U1]) : 0.0;
+    const double beta_u1 = has_label ? lat_log(p.w.beta[idx + p.U1 + 1]) : 0.0;
     rg.base2 = ((float)(a + bt - ll) + dn) * kLog2e;
     if (p.fastemit_lambda > 0.f && has_label) {
       rg.fe_coef = p.fastemit_lambda;
@@ -735,7 +735,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       if (kStats && valid) {
         const float lse = (m + log2f(s)) * 0.6931471805599453f;
         p.w.denom[idx] = -lse;
-        p.w.lp[idx] = make_float2(zb - lse, label >= 0 ? zl - lse : -INFINITY);
+        const float lpb = zb - lse, lpl = label >= 0 ? zl - lse : -INFINITY;
+        p.w.lp[idx] = make_float2(lpb, lpl);
+        p.w.pp[idx] = lat_make_prob(lpb, lpl);
         if (p.sumsq) p.sumsq[((int64_t)b * p.T + t) * p.U1 + u] = ssq;
       }
     }

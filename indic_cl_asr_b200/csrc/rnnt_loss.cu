@@ -15,6 +15,8 @@
 //     zero-fill passes (rnnt_pytorch.py:58, gpu_rnnt.py:156) nor the in-place mul_ pass of backward
 //     (rnnt_pytorch.py:87-91) exist.  Algorithmic traffic: 2 reads + 1 write of the logits tensor.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace clasr {
 
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) rnnt_lse_gather_kernel(
     if (u < Ub1 - 1) zl = z[labels[(int64_t)b * (U1 - 1) + u]] + denom;
     w.denom[idx] = denom;
     w.lp[idx] = make_float2(zb + denom, zl);
+    w.pp[idx] = lat_make_prob(zb + denom, zl);
   }
 }
 
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) rnnt_lse_gather_vec_kernel(
       if (u < Ub1 - 1) zl = z[labels[(int64_t)b * (U1 - 1) + u]] + denom;
       w.denom[idx] = denom;
       w.lp[idx] = make_float2(zb + denom, zl);
+      w.pp[idx] = lat_make_prob(zb + denom, zl);
     }
   }
 }
@@ -196,14 +200,14 @@ __global__ void __launch_bounds__(kRowWarps * 32) rnnt_grad_vec_kernel(
       continue;
     }
     const int64_t idx = ((int64_t)b * w.ND + t + u) * U1 + u;
-    const double a = w.alpha[idx], bt = w.beta[idx], ll = w.ll_fwd[b];
+    const double a = lat_log(w.alpha[idx]), bt = lat_log(w.beta[idx]), ll = w.ll_fwd[b];
     const float dn = w.denom[idx];
     const float2 lpair = w.lp[idx];
     const float go = grad_out ? grad_out[b] : 1.f;
     const bool has_label = u < Ub1 - 1;
     const int label = has_label ? (int)labels[(int64_t)b * (U1 - 1) + u] : -1;
-    const double beta_t1 = (t < Tb - 1) ? w.beta[idx + U1] : 0.0;      // beta[t+1,u]
-    const double beta_u1 = has_label ? w.beta[idx + U1 + 1] : 0.0;     // beta[t,u+1]
+    const double beta_t1 = (t < Tb - 1) ? lat_log(w.beta[idx + U1]) : 0.0;      // beta[t+1,u]
+    const double beta_u1 = has_label ? lat_log(w.beta[idx + U1 + 1]) : 0.0;     // beta[t,u+1]
     const float base2 = ((float)(a + bt - ll) + dn) * kLog2eF;  // grad = exp(alpha + beta + logpk - ll), logpk = dn + z
     const bool fe = fastemit_lambda > 0.f && has_label;
     const float fe_base2 = fe ? ((float)(a + beta_u1 - ll + (double)lpair.y) + dn) * kLog2eF : -INFINITY;
@@ -249,7 +253,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) rnnt_grad_vec_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3/K4: alpha and beta wavefronts.  grid = (B, 2): blockIdx.y == 0 -> alpha, 1 -> beta.
+// K3/K4, generic variant (block-synchronous, fp64 log space): grid = (B, 2): blockIdx.y == 0 -> alpha, 1 -> beta.
+// Used for U+1 > 1024 or when the seam buffers of the warp-shuffle kernel below would not fit in shared memory.
 // Thread u owns lattice column u; diagonal n holds cells t = n - u.  The (blank,label) log-probs of
 // `dch` diagonals at a time are staged into shared memory with cp.async, double-buffered.
 // ------------------------------------------------------------------------------------------------
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
   const int nrows = nd - 1;        // recursion steps
   const int64_t base = (int64_t)b * w.ND * U1;
   const float2* __restrict__ lp = w.lp + base;
-  double* __restrict__ out = (backward ? w.beta : w.alpha) + base;
+  LatNum* __restrict__ out = (backward ? w.beta : w.alpha) + base;
 
   // step r (0..nrows-1) consumes lp row:  forward r  (produces diagonal r+1)
   //                                       backward nd-2-r (produces that same diagonal)
@@ -300,12 +305,12 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
   // initial diagonal
   if (threadIdx.x == 0) {
     if (!backward) {
-      vals[0] = 0.0; out[0] = 0.0;
+      vals[0] = 0.0; out[0] = lat_from_log(0.0);
     } else {
       const int64_t li = (int64_t)(nd - 1) * U1 + (Ub1 - 1);
       const double v = (double)lp[li].x;
       vals[Ub1 - 1] = v;
-      out[li] = v;
+      out[li] = lat_from_log(v);
     }
   }
   issue_chunk(0);
@@ -335,7 +340,7 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
             if (u > 0) emit = prev[u - 1] + (double)lrow[u - 1].y;     // alpha[t,u-1] + logp(label_{u-1} | t,u-1)
             const double v = log_sum_exp_d(emit, no_emit);
             nxt[u] = v;
-            out[(int64_t)n * U1 + u] = v;
+            out[(int64_t)n * U1 + u] = lat_from_log(v);
           }
         }
       } else {
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
             if (u < Ub1 - 1) emit = prev[u + 1] + (double)l.y;         // beta[t,u+1] + logp(label_u | t,u)
             const double v = log_sum_exp_d(emit, no_emit);
             nxt[u] = v;
-            out[(int64_t)n * U1 + u] = v;
+            out[(int64_t)n * U1 + u] = lat_from_log(v);
           }
         }
       }
@@ -372,8 +377,260 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3/K4, warp-shuffle wavefront (the default).  Reference: gpu_rnnt_kernel.py:73-172 (alpha), :175-269 (beta) — there
+// one block-wide barrier and a global-memory round trip per anti-diagonal.  Here:
+//   * thread j owns lattice column j (alpha: u = j; beta runs the mirrored lattice, u = U_b - j) and walks it in time;
+//     inside a warp lane l is l steps behind lane l-1 (the anti-diagonal skew), so the value a cell needs from its
+//     left neighbour is what the neighbouring LANE produced one step earlier: ONE __shfl_up per step, no barrier;
+//   * warps are chained through a shared-memory seam: lane 31 of warp w publishes its column (indexed by time step)
+//     with a release store of a progress counter every kSeamPublish steps, lane 0 of warp w+1 acquires it.  Warp w+1
+//     therefore runs ~40 steps behind warp w and the block never synchronises after start-up;
+//   * arithmetic in a SCALED LINEAR domain instead of log space: a value is m * 2^e (m fp32, e int32), the two incoming
+//     terms are aligned with an exact power of two, added, and re-normalised with integer operations on the exponent
+//     field.  The dependent chain per step is shuffle + ~8 integer / fp32 operations instead of fp64 adds around
+//     expf / log1pf, and the relative rounding error per step is 2^-24 wherever alpha sits (in log space the ABSOLUTE
+//     error of an fp32 alpha ~ 2e3 would be 2.4e-4, which is why the generic kernel below carries fp64);
+//   * the transition probabilities exp(logp) are split into mantissa and integer exponent off the dependent chain
+//     (compensated product with log2(e), MUFU.EX2 on the fraction), prefetched kLatPrefetch steps ahead;
+//   * results leave as fp64 natural logs in the same diagonal-major workspace: a warp's 32 stores of one step are
+//     256 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSeamPublish = 8;
+
+__device__ __forceinline__ float lat_pow2(int d) {   // 2^d for d <= 0; 0 below 2^-126
+  return __int_as_float(max(d + 127, 0) << 23);
+}
+// x * 2^E = ma 2^ea + mb 2^eb, E = max(ea, eb): no normalisation (the caller does that every kLatPrefetch steps)
+__device__ __forceinline__ void lat_add_lazy(float ma, int ea, float mb, int eb, float& x, int& E) {
+  E = max(ea, eb);
+  x = fmaf(ma, lat_pow2(ea - E), mb * lat_pow2(eb - E));
+}
+// bring m into [1, 2) (0 and NaN keep their mantissa; 0 gets the canonical exponent)
+__device__ __forceinline__ void lat_normalise(float& m, int& e) {
+  const int bits = __float_as_int(m);
+  const int k = (bits >> 23) - 127;
+  const bool pos = m > 0.f;
+  m = pos ? __int_as_float(bits - (k << 23)) : m;
+  e = pos ? e + k : kLatZeroExp;
+}
+
+// One thread runs column j of the alpha lattice AND column j of the mirrored beta lattice: two independent dependent
+// chains in one instruction stream (a lone warp per scheduler issues a dependent instruction only every ~5 cycles, so
+// the second chain is nearly free), and the step body is branch-free apart from the (rare, warp-uniform) seam wait.
+// kPF: cells in flight per lane and direction (4 registers each), also the normalisation period of the chains.
+template <int kPF, bool kHasLeft>
+__device__ __forceinline__ void rnnt_lattice_run(const LatticeWs& w, int b, int Tb, int Ub1, int T, int U1, int warp,
+                                                 int lane, int nw, int* prog, LatNum* seam, float fastemit_lambda,
+                                                 float* __restrict__ costs) {
+  const int j = warp * 32 + lane;                           // column in processing order
+  const bool col_ok = j < Ub1;
+  const unsigned t_lim = col_ok ? (unsigned)Tb : 0u;        // valid <=> (unsigned)tt < t_lim
+  const int nlanes = min(32, Ub1 - 32 * warp);
+  const int nsteps = Tb + nlanes - 1;
+  const int64_t base = (int64_t)b * w.ND * U1;
+  const bool publishes = warp + 1 < nw;                     // a full warp with a right-hand neighbour
+  const int nwc = (int)(blockDim.x >> 5);                   // seam layout: [direction][warp][T]
+  const bool last_col = j == Ub1 - 1;
+
+  // This lane's cells lie on one line of the diagonal-major arrays: time index tt = s - lane in processing order is
+  // lattice row t = tt (alpha) or Tb-1-tt (beta), array index (t + u) U1 + u -> a constant stride of +-U1 per step.
+  const uint4* pin[2];
+  LatNum* pout[2];
+  int64_t dstep[2];
+  const LatNum* seam_in[2];
+  LatNum* seam_out[2];
+  unsigned prog_prev[2], prog_mine[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const int u = d ? Ub1 - 1 - j : j;
+    const int64_t idx0 = base + (int64_t)((d ? Tb - 1 + lane : -lane) + u) * U1 + u;   // index at step s = 0
+    dstep[d] = d ? -(int64_t)U1 : (int64_t)U1;
+    pin[d] = reinterpret_cast<const uint4*>(w.pp) + idx0;
+    pout[d] = (d ? w.beta : w.alpha) + idx0;
+    seam_in[d] = seam + (size_t)(d * nwc + (kHasLeft ? warp - 1 : 0)) * T;
+    seam_out[d] = seam + (size_t)(d * nwc + warp) * T - lane;   // indexed by step s: time index tt = s - 31 for lane 31
+    prog_prev[d] = (unsigned)__cvta_generic_to_shared(prog + d * 32 + (kHasLeft ? warp - 1 : 0));
+    prog_mine[d] = (unsigned)__cvta_generic_to_shared(prog + d * 32 + warp);
+  }
+  const uint4 kNoCell = make_uint4(0u, 0u, (unsigned)kLatZeroExp, (unsigned)kLatZeroExp);
+  uint4 q[2][kPF];
+#pragma unroll
+  for (int i = 0; i < kPF; ++i) {
+    const bool ok = (unsigned)(i - lane) < t_lim;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) q[d][i] = ok ? __ldg(pin[d] + dstep[d] * i) : kNoCell;
+  }
+#pragma unroll
+  for (int d = 0; d < 2; ++d) pin[d] += dstep[d] * kPF;
+
+  // own chain (alpha: alpha[t-1,u] p_blank[t-1,u]; beta: beta[t+1,u]) / value handed to the right-hand lane next step.
+  // Column 0 starts from 1: alpha[0,0] = 1, and beta[T-1,U] = 1 * p_blank[T-1,U].
+  float cm[2], rm[2];
+  int ce[2], re[2];
+  float fin_m[2] = {0.f, 0.f};
+  int fin_e[2] = {kLatZeroExp, kLatZeroExp};
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    cm[d] = j == 0 ? 1.f : 0.f;
+    ce[d] = j == 0 ? 0 : kLatZeroExp;
+    rm[d] = 0.f;
+    re[d] = kLatZeroExp;
+  }
+  int avail = 0;                         // time steps BOTH left-hand chains have published
+  int tt = -lane;
+  for (int s0 = 0; s0 < nsteps; s0 += kPF) {
+#pragma unroll
+    for (int i = 0; i < kPF; ++i, ++tt) {
+      const int s = s0 + i;              // steps past nsteps touch invalid cells only (no loads, no stores)
+      const bool valid = (unsigned)tt < t_lim;
+      const bool ld_ok = (unsigned)(tt + kPF) < t_lim;
+      if (kHasLeft && s < Tb && s >= avail) {   // warp-uniform and rare: the left-hand warp runs ~40 steps ahead
+        int v = 0;
+        for (uint32_t it = 0;; ++it) {
+          if (lane == 0) {
+            int v0, v1;
+            asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v0) : "r"(prog_prev[0]) : "memory");
+            asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v1) : "r"(prog_prev[1]) : "memory");
+            v = min(v0, v1);
+          }
+          v = __shfl_sync(0xffffffffu, v, 0);
+          if (v > s) break;
+          if (it > (1u << 24)) __trap();   // a protocol bug must not hang the GPU
+        }
+        avail = v;
+      }
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const uint4 cp = q[d][i];
+        q[d][i] = ld_ok ? __ldg(pin[d]) : kNoCell;
+        pin[d] += dstep[d];
+        const float pbm = __uint_as_float(cp.x), plm = __uint_as_float(cp.y);
+        const int pbe = (int)cp.z, ple = (int)cp.w;
+        // ---- value from the left-hand column (same time index): the neighbouring lane produced it one step ago
+        float lm = __shfl_up_sync(0xffffffffu, rm[d], 1);
+        int le = __shfl_up_sync(0xffffffffu, re[d], 1);
+        if (kHasLeft) {                  // lane 0 takes it from the seam at time index s (all lanes read: broadcast)
+          const LatNum sv = seam_in[d][min(s, Tb - 1)];
+          const bool take = lane == 0 && s < Tb;
+          lm = lane == 0 ? (take ? sv.m : 0.f) : lm;
+          le = lane == 0 ? (take ? sv.e : kLatZeroExp) : le;
+        } else {
+          lm = lane == 0 ? 0.f : lm;
+          le = lane == 0 ? kLatZeroExp : le;
+        }
+        float nm;
+        int ne;
+        if (d == 0) {
+          // alpha[t,u] = alpha[t-1,u] p_blank[t-1,u] + alpha[t,u-1] p_label[t,u-1]: both products were formed by their
+          // source cells (cm by this lane one step ago, lm by the left-hand lane)
+          lat_add_lazy(cm[d], ce[d], lm, le, nm, ne);
+        } else {
+          // beta[t,u] = beta[t+1,u] p_blank[t,u] + beta[t,u+1] p_label[t,u]   (mirrored: own chain / left-hand lane)
+          lat_add_lazy(cm[d] * pbm, ce[d] + pbe, lm * plm, le + ple, nm, ne);
+        }
+        nm = valid ? nm : 0.f;
+        ne = valid ? ne : kLatZeroExp;
+        if (i == kPF - 1) lat_normalise(nm, ne);   // mantissas grow by < 2.83x per step: 2^13 at most in between
+        ne = max(ne, 2 * kLatZeroExp);             // chains of zeros must not wrap the exponent
+        if (valid) {
+          LatNum o;
+          o.m = nm;
+          o.e = ne;
+          *pout[d] = o;
+        }
+        pout[d] += dstep[d];
+        if (d == 0) {
+          cm[d] = nm * pbm; ce[d] = ne + pbe;
+          rm[d] = nm * plm; re[d] = ne + ple;
+        } else {
+          cm[d] = rm[d] = nm;
+          ce[d] = re[d] = ne;
+        }
+        const bool fin = last_col && tt == Tb - 1;   // alpha: the chained product alpha[T-1,U] p_blank; beta: beta[0,0]
+        fin_m[d] = fin ? cm[d] : fin_m[d];
+        fin_e[d] = fin ? ce[d] : fin_e[d];
+        if (publishes) {                 // warp-uniform
+          float sm = rm[d];
+          int se = re[d];
+          lat_normalise(sm, se);         // the consumer's mantissa bound must not compound across warps
+          if (lane == 31 && valid) {
+            LatNum o;
+            o.m = sm;
+            o.e = se;
+            seam_out[d][s] = o;
+            if (((tt + 1) % kSeamPublish) == 0 || tt + 1 == Tb)
+              asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(prog_mine[d]), "r"(tt + 1) : "memory");
+          }
+        }
+      }
+    }
+  }
+  if (col_ok && last_col) {
+    // gpu_rnnt_kernel.py:167-172: ll = alpha[T-1,U] + logp(blank | T-1,U);  :266-269: llBackward = beta[0,0]
+    const double ll = lat_log(fin_m[0], fin_e[0]);
+    w.ll_fwd[b] = ll;
+    if (costs) costs[b] = (float)(-ll * (1.0 + (double)fastemit_lambda));  // rnnt_helper.py:106-116
+    w.ll_bwd[b] = lat_log(fin_m[1], fin_e[1]);
+  }
+}
+
+template <int kMaxThreads, int kPF>
+__global__ void __launch_bounds__(kMaxThreads) rnnt_lattice_shfl_kernel(LatticeWs w, const int64_t* __restrict__ act_lens,
+                                                                        const int64_t* __restrict__ label_lens, int T,
+                                                                        int U1, float fastemit_lambda,
+                                                                        float* __restrict__ costs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int Tb = (int)act_lens[b], Ub1 = (int)label_lens[b] + 1;
+  int* prog = reinterpret_cast<int*>(smem_raw);             // [2][32] time steps published by each warp's last lane
+  LatNum* seam = reinterpret_cast<LatNum*>(prog + 64);      // [2][warps][T]
+  if (threadIdx.x < 64) prog[threadIdx.x] = 0;
+  __syncthreads();                                          // the only block-wide barrier
+  if (Tb <= 0) {
+    if (threadIdx.x == 0) {
+      w.ll_fwd[b] = 0.0;
+      w.ll_bwd[b] = 0.0;
+      if (costs) costs[b] = 0.f;
+    }
+    return;
+  }
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int nw = (Ub1 + 31) >> 5;
+  if (warp >= nw) return;
+  if (warp == 0) rnnt_lattice_run<kPF, false>(w, b, Tb, Ub1, T, U1, warp, lane, nw, prog, seam, fastemit_lambda, costs);
+  else rnnt_lattice_run<kPF, true>(w, b, Tb, Ub1, T, U1, warp, lane, nw, prog, seam, fastemit_lambda, costs);
+}
+
+static int launch_rnnt_lattice_generic(const LatticeWs& w, const int64_t* act_lens, const int64_t* label_lens, int B,
+                                       int T, int U1, float fastemit_lambda, float* costs, cudaStream_t stream);
+
 int launch_rnnt_lattice(const LatticeWs& w, const int64_t* act_lens, const int64_t* label_lens, int B, int T, int U1,
                         float fastemit_lambda, float* costs, cudaStream_t stream) {
+  // CLASR_LATTICE=generic selects the block-synchronous fp64 log-space kernel (kept for U+1 > 1024 and as an A/B arm)
+  const char* sel = getenv("CLASR_LATTICE");
+  const int warps = (U1 + 31) / 32;
+  const size_t smem = 64 * sizeof(int) + (size_t)2 * warps * T * sizeof(LatNum);
+  if (U1 > 1024 || smem > 160 * 1024 || (sel && !strcmp(sel, "generic")))
+    return launch_rnnt_lattice_generic(w, act_lens, label_lens, B, T, U1, fastemit_lambda, costs, stream);
+  auto kern = warps <= 8 ? rnnt_lattice_shfl_kernel<256, 8> : rnnt_lattice_shfl_kernel<1024, 2>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("rnnt_lattice: T=%d U1=%d needs %zu bytes of shared memory: %s", T, U1, smem, cudaGetErrorString(e));
+      return CLASR_STATUS_INVALID_VALUE;
+    }
+  }
+  prof_begin("rnnt_lattice", stream);
+  kern<<<B, warps * 32, smem, stream>>>(w, act_lens, label_lens, T, U1, fastemit_lambda, costs);
+  prof_end("rnnt_lattice", stream);
+  CLASR_CHECK_LAUNCH("rnnt_lattice");
+  return CLASR_STATUS_SUCCESS;
+}
+
+static int launch_rnnt_lattice_generic(const LatticeWs& w, const int64_t* act_lens, const int64_t* label_lens, int B,
+                                       int T, int U1, float fastemit_lambda, float* costs, cudaStream_t stream) {
   int threads = ((U1 + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   if (threads < 32) threads = 32;
@@ -419,14 +676,14 @@ __global__ void __launch_bounds__(kRowWarps * 32) rnnt_grad_kernel(
   const float* __restrict__ z = logits + row * Vp;
   const int64_t idx = ((int64_t)b * w.ND + t + u) * U1 + u;
   // fp64 lattice values; every exp() argument is formed in fp64 and rounded once to fp32
-  const double a = w.alpha[idx], bt = w.beta[idx], ll = w.ll_fwd[b];
+  const double a = lat_log(w.alpha[idx]), bt = lat_log(w.beta[idx]), ll = w.ll_fwd[b];
   const float dn = w.denom[idx];
   const float2 lpair = w.lp[idx];
   const float go = grad_out ? grad_out[b] : 1.f;
   const bool has_label = u < Ub1 - 1;
   const int label = has_label ? (int)labels[(int64_t)b * (U1 - 1) + u] : -1;
-  const double beta_t1 = (t < Tb - 1) ? w.beta[idx + U1] : 0.0;      // beta[t+1,u]
-  const double beta_u1 = has_label ? w.beta[idx + U1 + 1] : 0.0;     // beta[t,u+1]
+  const double beta_t1 = (t < Tb - 1) ? lat_log(w.beta[idx + U1]) : 0.0;      // beta[t+1,u]
+  const double beta_u1 = has_label ? lat_log(w.beta[idx + U1 + 1]) : 0.0;     // beta[t,u+1]
   const float base = (float)(a + bt - ll) + dn;  // grad = exp(alpha + beta + logpk - ll), logpk = dn + z
   const bool fe = fastemit_lambda > 0.f && has_label;
   const float fe_base = fe ? (float)(a + beta_u1 - ll + (double)lpair.y) + dn : 0.f;
@@ -475,8 +732,8 @@ __global__ void rnnt_export_lattice_kernel(LatticeWs w, const int64_t* __restric
   const int t = rem / U1, u = rem - t * U1;
   const bool valid = t < (int)act_lens[b] && u <= (int)label_lens[b];
   const int64_t idx = ((int64_t)b * w.ND + t + u) * U1 + u;
-  alphas[i] = valid ? (float)w.alpha[idx] : 0.f;
-  betas[i] = valid ? (float)w.beta[idx] : 0.f;
+  alphas[i] = valid ? (float)lat_log(w.alpha[idx]) : 0.f;
+  betas[i] = valid ? (float)lat_log(w.beta[idx]) : 0.f;
 }
 
 }  // namespace clasr
