@@ -110,7 +110,7 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
 // alpha / beta are stored like this (8 bytes per cell, like the fp64 log they replace) and decoded where they are
 // consumed (lat_log): the wavefront's dependent chain then carries no transcendental and no fp64 at all, and the
 // relative rounding error per step is 2^-24 wherever alpha sits.
-struct LatNum {
+struct __align__(8) LatNum {
   float m;
   int e;
 };

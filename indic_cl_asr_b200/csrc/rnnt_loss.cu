@@ -396,7 +396,6 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(LatticeWs w, const i
 //   * results leave as fp64 natural logs in the same diagonal-major workspace: a warp's 32 stores of one step are
 //     256 contiguous bytes.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSeamPublish = 8;
 
 __device__ __forceinline__ float lat_pow2(int d) {   // 2^d for d <= 0; 0 below 2^-126
   return __int_as_float(max(d + 127, 0) << 23);
@@ -453,13 +452,22 @@ __device__ __forceinline__ void rnnt_lattice_run(const LatticeWs& w, int b, int 
     prog_prev[d] = (unsigned)__cvta_generic_to_shared(prog + d * 32 + (kHasLeft ? warp - 1 : 0));
     prog_mine[d] = (unsigned)__cvta_generic_to_shared(prog + d * 32 + warp);
   }
-  const uint4 kNoCell = make_uint4(0u, 0u, (unsigned)kLatZeroExp, (unsigned)kLatZeroExp);
+  // cells in flight: q[d][i] is the cell of step s0 + i.  Loads are predicated and leave the registers untouched for
+  // cells outside the lattice (whatever they hold is discarded by the `valid` selects below).
   uint4 q[2][kPF];
+  auto load_cell = [](uint4& r, const uint4* p, bool ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t@p ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%5];\n\t}"
+                 : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w)
+                 : "r"((int)ok), "l"(p));
+  };
 #pragma unroll
   for (int i = 0; i < kPF; ++i) {
     const bool ok = (unsigned)(i - lane) < t_lim;
 #pragma unroll
-    for (int d = 0; d < 2; ++d) q[d][i] = ok ? __ldg(pin[d] + dstep[d] * i) : kNoCell;
+    for (int d = 0; d < 2; ++d) {
+      q[d][i] = make_uint4(0u, 0u, 0u, 0u);
+      load_cell(q[d][i], pin[d] + dstep[d] * i, ok);
+    }
   }
 #pragma unroll
   for (int d = 0; d < 2; ++d) pin[d] += dstep[d] * kPF;
@@ -480,12 +488,11 @@ __device__ __forceinline__ void rnnt_lattice_run(const LatticeWs& w, int b, int 
   int avail = 0;                         // time steps BOTH left-hand chains have published
   int tt = -lane;
   for (int s0 = 0; s0 < nsteps; s0 += kPF) {
-#pragma unroll
-    for (int i = 0; i < kPF; ++i, ++tt) {
-      const int s = s0 + i;              // steps past nsteps touch invalid cells only (no loads, no stores)
-      const bool valid = (unsigned)tt < t_lim;
-      const bool ld_ok = (unsigned)(tt + kPF) < t_lim;
-      if (kHasLeft && s < Tb && s >= avail) {   // warp-uniform and rare: the left-hand warp runs ~40 steps ahead
+    // ---- seam hand-shake, once per kPF steps (keeps the step body free of branches): the left-hand warp must have
+    // published every time index this block of steps reads
+    if (kHasLeft) {
+      const int need = min(s0 + kPF, Tb);
+      if (avail < need) {                // warp-uniform; rare once the pipeline is full (the producer runs ahead)
         int v = 0;
         for (uint32_t it = 0;; ++it) {
           if (lane == 0) {
@@ -495,15 +502,22 @@ __device__ __forceinline__ void rnnt_lattice_run(const LatticeWs& w, int b, int 
             v = min(v0, v1);
           }
           v = __shfl_sync(0xffffffffu, v, 0);
-          if (v > s) break;
+          if (v >= need) break;
           if (it > (1u << 24)) __trap();   // a protocol bug must not hang the GPU
         }
         avail = v;
       }
+    }
+#pragma unroll
+    for (int i = 0; i < kPF; ++i, ++tt) {
+      const int s = s0 + i;              // steps past nsteps touch invalid cells only (no loads, no stores)
+      const bool valid = (unsigned)tt < t_lim;
+      const bool ld_ok = (unsigned)(tt + kPF) < t_lim;
+      const bool fin = last_col && tt == Tb - 1;   // alpha: the chained product alpha[T-1,U] p_blank; beta: beta[0,0]
 #pragma unroll
       for (int d = 0; d < 2; ++d) {
         const uint4 cp = q[d][i];
-        q[d][i] = ld_ok ? __ldg(pin[d]) : kNoCell;
+        load_cell(q[d][i], pin[d], ld_ok);
         pin[d] += dstep[d];
         const float pbm = __uint_as_float(cp.x), plm = __uint_as_float(cp.y);
         const int pbe = (int)cp.z, ple = (int)cp.w;
@@ -512,7 +526,7 @@ __device__ __forceinline__ void rnnt_lattice_run(const LatticeWs& w, int b, int 
         int le = __shfl_up_sync(0xffffffffu, re[d], 1);
         if (kHasLeft) {                  // lane 0 takes it from the seam at time index s (all lanes read: broadcast)
           const LatNum sv = seam_in[d][min(s, Tb - 1)];
-          const bool take = lane == 0 && s < Tb;
+          const bool take = s < Tb;
           lm = lane == 0 ? (take ? sv.m : 0.f) : lm;
           le = lane == 0 ? (take ? sv.e : kLatZeroExp) : le;
         } else {
@@ -547,22 +561,22 @@ __device__ __forceinline__ void rnnt_lattice_run(const LatticeWs& w, int b, int 
           cm[d] = rm[d] = nm;
           ce[d] = re[d] = ne;
         }
-        const bool fin = last_col && tt == Tb - 1;   // alpha: the chained product alpha[T-1,U] p_blank; beta: beta[0,0]
         fin_m[d] = fin ? cm[d] : fin_m[d];
         fin_e[d] = fin ? ce[d] : fin_e[d];
-        if (publishes) {                 // warp-uniform
-          float sm = rm[d];
-          int se = re[d];
-          lat_normalise(sm, se);         // the consumer's mantissa bound must not compound across warps
-          if (lane == 31 && valid) {
-            LatNum o;
-            o.m = sm;
-            o.e = se;
-            seam_out[d][s] = o;
-            if (((tt + 1) % kSeamPublish) == 0 || tt + 1 == Tb)
-              asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(prog_mine[d]), "r"(tt + 1) : "memory");
-          }
+        if (publishes) {                 // warp-uniform; the store itself is a single predicated STS.64
+          LatNum o;
+          o.m = rm[d];
+          o.e = re[d];
+          lat_normalise(o.m, o.e);       // the consumer's mantissa bound must not compound across warps
+          if (lane == 31 && valid) seam_out[d][s] = o;
         }
+      }
+    }
+    if (publishes) {                     // one release per kPF steps: lane 31 has finished time indices < s0 + kPF - 31
+      const int done = min(max(s0 + kPF - 31, 0), Tb);
+      if (lane == 31 && done > 0) {
+        asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(prog_mine[0]), "r"(done) : "memory");
+        asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(prog_mine[1]), "r"(done) : "memory");
       }
     }
   }
