@@ -394,7 +394,10 @@ def main_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        import datetime
+        # a mismatched collective must fail within minutes, not hold the box for NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"),
+                                timeout=datetime.timedelta(seconds=120))
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     torch.backends.cudnn.allow_tf32 = False       # "fp32" config: torch's own small GEMMs/convs stay true fp32
@@ -457,6 +460,12 @@ def main_b200(args):
             run()
         with ClockSampler(local_rank) as clk:
             total_ms, per = time_steps(run, steps, flush, barrier, dev, world)
+            # an NVML query can take tens of ms: keep the identical load running (untimed) so that the sampler sees
+            # enough of it for a median.  A FIXED count: the step contains a collective, every rank must replay it
+            # the same number of times.
+            for _ in range(40):
+                run()
+            torch.cuda.synchronize()
         res = dict(wl=wl, step=step, ins=ins, gs=gs, total_ms=total_ms, per=per, ms=total_ms / steps,
                    value=B_glob * steps / (total_ms / 1e3), launches_per_step=int(launches_per_step),
                    clocks=clk.summary(), precision=wl.precision, n_params=wl.n_params, graph_error=graph_error)
@@ -656,9 +665,22 @@ def main_b200(args):
             "clocks": main_res["clocks"], "roofline": roofline, "roofline_more": extra, "kernel_ms": kern,
             "cpu_baseline": cpu, "impl": "b200",
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Leave without tearing the NCCL communicator down: destroy_process_group() with CUDA graphs that captured
+    collectives still alive can block for the watchdog timeout.  Every rank has finished its work when it gets here."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _time_ms(fn, iters=10, warm=3):
@@ -838,9 +860,9 @@ def main_config4(args, dev, world, rank):
                        "l2": "working set 1.9 GB per sweep, far larger than L2"},
             "roofline": {"bound": "hbm", "achieved": g, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": g / pk["hbm_gbs"],
                          "traffic": None, "algorithmic_bytes": by},
-            "importance_allreduce": ar, "clocks": clk.summary(), "gpu_launches": 2 * args.steps, "impl": "b200"}))
-    if world > 1:
-        dist.destroy_process_group()
+            "importance_allreduce": ar, "clocks": clk.summary(), "gpu_launches": 2 * args.steps, "impl": "b200"}),
+            flush=True)
+    finish(world)
 
 
 def main_reference(args):
