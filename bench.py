@@ -73,6 +73,8 @@ def parse():
     ap.add_argument("--ragged", action="store_true", help="enc_len ~ U{T/2..T}, tgt_len ~ U{U/2..U} (SURVEY.md §8d)")
     ap.add_argument("--dropout", type=float, default=None, help="joint dropout (the shipped checkpoint trains with 0.2)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--batch", type=int, default=None, help="override the config's global batch (experiments: --batch 4 on one "
+                                                            "GPU is the per-GPU work of the 8-GPU strong-scaling point)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -103,6 +105,9 @@ def resolve_cfg(args):
         c["dropout"] = args.dropout
     if args.ragged:
         c["ragged"] = True
+    if getattr(args, "batch", None):
+        c["B"] = args.batch
+        c["workload"] += f" [batch overridden: B={args.batch}]"
     return c
 
 
@@ -321,10 +326,19 @@ class Workload:
         lang = self.lang_ids_of(B_local)
         fp, cl, world = self.fp, self.cl, self.world
 
+        pen_stream = torch.cuda.Stream(device=self.dev)
+        pen_overlap = os.environ.get("CLASR_PEN_OVERLAP", "0") != "0"   # A/B switch; measured neutral to slower
+
         def step(enc, dec, tr, el, tl):
+            cur = torch.cuda.current_stream(self.dev)
             if variant == "ewc":
+                # the penalty sweep only has to land in the gradient buffer before backward() accumulates on top of it
+                # (cl_baseline_ewc.py:228-240): it runs beside the forward pass on its own stream
                 fp.bind_grads(zero=False)
-                _, avg = cl.get_penalty_grads_async(self.ewc_cfg, self.fish, self.theta, self.star, out=fp.grad)
+                if pen_overlap:
+                    pen_stream.wait_stream(cur)
+                with torch.cuda.stream(pen_stream if pen_overlap else cur):
+                    _, avg = cl.get_penalty_grads_async(self.ewc_cfg, self.fish, self.theta, self.star, out=fp.grad)
             else:
                 fp.bind_grads(zero=True)
                 avg = None
@@ -335,6 +349,8 @@ class Workload:
             else:
                 dec_out = dec
             loss, _ = self.hybrid(enc, el, dec_out, tr, tl, language_ids=lang)   # hybrid_rnnt_ctc_models.py:868-902
+            if variant == "ewc" and pen_overlap:
+                cur.wait_stream(pen_stream)
             (loss * scale).backward()      # local mean_batch x B_local/B: the SUM all-reduce gives the global mean's gradient
             if world > 1:
                 allreduce_flat_(fp.grad)

@@ -115,6 +115,10 @@ class RNNTJoint(torch.nn.Module):
         # the benchmark shape) — an explicit trade of HBM for time that the caller has to ask for.
         self.backward_mode = backward_mode
         self.stash_gib = float(stash_gib)
+        import os
+        # measured SLOWER inside the captured step (B_local = 4: 1.87 -> 1.89 ms; together with a side-stream penalty
+        # sweep 1.99 ms): every extra graph branch costs more in cross-stream edges than the ~35 us it hides
+        self.overlap_projections = os.environ.get("CLASR_PROJ_OVERLAP", "0") != "0"
 
     # ------------------------------------------------------------------ construction (:1667-1710)
     def _joint_net_modules(self, num_classes, pred_n_hidden, enc_n_hidden, joint_n_hidden, activation, dropout):
@@ -276,8 +280,20 @@ class RNNTJoint(torch.nn.Module):
         if use_tcgen05:
             # ONE projection and ONE dropout draw per forward call, shared by the loss pass and (MAS importance pass)
             # the stored-logits pass — the reference stores the logits of the same joint call (:1480-1496, 1649-1650)
-            f = self.project_encoder(encoder_outputs)   # [B,T,H]  (tcgen05 GEMM)
-            g = self.project_prednet(decoder_outputs)   # [B,U1,H]
+            # The two projections are independent small GEMMs (each a chain of ~4 launch-latency-bound kernels): the
+            # prediction-network one runs on a side stream beside the encoder one.  Autograd replays a node on the stream
+            # of its forward, so their backward passes (the tail of the step) overlap the same way.
+            if self.overlap_projections:
+                cur = torch.cuda.current_stream(encoder_outputs.device)
+                side = self._side_stream(encoder_outputs.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    g = self.project_prednet(decoder_outputs)   # [B,U1,H]
+                f = self.project_encoder(encoder_outputs)       # [B,T,H]  (tcgen05 GEMM)
+                cur.wait_stream(side)   # g stays referenced (autograd) until the next call's side.wait_stream(cur)
+            else:
+                f = self.project_encoder(encoder_outputs)
+                g = self.project_prednet(decoder_outputs)
             drop = self._dropout_args()
             losses = self._forward_fused_tcgen05(f, g, drop, encoder_lengths, transcripts, transcript_lengths,
                                                  language_ids)
@@ -378,6 +394,12 @@ class RNNTJoint(torch.nn.Module):
         if self.store_sub_enc or self.store_sub_logits:
             self.store_list = stored
         return losses, wer, wer_num, wer_denom
+
+    def _side_stream(self, device) -> torch.cuda.Stream:
+        streams = self.__dict__.setdefault("_side_streams", {})
+        if device not in streams:
+            streams[device] = torch.cuda.Stream(device=device)
+        return streams[device]
 
     # -- B200 path: fused joint + loss, logits never materialised -----------------------------------
     def _tcgen05_supported(self, language_ids) -> bool:
