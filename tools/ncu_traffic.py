@@ -15,8 +15,7 @@ rows = list(csv.reader(raw.splitlines()))
 hdr = rows[0]
 ci = {h: i for i, h in enumerate(hdr)}
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "sm__pipe_tensor_subunit_op_dense_cycles_active.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed_pipe_tensor.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__cycles_elapsed.max", "lts__t_sector_hit_rate.pct"]
 units = rows[1]
@@ -48,8 +47,8 @@ if out_path and res:
         table = {}
     table[key] = {"dram_bytes_read": to_bytes(last, "dram__bytes_read.sum"),
                   "dram_bytes_write": to_bytes(last, "dram__bytes_write.sum"),
-                  "gpu_time_us": last.get("gpu__time_duration.sum"),
-                  "tensor_pipe_active_pct": last.get("sm__pipe_tensor_subunit_op_dense_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                  "gpu_time": last.get("gpu__time_duration.sum"), "gpu_time_unit": last.get("gpu__time_duration.sum|unit"),
+                  "tensor_pipe_active_pct": last.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
                   "source": f"ncu --set full --clock-control none, {rep.split('/')[-1]}, launch {len(res)} of {len(res)} matching"}
     with open(out_path, "w") as fh:
         json.dump(table, fh, indent=1, sort_keys=True)
