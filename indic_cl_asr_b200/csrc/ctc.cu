@@ -12,30 +12,34 @@
 // row with fp32 atomics in LINEAR space (each term alpha*beta/(y*P) is a posterior <= 1, so no max-shift
 // is needed), then one coalesced vectorised pass writes the Vp-wide gradient row.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace clasr {
 
-// alpha / beta are carried and stored in fp64 while all transcendental work is fp32 on differences (see
-// LatticeWs in common.cuh for the rationale: |alpha| ~ 2e3 at the named sizes defeats an fp32 recursion).
+// alpha / beta are stored in the scaled linear domain (LatNum, common.cuh: fp32 mantissa + int32 exponent — |alpha| ~ 2e3
+// in log space at the named sizes defeats an fp32 log-space recursion, which is what ATen's kernel runs).
 struct CtcWs {
-  double* alpha;  // [B,T,S]
-  double* beta;   // [B,T,S]
+  LatNum* alpha;  // [B,T,S]
+  LatNum* beta;   // [B,T,S]
+  LatNum* prob;   // [B,T,S] y_t(l'_s) = exp(log_probs[t, l'_s]) split into mantissa / exponent (wavefront kernel's pre-pass)
   double* nll;    // [B] raw negative log-likelihood (inf when infeasible)
   int S;
 };
 
 inline size_t ctc_ws_bytes(int B, int T, int maxU) {
   size_t S = 2 * (size_t)maxU + 1;
-  size_t bytes = 2 * (size_t)B * T * S * sizeof(double) + (size_t)B * sizeof(double);
+  size_t bytes = 3 * (size_t)B * T * S * sizeof(LatNum) + (size_t)B * sizeof(double);
   return (bytes + 255) / 256 * 256;
 }
 inline CtcWs ctc_ws_carve(void* ws, int B, int T, int maxU) {
   CtcWs w;
   w.S = 2 * maxU + 1;
   size_t n = (size_t)B * T * w.S;
-  w.alpha = (double*)ws;
+  w.alpha = (LatNum*)ws;
   w.beta = w.alpha + n;
-  w.nll = w.beta + n;
+  w.prob = w.beta + n;
+  w.nll = (double*)(w.prob + n);
   return w;
 }
 
@@ -59,6 +63,7 @@ __device__ __forceinline__ double ctc_step(const double* prev, int pad, int s, i
   return lse3_d(prev[pad + s], prev[pad + s + 1], skip ? prev[pad + s + 2] : -INFINITY) + (double)y;
 }
 
+// Generic variant (block-synchronous, fp64 log space): any target length; also the A/B arm (CLASR_CTC_LATTICE=generic).
 __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const float* __restrict__ log_probs,
                                                            const int64_t* __restrict__ targets,
                                                            int64_t target_stride,
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const float* __restri
   const int Sb = 2 * Ub + 1;
   const int S = w.S;
   const float* __restrict__ lp = log_probs + (int64_t)b * T * Vp;
-  double* __restrict__ out = (backward ? w.beta : w.alpha) + (int64_t)b * T * S;
+  LatNum* __restrict__ out = (backward ? w.beta : w.alpha) + (int64_t)b * T * S;
   const int64_t* __restrict__ tg = targets + (int64_t)b * target_stride;
   const int pad = 2;
   const int W = Sb + 2 * pad;
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const float* __restri
           if (active) {
             const double v = ctc_step(prev, pad, s1, Sb, backward, step == 0, skip1, y);
             nxt[pad + s1] = v;
-            out[(int64_t)t * S + s1] = v;
+            out[(int64_t)t * S + s1] = lat_from_log(v);
           }
         } else {
           // very long targets (2U+1 > 1024): several states per thread, no prefetch queue
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const float* __restri
             const float y = __ldg(lp + (int64_t)t * Vp + cls);
             const double v = ctc_step(prev, pad, s, Sb, backward, step == 0, skip, y);
             nxt[pad + s] = v;
-            out[(int64_t)t * S + s] = v;
+            out[(int64_t)t * S + s] = lat_from_log(v);
           }
         }
         __syncthreads();
@@ -152,6 +157,241 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const float* __restri
   if (!backward && threadIdx.x == 0) {
     double l = prev[pad + Sb - 1];
     if (Sb > 1) l = log_sum_exp_d(l, prev[pad + Sb - 2]);
+    const double nll = -l;
+    w.nll[b] = nll;
+    nll_out[b] = (zero_infinity && nll == (double)INFINITY) ? 0.f : (float)nll;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-shuffle wavefront (the default).  Same machinery as the transducer lattice (rnnt_loss.cu): thread j owns lattice
+// state j of the alpha recursion AND state S-1-j of the beta recursion (two independent dependent chains per thread),
+// values live in the scaled linear domain, the s-1 / s-2 neighbours of the previous time step come from the
+// neighbouring LANES (two shuffles), warps are chained through a shared-memory seam (lanes 30 / 31 publish their
+// column, one release per kCtcBlock steps), and the step body is branch-free.  A pre-pass gathers y_t(l'_s) for the
+// whole sample and splits it into mantissa / exponent with all threads in parallel (the gather is the only
+// uncoalesced access: one 4-byte load per lattice state and time step, as in ATen's kernel).
+//   alpha_t(s) = (alpha_{t-1}(s) + alpha_{t-1}(s-1) + [skip] alpha_{t-1}(s-2)) y_t(l'_s)      (beta mirrored, ATen's
+//   convention: beta_t includes y_t).
+// ------------------------------------------------------------------------------------------------
+constexpr int kCtcBlock = 8;   // steps per seam hand-shake = probabilities in flight per lane = normalisation period
+
+__device__ __forceinline__ float ctc_pow2(int d) { return __int_as_float(max(d + 127, 0) << 23); }
+__device__ __forceinline__ void ctc_normalise(float& m, int& e) {
+  const int bits = __float_as_int(m);
+  const int k = (bits >> 23) - 127;
+  const bool pos = m > 0.f;
+  m = pos ? __int_as_float(bits - (k << 23)) : m;
+  e = pos ? e + k : kLatZeroExp;
+}
+
+template <bool kBeta>
+__global__ void __launch_bounds__(512) ctc_lattice_shfl_kernel(const float* __restrict__ log_probs,
+                                                                const int64_t* __restrict__ targets,
+                                                                int64_t target_stride,
+                                                                const int64_t* __restrict__ input_lens,
+                                                                const int64_t* __restrict__ target_lens, int T, int Vp,
+                                                                int blank, int zero_infinity, CtcWs w,
+                                                                float* __restrict__ nll_out) {
+  constexpr int kDirs = kBeta ? 2 : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int Tb = (int)input_lens[b];
+  const int Ub = (int)target_lens[b];
+  const int Sb = 2 * Ub + 1;
+  const int S = w.S;
+  int* prog = reinterpret_cast<int*>(smem_raw);               // [2][32] time steps published per warp and direction
+  uint4* seam = reinterpret_cast<uint4*>(prog + 64);          // [2][warps][T] lanes 30 / 31 as {m30, e30, m31, e31}
+  if (threadIdx.x < 64) prog[threadIdx.x] = 0;
+  if (Tb <= 0) {
+    if (threadIdx.x == 0) {
+      const float v = (Ub == 0) ? 0.f : INFINITY;             // torch: zero-length input with a non-empty target is infeasible
+      w.nll[b] = (double)v;
+      nll_out[b] = (zero_infinity && v == INFINITY) ? 0.f : v;
+    }
+    return;
+  }
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int nw = (Sb + 31) >> 5;
+  const int nwc = (int)(blockDim.x >> 5);
+  const int j = threadIdx.x;
+  const bool col_ok = j < Sb;
+  const int64_t* __restrict__ tg = targets + (int64_t)b * target_stride;
+  const float* __restrict__ lp = log_probs + (int64_t)b * T * Vp;
+  const int64_t sbase = (int64_t)b * T * S;
+
+  // ---- per-direction constants of this thread's lattice state
+  int st[2];          // lattice state
+  bool skip[2];       // may take the two-state jump (different neighbouring labels)
+#pragma unroll
+  for (int d = 0; d < kDirs; ++d) {
+    const int s = d ? Sb - 1 - j : j;
+    st[d] = s;
+    skip[d] = false;
+    if (col_ok && (s & 1)) {
+      const int cls = (int)tg[s >> 1];
+      if (!d) skip[d] = (s >= 3) && ((int)tg[(s >> 1) - 1] != cls);
+      else skip[d] = (s + 2 < Sb) && ((int)tg[(s >> 1) + 1] != cls);
+    }
+  }
+  // ---- pre-pass: y_t(l'_s) for every (t, s) of this sample, split into mantissa / exponent (independent iterations:
+  // full ILP; stores coalesced over s).  The thread that produces prob[t][s] is not the one that consumes it (beta
+  // runs mirrored), hence the barrier.
+  if (col_ok) {
+    const int cls = (j & 1) ? (int)tg[j >> 1] : blank;
+    LatNum* __restrict__ pr = w.prob + sbase + j;
+    const float* __restrict__ src = lp + cls;
+#pragma unroll 16
+    for (int t = 0; t < Tb; ++t) {   // 16 independent gathers in flight per thread
+      LatNum o;
+      lat_prob_split(__ldg(src + (int64_t)t * Vp), o.m, o.e);
+      pr[(int64_t)t * S] = o;
+    }
+  }
+  __syncthreads();                                            // the only block-wide barrier before the wavefront
+  if (warp < nw) {
+    const unsigned t_lim = col_ok ? (unsigned)Tb : 0u;
+    const bool has_left = warp > 0;
+    const bool publishes = warp + 1 < nw;
+    const LatNum* pin[2];
+    LatNum* pout[2];
+    int64_t dstep[2];
+    const uint4* seam_in[2];
+    uint4* seam_out[2];
+    unsigned prog_prev[2], prog_mine[2];
+#pragma unroll
+    for (int d = 0; d < kDirs; ++d) {
+      const int64_t i0 = sbase + (int64_t)(d ? Tb - 1 : 0) * S + st[d];      // step 0: t = 0 (alpha) / Tb-1 (beta)
+      dstep[d] = d ? -(int64_t)S : (int64_t)S;
+      pin[d] = w.prob + i0;
+      pout[d] = (d ? w.beta : w.alpha) + i0;
+      seam_in[d] = seam + (size_t)(d * nwc + (has_left ? warp - 1 : 0)) * T;
+      seam_out[d] = seam + (size_t)(d * nwc + warp) * T;
+      prog_prev[d] = (unsigned)__cvta_generic_to_shared(prog + d * 32 + (has_left ? warp - 1 : 0));
+      prog_mine[d] = (unsigned)__cvta_generic_to_shared(prog + d * 32 + warp);
+    }
+    uint2 q[2][kCtcBlock];
+    auto load_prob = [](uint2& r, const LatNum* p, bool ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.global.v2.u32 {%0,%1}, [%3];\n\t}"
+                   : "+r"(r.x), "+r"(r.y)
+                   : "r"((int)ok), "l"(p));
+    };
+#pragma unroll
+    for (int i = 0; i < kCtcBlock; ++i) {
+      const bool ok = (unsigned)i < t_lim;
+#pragma unroll
+      for (int d = 0; d < kDirs; ++d) {
+        q[d][i] = make_uint2(0u, (unsigned)kLatZeroExp);
+        load_prob(q[d][i], pin[d] + dstep[d] * i, ok);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < kDirs; ++d) pin[d] += dstep[d] * kCtcBlock;
+    // state 0 of each direction starts from 1: alpha_0(0) = y_0(blank), alpha_0(1) = (0 + 1) y_0(l_1), the rest 0
+    float cm[2];
+    int ce[2];
+#pragma unroll
+    for (int d = 0; d < kDirs; ++d) {
+      cm[d] = j == 0 ? 1.f : 0.f;
+      ce[d] = j == 0 ? 0 : kLatZeroExp;
+    }
+    int avail = 0;
+    for (int s0 = 0; s0 < Tb; s0 += kCtcBlock) {
+      if (has_left) {   // the left-hand warp must have finished every time index < s0 + kCtcBlock - 1 (read at step+1)
+        const int need = min(s0 + kCtcBlock - 1, Tb - 1);
+        if (avail < need) {
+          int v = 0;
+          for (uint32_t it = 0;; ++it) {
+            if (lane == 0) {
+              int v0, v1 = 0x7fffffff;
+              asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v0) : "r"(prog_prev[0]) : "memory");
+              if (kBeta) asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v1) : "r"(prog_prev[1]) : "memory");
+              v = min(v0, v1);
+            }
+            v = __shfl_sync(0xffffffffu, v, 0);
+            if (v >= need) break;
+            if (it > (1u << 24)) __trap();
+          }
+          avail = v;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kCtcBlock; ++i) {
+        const int step = s0 + i;
+        const bool valid = (unsigned)step < t_lim;
+        const bool ld_ok = (unsigned)(step + kCtcBlock) < t_lim;
+#pragma unroll
+        for (int d = 0; d < kDirs; ++d) {
+          const uint2 cp = q[d][i];
+          load_prob(q[d][i], pin[d], ld_ok);
+          pin[d] += dstep[d];
+          const float pm = __uint_as_float(cp.x);
+          const int pe = (int)cp.y;
+          // previous time step's values of the two lower neighbours
+          float m1 = __shfl_up_sync(0xffffffffu, cm[d], 1);
+          int e1 = __shfl_up_sync(0xffffffffu, ce[d], 1);
+          float m2 = __shfl_up_sync(0xffffffffu, cm[d], 2);
+          int e2 = __shfl_up_sync(0xffffffffu, ce[d], 2);
+          if (has_left) {   // warp-uniform; lanes 0 / 1 take them from the left-hand warp's lanes 30 / 31 (time step - 1)
+            const uint4 sv = seam_in[d][max(step - 1, 0)];
+            const bool any = step > 0;
+            const float a30 = any ? __uint_as_float(sv.x) : 0.f, a31 = any ? __uint_as_float(sv.z) : 0.f;
+            const int x30 = any ? (int)sv.y : kLatZeroExp, x31 = any ? (int)sv.w : kLatZeroExp;
+            m1 = lane == 0 ? a31 : m1;
+            e1 = lane == 0 ? x31 : e1;
+            m2 = lane == 0 ? a30 : (lane == 1 ? a31 : m2);
+            e2 = lane == 0 ? x30 : (lane == 1 ? x31 : e2);
+          } else {
+            m1 = lane == 0 ? 0.f : m1;
+            e1 = lane == 0 ? kLatZeroExp : e1;
+            m2 = lane < 2 ? 0.f : m2;
+            e2 = lane < 2 ? kLatZeroExp : e2;
+          }
+          m2 = skip[d] ? m2 : 0.f;
+          e2 = skip[d] ? e2 : kLatZeroExp;
+          const int E = max(ce[d], max(e1, e2));
+          float x = cm[d] * ctc_pow2(ce[d] - E);
+          x = fmaf(m1, ctc_pow2(e1 - E), x);
+          x = fmaf(m2, ctc_pow2(e2 - E), x);
+          float nm = valid ? x * pm : 0.f;
+          int ne = valid ? E + pe : kLatZeroExp;
+          if (i == kCtcBlock - 1) ctc_normalise(nm, ne);   // growth < 3 x 1.42 per step: 2^17 at most in between
+          ne = max(ne, 2 * kLatZeroExp);
+          if (valid) {
+            LatNum o;
+            o.m = nm;
+            o.e = ne;
+            *pout[d] = o;
+          }
+          pout[d] += dstep[d];
+          cm[d] = nm;
+          ce[d] = ne;
+          if (publishes) {   // warp-uniform: lanes 30 / 31 publish their (normalised) values of this time step
+            float sm = nm;
+            int se = ne;
+            ctc_normalise(sm, se);
+            if (lane >= 30 && step < Tb)   // one predicated 8-byte store per lane: {m30, e30} | {m31, e31}
+              reinterpret_cast<uint2*>(seam_out[d] + step)[lane - 30] = make_uint2(__float_as_uint(sm), (unsigned)se);
+          }
+        }
+      }
+      if (publishes) {
+        const int done = min(s0 + kCtcBlock, Tb);   // time indices < done are in the seam
+        __syncwarp();   // lane 30's seam stores are ordered before lane 31's release
+        if (lane == 31) {
+          asm volatile("fence.acq_rel.cta;" ::: "memory");
+          asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(prog_mine[0]), "r"(done) : "memory");
+          if (kBeta) asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(prog_mine[1]), "r"(done) : "memory");
+        }
+      }
+    }
+  }
+  __syncthreads();   // every alpha_{T-1}(s) of this sample is in global memory
+  if (threadIdx.x == 0) {
+    const LatNum* last = w.alpha + sbase + (int64_t)(Tb - 1) * S;
+    double l = lat_log(last[Sb - 1]);
+    if (Sb > 1) l = log_sum_exp_d(l, lat_log(last[Sb - 2]));
     const double nll = -l;
     w.nll[b] = nll;
     nll_out[b] = (zero_infinity && nll == (double)INFINITY) ? 0.f : (float)nll;
@@ -182,13 +422,13 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const float* __restrict__
   const float* __restrict__ lp = log_probs + ((int64_t)b * T + t) * Vp;
   for (int c = threadIdx.x; c < Vp; c += blockDim.x) occ[c] = 0.f;
   __syncthreads();
-  const double* __restrict__ al = w.alpha + ((int64_t)b * T + t) * S;
-  const double* __restrict__ be = w.beta + ((int64_t)b * T + t) * S;
+  const LatNum* __restrict__ al = w.alpha + ((int64_t)b * T + t) * S;
+  const LatNum* __restrict__ be = w.beta + ((int64_t)b * T + t) * S;
   const int64_t* __restrict__ tg = targets + (int64_t)b * target_stride;
   for (int s = threadIdx.x; s < Sb; s += blockDim.x) {
     const int cls = (s & 1) ? (int)tg[s >> 1] : blank;
     // alpha_t(s) * beta_t(s) / (y_t(cls) * P(l|x)) : posterior mass of state s at time t, in [0,1]
-    const float e = (float)(al[s] + be[s] + nll - (double)__ldg(lp + cls));
+    const float e = (float)(lat_log(al[s]) + lat_log(be[s]) + nll - (double)__ldg(lp + cls));
     if (e > -INFINITY) atomicAdd(occ + cls, expf(e));
   }
   __syncthreads();
@@ -263,6 +503,24 @@ extern "C" int clasr_ctc_loss_fwd(const float* log_probs, const int64_t* targets
   if (rc) return rc;
   CLASR_CHECK_ARG(nll, "ctc_loss_fwd: null nll");
   CtcWs w = ctc_ws_carve(workspace, B, T, max_target_len);
+  cudaStream_t s = (cudaStream_t)stream;
+  // wavefront kernel when a thread per lattice state (2U+1 <= 512: 128 registers each) and the [2][warps][T] seam fit; CLASR_CTC_LATTICE=generic: A/B arm
+  const int warps = (w.S + 31) / 32;
+  const size_t seam_smem = 64 * sizeof(int) + (size_t)2 * warps * T * sizeof(uint4);
+  const char* sel = getenv("CLASR_CTC_LATTICE");
+  if (w.S <= 512 && seam_smem <= 200 * 1024 && !(sel && !strcmp(sel, "generic"))) {
+    auto kern = need_beta ? ctc_lattice_shfl_kernel<true> : ctc_lattice_shfl_kernel<false>;
+    if (seam_smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seam_smem);
+      CLASR_CHECK_ARG(e == cudaSuccess, "ctc_loss_fwd: seam does not fit in shared memory (%zu bytes)", seam_smem);
+    }
+    prof_begin("ctc_lattice", s);
+    kern<<<B, warps * 32, seam_smem, s>>>(log_probs, targets, target_stride, input_lens, target_lens, T, Vp, blank,
+                                          zero_infinity, w, nll);
+    prof_end("ctc_lattice", s);
+    CLASR_CHECK_LAUNCH("ctc_lattice");
+    return CLASR_STATUS_SUCCESS;
+  }
   int threads = ((w.S + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   size_t smem = (size_t)2 * (w.S + 4) * sizeof(double);
@@ -270,10 +528,10 @@ extern "C" int clasr_ctc_loss_fwd(const float* log_probs, const int64_t* targets
     cudaError_t e = cudaFuncSetAttribute(ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     CLASR_CHECK_ARG(e == cudaSuccess, "ctc_loss_fwd: target too long for shared memory (%zu bytes)", smem);
   }
-  prof_begin("ctc_lattice", (cudaStream_t)stream);
-  ctc_lattice_kernel<<<dim3(B, need_beta ? 2 : 1), threads, smem, (cudaStream_t)stream>>>(
+  prof_begin("ctc_lattice", s);
+  ctc_lattice_kernel<<<dim3(B, need_beta ? 2 : 1), threads, smem, s>>>(
       log_probs, targets, target_stride, input_lens, target_lens, T, Vp, blank, zero_infinity, w, nll);
-  prof_end("ctc_lattice", (cudaStream_t)stream);
+  prof_end("ctc_lattice", s);
   CLASR_CHECK_LAUNCH("ctc_lattice");
   return CLASR_STATUS_SUCCESS;
 }
