@@ -65,7 +65,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configs[config-1]")
     ap.add_argument("--mode", default="tcgen05", choices=["tcgen05", "materialised"])
-    ap.add_argument("--precision", default=None, choices=["auto", "bf16x3", "fp16x3", "bf16"],
+    ap.add_argument("--precision", default=None, choices=["auto", "bf16x3", "fp16x3", "fp16m8", "bf16"],
                     help="default: the config's (auto = the module default, fp16x3)")
     ap.add_argument("--backward", default="recompute", choices=["recompute", "stash"],
                     help="recompute (module default): the logits never reach HBM; stash: keep them for the backward pass")
@@ -552,7 +552,7 @@ def main_b200(args):
     main_res = measure(args.backward, B_local, B_global, host, want_e2e=not args.no_e2e)
     wl, step, ins = main_res["wl"], main_res["step"], main_res["ins"]
     precision = main_res["precision"]
-    x3 = precision in ("bf16x3", "fp16x3")
+    x3 = precision in ("bf16x3", "fp16x3", "fp16m8")
 
     # ---------------- per-kernel durations (library-side CUDA events on the launch stream, eager launches) -> roofline
     wl.hybrid.overlap_ctc = False   # per-kernel durations must not include time shared with the side-stream CTC branch

@@ -49,6 +49,12 @@ extern "C" {
                              joint brings W_out, ReLU hidden values and dZ to O(1) with exact power-of-two scales it
                              undoes itself.  Plain GEMM / linear entries apply no scaling: their operands must fit
                              fp16's range. */
+#define CLASR_PREC_FP16M8 3 /* fp16 hi.hi + TWO e4m3 correction terms (hi8.lo8 + lo8.hi8 as dense kind::f8f6f4 MMAs, K = 32
+                             per instruction): 2 issue-equivalents per product instead of 3 in the two backward GEMMs of the
+                             fused joint.  Every operand x is brought to max|x| in [2^13, 2^14) by an exact power of two;
+                             x16 = fp16(x), hi8 = e4m3(x 2^-6), lo8 = e4m3((x - x16) 2^6), so that the three MMAs accumulate
+                             at ONE common scale with no scale factors.  ~1e-5 of max|result| per GEMM (tools/
+                             fp8_const_scale_study.py).  Plain GEMM entries: operands must already be scaled like that. */
 
 CLASR_API int clasr_version(void);
 CLASR_API const char* clasr_last_error(void);

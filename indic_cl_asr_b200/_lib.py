@@ -21,7 +21,7 @@ _lib = None
 
 STATUS_SUCCESS = 0
 ACT = {"relu": 0, "sigmoid": 1, "tanh": 2}
-PREC = {"bf16": 0, "bf16x3": 1, "fp16x3": 2}
+PREC = {"bf16": 0, "bf16x3": 1, "fp16x3": 2, "fp16m8": 3}
 
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 

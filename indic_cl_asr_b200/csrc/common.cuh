@@ -15,9 +15,11 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 void prof_begin(const char* name, cudaStream_t s);
 void prof_end(const char* name, cudaStream_t s);
-static inline bool prec_ok(int p) { return p == CLASR_PREC_BF16 || p == CLASR_PREC_BF16X3 || p == CLASR_PREC_FP16X3; }
-static inline bool prec_x3(int p) { return p == CLASR_PREC_BF16X3 || p == CLASR_PREC_FP16X3; }   // hi/lo split, 3 MMAs
-static inline bool prec_f16(int p) { return p == CLASR_PREC_FP16X3; }                             // operands are fp16
+static inline bool prec_ok(int p) { return p >= CLASR_PREC_BF16 && p <= CLASR_PREC_FP16M8; }
+// hi/lo split (fp32-grade): the joint GEMM itself issues 3 MMAs per product in all of these
+static inline bool prec_x3(int p) { return p == CLASR_PREC_BF16X3 || p == CLASR_PREC_FP16X3 || p == CLASR_PREC_FP16M8; }
+static inline bool prec_f16(int p) { return p == CLASR_PREC_FP16X3 || p == CLASR_PREC_FP16M8; }   // 16-bit operands are fp16
+static inline bool prec_m8(int p) { return p == CLASR_PREC_FP16M8; }   // backward GEMMs: fp16 + 2 e4m3 correction terms
 
 #define CLASR_CHECK_ARG(cond, ...)              \
   do {                                          \

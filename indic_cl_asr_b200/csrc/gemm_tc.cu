@@ -44,7 +44,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   cuuint64_t strides[1] = {row_stride_elems * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  CUresult r = encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                       const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                       : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -64,17 +65,22 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 // ------------------------------------------------------------------------------------------------
 __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t src_ld,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int cols_pad,
-                                  int f16, const float* __restrict__ scale_dev) {
+                                  int f16, const float* __restrict__ scale_dev, uint8_t* __restrict__ hi8,
+                                  uint8_t* __restrict__ lo8) {
   const float scale = scale_dev ? __ldg(scale_dev) : 1.f;   // power of two (exact)
   const int64_t n = rows * (int64_t)cols_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols_pad;
     const int c = (int)(i - r * cols_pad);
     const float x = c < cols ? src[r * src_ld + c] * scale : 0.f;
-    if (f16) {   // the same 2-byte slots hold fp16 (CLASR_PREC_FP16X3)
+    if (f16) {   // the same 2-byte slots hold fp16 (CLASR_PREC_FP16X3 / FP16M8)
       const __half h = __float2half_rn(x);
       reinterpret_cast<__half*>(hi)[i] = h;
       if (lo) reinterpret_cast<__half*>(lo)[i] = __float2half_rn(x - __half2float(h));
+      if (hi8) {   // FP16M8: the e4m3 correction operands (tc::pack_m8)
+        hi8[i] = (uint8_t)__nv_cvt_float_to_fp8(x * 0.015625f, __NV_SATFINITE, __NV_E4M3);
+        lo8[i] = (uint8_t)__nv_cvt_float_to_fp8((x - __half2float(h)) * 64.f, __NV_SATFINITE, __NV_E4M3);
+      }
     } else {
       __nv_bfloat16 h, l;
       tc::split_bf16(x, h, l);
@@ -85,12 +91,13 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t rows, i
 }
 
 int launch_split_bf16(const float* src, int64_t rows, int cols, int64_t src_ld, void* hi, void* lo, int cols_pad,
-                      cudaStream_t s, int f16, const float* scale_dev) {
+                      cudaStream_t s, int f16, const float* scale_dev, void* hi8 = nullptr, void* lo8 = nullptr) {
   const int64_t n = rows * (int64_t)cols_pad;
   int grid = (int)((n + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   if (grid < 1) grid = 1;
-  split_bf16_kernel<<<grid, 256, 0, s>>>(src, rows, cols, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, cols_pad, f16, scale_dev);
+  split_bf16_kernel<<<grid, 256, 0, s>>>(src, rows, cols, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, cols_pad, f16,
+                                         scale_dev, (uint8_t*)hi8, (uint8_t*)lo8);
   CLASR_CHECK_LAUNCH("split_bf16");
   return CLASR_STATUS_SUCCESS;
 }
@@ -330,6 +337,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // i.e. the arithmetic intensity of a 256 x 256 tile at the smem cost of 128 x 128.  The 1-CTA kernel above moves
 // 64 B/clk/SM at full MMA rate in BF16X3 (measured: L2-bound at ~10.8 TB/s); this one 42.7 B/clk/SM.
 // ------------------------------------------------------------------------------------------------
+// kTerms == 4 (CLASR_PREC_FP16M8): a stage holds {fp16, e4m3 hi8, e4m3 lo8} of each operand — 2 + 1 + 1 bytes per element,
+// the same 64 KB as the {hi16, lo16} stage of kTerms == 3:  A16 16 KB | A_h8 8 KB | A_l8 8 KB | B16 16 KB | B_h8 8 KB | B_l8 8 KB
 template <int kTerms>
 struct Gemm2Smem {
   static constexpr int kParts = kTerms == 1 ? 1 : 2;
@@ -344,7 +353,10 @@ struct Gemm2Smem {
 template <int kTerms>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, GemmParams p) {
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const __grid_constant__ CUtensorMap tmA_l8, const __grid_constant__ CUtensorMap tmB_l8, GemmParams p) {
+  // kTerms == 4: tmA_lo / tmB_lo are the e4m3 hi8 maps, tmA_l8 / tmB_l8 the e4m3 lo8 maps
+  constexpr bool kM8 = kTerms == 4;
   using S = Gemm2Smem<kTerms>;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
@@ -386,6 +398,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     tc::prefetch_tmap(&tmA_hi);
     tc::prefetch_tmap(&tmB_hi);
     if (kTerms > 1) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); }
+    if (kM8) { tc::prefetch_tmap(&tmA_l8); tc::prefetch_tmap(&tmB_l8); }
   }
   if (warp == 1 && tc::elect_one()) {
     for (int i = 0; i < S::kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
@@ -418,8 +431,28 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         if (tc::elect_one()) {
           uint8_t* st = smem + stage * S::kStageBytes;
           if (leader) tc::mbar_expect_tx(&full[stage], 2 * S::kStageBytes);
+          if (kM8) {
+            // 8-bit correction operands: K-major = [128 rows][64 B] boxes (64-byte swizzle); MN-major = ONE [64 K rows][128 B]
+            // box (128-byte swizzle) for this CTA's 128 rows of A / 128 columns of B
+            uint8_t* sa8 = st + S::kABytes;                    // A_h8 | A_l8
+            uint8_t* sb8 = st + 2 * S::kABytes + S::kBBytes;   // B_h8 | B_l8
+            if (!p.a_mn) {
+              tc::tma_load_2d_2sm(sa8, &tmA_lo, &full[stage], kb * kBK, m0);
+              tc::tma_load_2d_2sm(sa8 + 8192, &tmA_l8, &full[stage], kb * kBK, m0);
+            } else {
+              tc::tma_load_2d_2sm(sa8, &tmA_lo, &full[stage], m0, kb * kBK);
+              tc::tma_load_2d_2sm(sa8 + 8192, &tmA_l8, &full[stage], m0, kb * kBK);
+            }
+            if (!p.b_mn) {
+              tc::tma_load_2d_2sm(sb8, &tmB_lo, &full[stage], kb * kBK, n0);
+              tc::tma_load_2d_2sm(sb8 + 8192, &tmB_l8, &full[stage], kb * kBK, n0);
+            } else {
+              tc::tma_load_2d_2sm(sb8, &tmB_lo, &full[stage], n0, kb * kBK);
+              tc::tma_load_2d_2sm(sb8 + 8192, &tmB_l8, &full[stage], n0, kb * kBK);
+            }
+          }
 #pragma unroll
-          for (int part = 0; part < S::kParts; ++part) {
+          for (int part = 0; part < (kM8 ? 1 : S::kParts); ++part) {
             const CUtensorMap* ta = part == 0 ? &tmA_hi : &tmA_lo;
             const CUtensorMap* tb = part == 0 ? &tmB_hi : &tmB_lo;
             uint8_t* sa = st + part * S::kABytes;
@@ -488,9 +521,26 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             };
             const uint32_t first = (kb == kb_begin && kk == 0) ? 0u : 1u;
             tc::umma_ss_2sm(d_tmem, adesc(a_hi), bdesc(b_hi), idesc, first);
-            if (kTerms > 1) {
+            if (kTerms == 3) {
               tc::umma_ss_2sm(d_tmem, adesc(a_hi), bdesc(b_lo), idesc, 1u);
               tc::umma_ss_2sm(d_tmem, adesc(a_lo), bdesc(b_hi), idesc, 1u);
+            }
+          }
+          if (kM8) {
+            // the two correction terms as dense e4m3 MMAs, K = 32 each: A_h8 . B_l8 + A_l8 . B_h8.  K advance: 32 B inside
+            // the 64-byte swizzle span (K-major) or four 8-row swizzle atoms = 4096 B (MN-major, 128-byte rows)
+            const uint32_t a_h8 = a_hi + S::kABytes, a_l8 = a_h8 + 8192;
+            const uint32_t b_h8 = a_hi + 2 * S::kABytes + S::kBBytes, b_l8 = b_h8 + 8192;
+#pragma unroll
+            for (int k8 = 0; k8 < kBK / 32; ++k8) {
+              auto a8 = [&](uint32_t base) {
+                return p.a_mn ? tc::make_desc_mnmajor_sw128(base + k8 * 4096, 8192) : tc::make_desc_kmajor_sw64(base + k8 * 32);
+              };
+              auto b8 = [&](uint32_t base) {
+                return p.b_mn ? tc::make_desc_mnmajor_sw128(base + k8 * 4096, 8192) : tc::make_desc_kmajor_sw64(base + k8 * 32);
+              };
+              tc::umma_f8_ss_2sm(d_tmem, a8(a_h8), b8(b_l8), idesc, 1u);
+              tc::umma_f8_ss_2sm(d_tmem, a8(a_l8), b8(b_h8), idesc, 1u);
             }
           }
           tc::umma_commit_2sm(&empty[stage], 0b11);  // both CTAs' ring slots are reusable once these MMAs retire
@@ -570,16 +620,24 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 //   a_mn == 0: A is [M, lda] with K contiguous      a_mn == 1: A is [K, lda] with M contiguous
 //   b_mn == 0: B is [N, ldb] with K contiguous      b_mn == 1: B is [K, ldb] with N contiguous
 // lda / ldb in elements (multiples of 8).  k_splits > 1 requires atomic_add and a zero-initialised C.
+// CLASR_PREC_FP16M8: A_lo / B_lo are the e4m3 hi8 arrays and A_l8 / B_l8 the e4m3 lo8 arrays (one BYTE per element, the
+// same leading dimensions in elements); CTA-pair kernel only.
 int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
                    int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
                    int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias,
-                   const float* alpha_dev, const float* alpha_dev2) {
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+                   const float* alpha_dev, const float* alpha_dev2, const void* A_l8 = nullptr,
+                   const void* B_l8 = nullptr) {
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, ta_l8, tb_l8;
   int rc;
-  const bool x3 = prec_x3(precision);
+  const bool m8 = prec_m8(precision);
+  const bool x3 = prec_x3(precision) && !m8;
+  if (m8 && (!A_l8 || !B_l8)) {
+    set_error("gemm_tc: fp16m8 needs the e4m3 operand arrays");
+    return CLASR_STATUS_INVALID_VALUE;
+  }
   // CTA pairs (256-row tiles) pay off once there are enough rows; CLASR_GEMM_PAIR=0/1 forces the choice (tests)
   static const int force_pair = [] { const char* e = getenv("CLASR_GEMM_PAIR"); return e ? atoi(e) : -1; }();
-  const bool use_pair = force_pair >= 0 ? force_pair != 0 : (M >= 4 * kBM);
+  const bool use_pair = m8 ? true : (force_pair >= 0 ? force_pair != 0 : (M >= 4 * kBM));
   const int b_box = use_pair ? kBN / 2 : kBN;
   auto mk = [&](CUtensorMap* t, const void* base, int64_t ld, int mn, int rows_mn, int box_mn) -> int {
     if (!mn) return make_tmap_bf16_2d(t, base, rows_mn, K, ld, box_mn, kBK);       // [MN rows, K cols]
@@ -593,6 +651,20 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
   } else {
     ta_lo = ta_hi;
     tb_lo = tb_hi;
+  }
+  ta_l8 = ta_hi;
+  tb_l8 = tb_hi;
+  if (m8) {
+    // one byte per element.  K-major: [MN rows, K bytes], box [128 rows][64 B], 64-byte swizzle.  MN-major: [K rows, MN
+    // bytes], box [64 K rows][128 B], 128-byte swizzle (this CTA's 128 rows / 128 columns are one swizzle span).
+    auto mk8 = [&](CUtensorMap* t, const void* base, int64_t ld, int mn, int rows_mn) -> int {
+      if (!mn) return make_tmap_2d(t, base, rows_mn, K, ld, 128, kBK, 1, 64);
+      return make_tmap_2d(t, base, K, rows_mn, ld, kBK, 128, 1, 128);
+    };
+    if ((rc = mk8(&ta_lo, A_lo, lda, a_mn, M))) return rc;
+    if ((rc = mk8(&ta_l8, A_l8, lda, a_mn, M))) return rc;
+    if ((rc = mk8(&tb_lo, B_lo, ldb, b_mn, N))) return rc;
+    if ((rc = mk8(&tb_l8, B_l8, ldb, b_mn, N))) return rc;
   }
   const int kb_total = (K + kBK - 1) / kBK;
   if (k_splits <= 0) {
@@ -627,12 +699,18 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
     const int tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + kBN - 1) / kBN) * k_splits;
     int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
     if (pairs < 1) pairs = 1;
-    if (x3) {
+    if (m8) {
+      cudaFuncSetAttribute(gemm2_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<4>::kTotalBytes);
+      gemm2_tc_kernel<4><<<2 * pairs, kGemmThreads, Gemm2Smem<4>::kTotalBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, ta_l8,
+                                                                                   tb_l8, p);
+    } else if (x3) {
       cudaFuncSetAttribute(gemm2_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<3>::kTotalBytes);
-      gemm2_tc_kernel<3><<<2 * pairs, kGemmThreads, Gemm2Smem<3>::kTotalBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+      gemm2_tc_kernel<3><<<2 * pairs, kGemmThreads, Gemm2Smem<3>::kTotalBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, ta_l8,
+                                                                                   tb_l8, p);
     } else {
       cudaFuncSetAttribute(gemm2_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<1>::kTotalBytes);
-      gemm2_tc_kernel<1><<<2 * pairs, kGemmThreads, Gemm2Smem<1>::kTotalBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+      gemm2_tc_kernel<1><<<2 * pairs, kGemmThreads, Gemm2Smem<1>::kTotalBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, ta_l8,
+                                                                                   tb_l8, p);
     }
     CLASR_CHECK_LAUNCH("gemm2_tc");
     return CLASR_STATUS_SUCCESS;
@@ -655,12 +733,15 @@ int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, co
 using namespace clasr;
 
 static inline int pad8(int k) { return (k + 7) / 8 * 8; }
+static inline int pad16(int k) { return (k + 15) / 16 * 16; }
 
 extern "C" size_t clasr_gemm_workspace_bytes(int M, int N, int K, int precision) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  const size_t parts = prec_x3(precision) ? 2 : 1;
-  // either orientation of either operand fits: rows x pad8(cols)
-  size_t a = ((size_t)pad8(M) * pad8(K) * 2 + 255) / 256 * 256, b = ((size_t)pad8(N) * pad8(K) * 2 + 255) / 256 * 256;
+  const size_t parts = prec_x3(precision) ? 2 : 1;   // fp16m8: fp16 + two e4m3 arrays = the bytes of two 16-bit arrays
+  // either orientation of either operand fits: rows x pad16(cols)
+  size_t a = ((size_t)pad8(M) * pad16(K) * 2 + 255) / 256 * 256, b = ((size_t)pad8(N) * pad16(K) * 2 + 255) / 256 * 256;
+  a = ((size_t)pad16(M) * pad16(K) * 2 + 255) / 256 * 256;
+  b = ((size_t)pad16(N) * pad16(K) * 2 + 255) / 256 * 256;
   return parts * (a + b);
 }
 
@@ -672,26 +753,36 @@ extern "C" int clasr_gemm_ex(const float* A, const float* B, float* C, int M, in
   CLASR_CHECK_ARG(workspace_bytes >= clasr_gemm_workspace_bytes(M, N, K, precision), "gemm: workspace too small");
   CLASR_CHECK_ARG((((uintptr_t)workspace) & 255) == 0, "gemm: workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  const bool x3 = prec_x3(precision);
-  const size_t a_sz = ((size_t)pad8(M) * pad8(K) * 2 + 255) / 256 * 256;
-  const size_t b_sz = ((size_t)pad8(N) * pad8(K) * 2 + 255) / 256 * 256;
+  const bool m8 = prec_m8(precision);
+  const bool x3 = prec_x3(precision) && !m8;
+  // row pitch: 8 elements (16 bytes) for the 16-bit arrays; fp16m8 pads to 16 so that the 1-byte arrays' rows are 16-byte
+  // multiples too (TMA global strides)
+  auto padk = [&](int k) { return m8 ? pad16(k) : pad8(k); };
+  const size_t a_sz = ((size_t)pad16(M) * pad16(K) * 2 + 255) / 256 * 256;
+  const size_t b_sz = ((size_t)pad16(N) * pad16(K) * 2 + 255) / 256 * 256;
   char* w = (char*)workspace;
   void* a_hi = w; w += a_sz;
-  void* a_lo = x3 ? w : nullptr; if (x3) w += a_sz;
+  void* a_lo = (x3 || m8) ? w : nullptr; if (x3 || m8) w += a_sz;      // fp16m8: hi8 in the first half, lo8 in the second
   void* b_hi = w; w += b_sz;
-  void* b_lo = x3 ? w : nullptr;
+  void* b_lo = (x3 || m8) ? w : nullptr;
+  void* a_l8 = m8 ? (char*)a_lo + a_sz / 2 : nullptr;
+  void* b_l8 = m8 ? (char*)b_lo + b_sz / 2 : nullptr;
   // a_trans: A is given as [K, M] row-major; else [M, K].  Same for B with N.
   const int a_rows = a_trans ? K : M, a_cols = a_trans ? M : K;
   const int b_rows = b_trans ? K : N, b_cols = b_trans ? N : K;
   int rc;
-  if ((rc = launch_split_bf16(A, a_rows, a_cols, a_cols, a_hi, a_lo, pad8(a_cols), s, prec_f16(precision), nullptr))) return rc;
-  if ((rc = launch_split_bf16(B, b_rows, b_cols, b_cols, b_hi, b_lo, pad8(b_cols), s, prec_f16(precision), nullptr))) return rc;
+  if ((rc = launch_split_bf16(A, a_rows, a_cols, a_cols, a_hi, m8 ? nullptr : a_lo, padk(a_cols), s, prec_f16(precision),
+                              nullptr, m8 ? a_lo : nullptr, a_l8)))
+    return rc;
+  if ((rc = launch_split_bf16(B, b_rows, b_cols, b_cols, b_hi, m8 ? nullptr : b_lo, padk(b_cols), s, prec_f16(precision),
+                              nullptr, m8 ? b_lo : nullptr, b_l8)))
+    return rc;
   if (k_splits > 1) {
     cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     CLASR_CHECK_ARG(e == cudaSuccess, "gemm: memset failed");
   }
-  return launch_gemm_tc(a_hi, a_lo, pad8(a_cols), a_trans, b_hi, b_lo, pad8(b_cols), b_trans, M, N, K, C, N, precision,
-                        k_splits > 1, k_splits, s, nullptr, nullptr, nullptr, nullptr, nullptr);
+  return launch_gemm_tc(a_hi, a_lo, padk(a_cols), a_trans, b_hi, b_lo, padk(b_cols), b_trans, M, N, K, C, N, precision,
+                        k_splits > 1, k_splits, s, nullptr, nullptr, nullptr, nullptr, nullptr, a_l8, b_l8);
 }
 
 extern "C" int clasr_gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, int precision,
@@ -757,7 +848,7 @@ extern "C" int clasr_linear_fwd(const float* x, const float* w, const float* bia
                                 int precision, void* workspace, size_t workspace_bytes, void* stream) {
   CLASR_CHECK_ARG(x && w && y && workspace, "linear_fwd: null pointer");
   CLASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear_fwd: non-positive dimension");
-  CLASR_CHECK_ARG(prec_ok(precision), "linear_fwd: bad precision");
+  CLASR_CHECK_ARG(prec_ok(precision) && !prec_m8(precision), "linear_fwd: bad precision (fp16m8 is a joint-backward mode)");
   CLASR_CHECK_ARG(workspace_bytes >= linear_ws_bytes(M, N, K, precision), "linear_fwd: workspace too small");
   CLASR_CHECK_ARG((((uintptr_t)workspace) & 255) == 0, "linear_fwd: workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;

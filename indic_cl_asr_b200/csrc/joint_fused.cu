@@ -25,7 +25,7 @@
 namespace clasr {
 
 int launch_split_bf16(const float* src, int64_t rows, int cols, int64_t src_ld, void* hi, void* lo, int cols_pad,
-                      cudaStream_t s, int f16, const float* scale_dev);
+                      cudaStream_t s, int f16, const float* scale_dev, void* hi8 = nullptr, void* lo8 = nullptr);
 
 constexpr int kJM = 128;            // rows (lattice cells) per tile
 constexpr int kJK = 64;             // K block (one 128-byte swizzle span of bf16)
@@ -87,7 +87,15 @@ struct JointFwdParams {
   float* db_acc;              // [Vp] bias gradient: column sums of dZ, accumulated by the pass-2 epilogue (zeroed first)
   int* rows_pad_dev;          // [1] total_tiles * 128 (written by the tile-offset kernel)
   // ---- kMode 3 (forward that keeps the logits for the backward): z = logits + bias, fp32, compact tile-row order
-  int f16;                    // 16-bit operands are fp16 instead of bf16 (CLASR_PREC_FP16X3)
+  int f16;                    // 16-bit operands are fp16 instead of bf16 (CLASR_PREC_FP16X3 / FP16M8)
+  // CLASR_PREC_FP16M8: the operands of the two backward GEMMs leave as {fp16, e4m3 hi8, e4m3 lo8} (tc::pack_m8) instead of
+  // {fp16 hi, fp16 lo}: dz_h8 / dz_l8 [rows_pad, ldz] and hid_h8 / hid_l8 [rows_pad, ldh], one byte per element, occupy
+  // the memory of dz_lo / hid_lo.  Every operand is scaled to max < 2^14 (gscale / wscale / ascale).
+  int m8;
+  uint8_t* dz_h8;
+  uint8_t* dz_l8;
+  uint8_t* hid_h8;
+  uint8_t* hid_l8;
   const float* gscale;        // fp16 only: [2] = {S, 1/S}, the power-of-two pre-scale of dZ (joint_gscale_kernel), or null
   const float* wscale;        // fp16 only: {Sw, 1/Sw, Sa, 1/Sa, 1/(Sw Sa)}: pre-scales of W_out (max|W| Sw ~ 1) and of the
                               // hidden activations (ReLU only, else 1); logits = acc / (Sw Sa) + b
@@ -271,8 +279,10 @@ static int launch_joint_gscale(const float* g, int64_t n, float headroom, float*
 
 // fp16 operands: gs[2..3] = {Sw, 1/Sw} (written before); ReLU: gs[16..17], gs[18..19] = scales of max|f|, max|g| ->
 // hidden values relu(f + g) <= max|f| + max|g| <= 2 max(1/Sf, 1/Sg): Sa = min(Sf, Sg) / 2.  Writes gs[4..6].
-__global__ void joint_ascale_kernel(float* __restrict__ gs, int relu) {
-  const float sa = relu ? 0.5f * fminf(gs[16], gs[18]) : 1.f;
+// `extra` (a power of two): 1, or for CLASR_PREC_FP16M8 the factor that brings the bounded hidden activations (times the
+// dropout rescale 1 / (1 - p)) to just below 2^14.
+__global__ void joint_ascale_kernel(float* __restrict__ gs, int relu, float extra) {
+  const float sa = (relu ? 0.5f * fminf(gs[16], gs[18]) : 1.f) * extra;
   gs[4] = sa;
   gs[5] = 1.f / sa;          // exact: power of two
   gs[6] = gs[3] * gs[5];
@@ -640,6 +650,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         } else {
           // pass 2: 16-column pieces (register budget: 96 per thread in the 640-thread layout), branch-free per element;
           // every special case is a warp-uniform branch around a whole piece
+          uint32_t m8_h8[4] = {0u, 0u, 0u, 0u}, m8_l8[4] = {0u, 0u, 0u, 0u};   // FP16M8: the even piece of a pair
 #pragma unroll 1
           for (int c = 0; tile_ok && c * 16 < ncols; ++c) {
             uint32_t rr[16];
@@ -698,7 +709,30 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
                 if (col0 + j == p.blank) zb_ = gr[j];
               p.dzb[grow] = zb_;
             }
-            {  // ldz is a multiple of 16: the piece is one whole 32-byte sector of the hi (and lo) operand row
+            if (p.m8) {
+              // FP16M8 operands: fp16 (one 32-byte sector) + e4m3 hi8 / lo8 (16 bytes each per piece: two consecutive
+              // pieces are stored together as one sector; ldz is a multiple of 32 in this mode)
+              uint32_t ph[8];
+              uint32_t h8w[4], l8w[4];
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                uint16_t ha, la, hb, lb;
+                tc::pack_m8(gr[4 * j4], gr[4 * j4 + 1], ph[2 * j4], ha, la);
+                tc::pack_m8(gr[4 * j4 + 2], gr[4 * j4 + 3], ph[2 * j4 + 1], hb, lb);
+                h8w[j4] = (uint32_t)ha | ((uint32_t)hb << 16);
+                l8w[j4] = (uint32_t)la | ((uint32_t)lb << 16);
+              }
+              st_global_256(p.dz_hi + grow * p.ldz + col0, ph);
+              if (c & 1) {
+                const uint32_t vh[8] = {m8_h8[0], m8_h8[1], m8_h8[2], m8_h8[3], h8w[0], h8w[1], h8w[2], h8w[3]};
+                const uint32_t vl[8] = {m8_l8[0], m8_l8[1], m8_l8[2], m8_l8[3], l8w[0], l8w[1], l8w[2], l8w[3]};
+                st_global_256(p.dz_h8 + grow * p.ldz + col0 - 16, vh);
+                st_global_256(p.dz_l8 + grow * p.ldz + col0 - 16, vl);
+              } else {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) { m8_h8[j4] = h8w[j4]; m8_l8[j4] = l8w[j4]; }
+              }
+            } else {  // ldz is a multiple of 16: the piece is one whole 32-byte sector of the hi (and lo) operand row
               uint32_t ph[8], pl[8];
 #pragma unroll
               for (int j2 = 0; j2 < 8; ++j2) {
@@ -792,7 +826,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       }
       __syncwarp();
       float2 fa[kBatch], ga[kBatch], fb[kBatch], gb[kBatch];
-      const float s_a = (kAct == CLASR_ACT_RELU && p.ascale) ? __ldg(p.ascale) : 1.f;
+      const float s_a = p.ascale ? __ldg(p.ascale) : 1.f;
       const float* __restrict__ ef_lane = p.ef + half * 32 + 2 * c;   // this lane's two features of a row
       const float* __restrict__ eg_lane = p.eg + half * 32 + 2 * c;
       auto load_batch = [&](int kb, int batch, float2 (&fo)[kBatch], float2 (&go_)[kBatch]) {
@@ -817,8 +851,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           const int i = batch * kBatch + j;
           float h0 = joint_combine<kAct>(fi[j].x, gi[j].x);
           float h1 = joint_combine<kAct>(fi[j].y, gi[j].y);
-          if (kAct == CLASR_ACT_RELU) {  // fp16 operands: unbounded ReLU values are brought to <= 1 (s_a = 1 otherwise)
-            h0 *= s_a;
+          if (kAct == CLASR_ACT_RELU || p.m8) {  // fp16 operands: unbounded ReLU values are brought to <= 1; FP16M8: every
+            h0 *= s_a;                           // activation to < 2^14 (s_a = 1 otherwise)
             h1 *= s_a;
           }
           if (p.drop_thresh) {  // warp-uniform
@@ -833,6 +867,18 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           const int rimm = (i & 3) + 8 * (i >> 2);  // compile-time part of the row index
           tc::st_shared_u32(ablk + aoff[i & 3] + rimm * 128, hw);
           if (kTerms > 1) tc::st_shared_u32(stg + soff[i & 3] + 8 * (i >> 2) * 64, lw);
+          if (kMode >= 1 && p.m8 && tile_ok) {
+            // FP16M8: the e4m3 operands of the dW GEMM go straight to global memory — a half-warp holds 32 consecutive k
+            // of one row, so each 16-bit store instruction writes one full 32-byte sector per half-warp
+            const __half2 hh = *reinterpret_cast<const __half2*>(&hw);
+            const uint16_t h8 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(h0 * 0.015625f, h1 * 0.015625f),
+                                                                  __NV_SATFINITE, __NV_E4M3);
+            const uint16_t l8 = (uint16_t)__nv_cvt_float2_to_fp8x2(
+                make_float2((h0 - __low2float(hh)) * 64.f, (h1 - __high2float(hh)) * 64.f), __NV_SATFINITE, __NV_E4M3);
+            const int64_t e = ((int64_t)tile * kJM + q * 32 + rimm + 4 * hs) * p.ldh + kb * kJK + half * 32 + 2 * c;
+            *reinterpret_cast<uint16_t*>(p.hid_h8 + e) = h8;
+            *reinterpret_cast<uint16_t*>(p.hid_l8 + e) = l8;
+          }
         }
       };
       load_batch(0, 0, fa, ga);
@@ -876,7 +922,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::kAloCol + kb * (kJK / 2) + half * 16;
           tc::tmem_st8(taddr, v0);
           tc::tmem_st8(taddr + 8, v1);
-          if (kMode >= 1 && tile_ok) {  // pass 2: the lo halves of this lane's row (32 k = 64 contiguous bytes) for dW
+          if (kMode >= 1 && tile_ok && !p.m8) {  // pass 2: the lo halves of this lane's row (32 k = 64 contiguous bytes) for dW
             __nv_bfloat16* dst = p.hid_lo + ((int64_t)tile * kJM + q * 32 + lane) * p.ldh + kb * kJK + half * 32;
             st_global_256(dst, v0);
             st_global_256(dst + 16, v1);
@@ -1052,12 +1098,23 @@ __global__ void __maxnreg__(CLASR_DZ_REGS) joint_dz_kernel(JointFwdParams p, int
           uint4 ph, pl;
           uint32_t* phw = reinterpret_cast<uint32_t*>(&ph);
           uint32_t* plw = reinterpret_cast<uint32_t*>(&pl);
+          if (p.m8) {   // FP16M8: fp16 + e4m3 hi8 / lo8 (8 bytes each; a warp's 32 column groups are 256 contiguous bytes)
+            uint16_t h8[4], l8[4];
 #pragma unroll
-          for (int j2 = 0; j2 < 4; ++j2) {
-            tc::pack_hi_lo(gr[2 * j2], gr[2 * j2 + 1], p.f16, phw[j2], plw[j2]);
+            for (int j2 = 0; j2 < 4; ++j2) tc::pack_m8(gr[2 * j2], gr[2 * j2 + 1], phw[j2], h8[j2], l8[j2]);
+            *reinterpret_cast<uint4*>(p.dz_hi + grow * p.ldz + col0) = ph;
+            *reinterpret_cast<uint2*>(p.dz_h8 + grow * p.ldz + col0) =
+                make_uint2((uint32_t)h8[0] | ((uint32_t)h8[1] << 16), (uint32_t)h8[2] | ((uint32_t)h8[3] << 16));
+            *reinterpret_cast<uint2*>(p.dz_l8 + grow * p.ldz + col0) =
+                make_uint2((uint32_t)l8[0] | ((uint32_t)l8[1] << 16), (uint32_t)l8[2] | ((uint32_t)l8[3] << 16));
+          } else {
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) {
+              tc::pack_hi_lo(gr[2 * j2], gr[2 * j2 + 1], p.f16, phw[j2], plw[j2]);
+            }
+            *reinterpret_cast<uint4*>(p.dz_hi + grow * p.ldz + col0) = ph;
+            if (kTerms > 1) *reinterpret_cast<uint4*>(p.dz_lo + grow * p.ldz + col0) = pl;
           }
-          *reinterpret_cast<uint4*>(p.dz_hi + grow * p.ldz + col0) = ph;
-          if (kTerms > 1) *reinterpret_cast<uint4*>(p.dz_lo + grow * p.ldz + col0) = pl;
         }
       }
     }
@@ -1267,7 +1324,8 @@ __global__ void __launch_bounds__(256) joint_dfg_fused_kernel(const float* __res
 int launch_gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo,
                    int64_t ldb, int b_mn, int M, int N, int K, float* C, int64_t ldc, int precision, int atomic_add,
                    int k_splits, cudaStream_t s, const int* m_dev, const int* k_dev, const float* bias = nullptr,
-                   const float* alpha_dev = nullptr, const float* alpha_dev2 = nullptr);
+                   const float* alpha_dev = nullptr, const float* alpha_dev2 = nullptr, const void* A_l8 = nullptr,
+                   const void* B_l8 = nullptr);
 
 // ------------------------------------------------------------------------------------------------
 // workspace layout of the fused path
@@ -1276,6 +1334,8 @@ struct JointWs {
   void* lattice;
   void* w_hi;
   void* w_lo;
+  void* w_h8;          // FP16M8 only
+  void* w_l8;
   int* tile_offsets;   // [B+1], then [1] rows_pad
   float* gscale;       // [2] fp16 operands: power-of-two pre-scale of dZ and its inverse
   float* bias_pad;     // [round_up(Vp,32)+32]
@@ -1301,7 +1361,8 @@ static inline JointBwdScratch joint_bwd_scratch_carve(void* base, int B, int T, 
   JointBwdScratch sc;
   const bool x3 = prec_x3(precision);
   sc.rows_cap = (int64_t)B * ((((int64_t)T * U1) + kJM - 1) / kJM) * kJM;
-  sc.ldz = (Vp + 15) / 16 * 16;
+  // FP16M8: the one-byte operand rows must start on 32-byte boundaries too (256-bit stores of two 16-column pieces)
+  sc.ldz = prec_m8(precision) ? (Vp + 31) / 32 * 32 : (Vp + 15) / 16 * 16;
   sc.ldh = H;
   char* p = (char*)base;
   size_t off = 0;
@@ -1351,6 +1412,9 @@ static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, in
   const size_t wbytes = ((size_t)j.vp_pad * H * 2 + 255) / 256 * 256;
   j.w_hi = p + off; off += wbytes;
   j.w_lo = p + off; off += prec_x3(precision) ? wbytes : 0;
+  j.w_h8 = p + off;                       // FP16M8: e4m3 hi8 | lo8 of W_out (one byte per element each)
+  j.w_l8 = p + off + wbytes / 2;
+  off += prec_m8(precision) ? wbytes : 0;
   j.tile_offsets = (int*)(p + off);
   off += ((size_t)(B + 2) * sizeof(int) + 255) / 256 * 256;
   j.gscale = (float*)(p + off);
@@ -1373,6 +1437,16 @@ static int set_dropout(JointFwdParams& p, float dropout_p, uint64_t seed) {
   p.drop_seed_a = (uint32_t)seed;
   p.drop_seed_b = (uint32_t)(seed >> 32);
   return CLASR_STATUS_SUCCESS;
+}
+
+// CLASR_PREC_FP16M8 operand scales: headroom factor that moves a "max -> ~1" scale to "max -> just below 2^14", and the
+// activation scale (bounded activations x dropout rescale 1 / (1 - p) -> below 2^14)
+static inline float m8_headroom(bool m8) { return m8 ? ldexpf(1.f, -14) : 1.f; }
+static inline float m8_act_scale(bool m8, float dropout_p) {
+  if (!m8) return 1.f;
+  int e = 0;
+  if (dropout_p > 0.f) frexpf(1.f / (1.f - dropout_p), &e);   // 1/(1-p) = f 2^e, f in [0.5, 1)
+  return ldexpf(1.f, 14 - e);
 }
 
 // CLASR_JOINT_PAIR=0/1 selects the 1-CTA / CTA-pair variant (default: pairs)
@@ -1492,18 +1566,21 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   const bool x3 = prec_x3(precision);
   // W_out [Vp,H] fp32 -> bf16 hi[,lo] (rows beyond Vp are never read: TMA zero-fills out-of-bounds rows)
   const float* wscale = nullptr;
+  const bool m8 = prec_m8(precision);
   if (prec_f16(precision)) {   // fp16 operands: W_out is split after a power-of-two scale that brings max|W| to ~1
-    if ((rc = launch_joint_gscale(w_out, (int64_t)Vp * H, kScaleHeadroom, jw.gscale + 2, s))) return rc;
+    // (FP16M8: every operand to just below 2^14, see include/clasr_b200.h)
+    if ((rc = launch_joint_gscale(w_out, (int64_t)Vp * H, kScaleHeadroom * m8_headroom(m8), jw.gscale + 2, s))) return rc;
     const int relu = activation == CLASR_ACT_RELU;
     if (relu) {
       if ((rc = launch_joint_gscale(f, (int64_t)B * T * H, 1.f, jw.gscale + 16, s))) return rc;
       if ((rc = launch_joint_gscale(g, (int64_t)B * U1 * H, 1.f, jw.gscale + 18, s))) return rc;
     }
-    joint_ascale_kernel<<<1, 1, 0, s>>>(jw.gscale, relu);
+    joint_ascale_kernel<<<1, 1, 0, s>>>(jw.gscale, relu, m8_act_scale(m8, dropout_p));
     CLASR_CHECK_LAUNCH("joint_ascale");
     wscale = jw.gscale + 2;
   }
-  if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s, prec_f16(precision), wscale)))
+  if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s, prec_f16(precision), wscale,
+                              m8 ? jw.w_h8 : nullptr, m8 ? jw.w_l8 : nullptr)))
     return rc;
   joint_tile_offsets_kernel<<<1, 256, 0, s>>>(act_lens, label_lens, B, jw.tile_offsets, jw.tile_offsets + B + 1,
                                               b_out, Vp, jw.bias_pad);
@@ -1515,8 +1592,9 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   p.tile_offsets = jw.tile_offsets;
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
   p.f16 = prec_f16(precision) ? 1 : 0;
+  p.m8 = m8 ? 1 : 0;
   p.wscale = p.f16 ? jw.gscale + 2 : nullptr;   // written by the forward call
-  p.ascale = (p.f16 && activation == CLASR_ACT_RELU) ? jw.gscale + 4 : nullptr;
+  p.ascale = (p.f16 && (activation == CLASR_ACT_RELU || m8)) ? jw.gscale + 4 : nullptr;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.sumsq = sumsq;
   if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;
@@ -1535,6 +1613,7 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
     CLASR_CHECK_ARG(st.rows_cap < 2147483647LL, "joint_rnnt_fwd: too many lattice cells");
     p.zbuf = st.z; p.ldzf = st.ldzf;
     p.hid_hi = (__nv_bfloat16*)st.hid_hi; p.hid_lo = (__nv_bfloat16*)st.hid_lo; p.ldh = H;
+    p.hid_h8 = (uint8_t*)st.hid_lo; p.hid_l8 = (uint8_t*)st.hid_lo + (size_t)st.rows_cap * H;   // FP16M8: in hid_lo's place
     CUtensorMap t_hid, t_z;
     if ((rc = make_tmap_bf16_2d(&t_hid, st.hid_hi, (uint64_t)st.rows_cap, H, H, kJM, kJK))) return rc;
     // TMA-store view of z: [rows_cap, ldzf] fp32, box = 32 rows x 8 columns (32-byte rows, 32-byte swizzle)
@@ -1597,14 +1676,19 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   p.bias = b_out; p.bias_pad = jw.bias_pad; p.labels = labels; p.act_lens = act_lens; p.label_lens = label_lens;
   p.tile_offsets = jw.tile_offsets;
   p.B = B; p.T = T; p.U1 = U1; p.H = H; p.Vp = Vp; p.blank = blank;
+  const bool m8 = prec_m8(precision);
   p.f16 = prec_f16(precision) ? 1 : 0;
+  p.m8 = m8 ? 1 : 0;
   p.wscale = p.f16 ? jw.gscale + 2 : nullptr;   // written by the forward call
-  p.ascale = (p.f16 && activation == CLASR_ACT_RELU) ? jw.gscale + 4 : nullptr;
+  p.ascale = (p.f16 && (activation == CLASR_ACT_RELU || m8)) ? jw.gscale + 4 : nullptr;
   p.w = lattice_ws_carve(jw.lattice, B, T, U1);
   p.grad_out = grad_out; p.grad_cells = grad_cells; p.fastemit_lambda = fastemit_lambda; p.clamp = clamp;
   if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;
   p.dz_hi = (__nv_bfloat16*)sc.dz_hi; p.dz_lo = (__nv_bfloat16*)sc.dz_lo; p.ldz = sc.ldz;
   p.hid_hi = (__nv_bfloat16*)sc.hid_hi; p.hid_lo = (__nv_bfloat16*)sc.hid_lo; p.ldh = sc.ldh;
+  // FP16M8: e4m3 hi8 | lo8 (one byte per element each) in the memory of the 16-bit lo arrays
+  p.dz_h8 = (uint8_t*)sc.dz_lo; p.dz_l8 = (uint8_t*)sc.dz_lo + (size_t)sc.rows_cap * sc.ldz;
+  p.hid_h8 = (uint8_t*)sc.hid_lo; p.hid_l8 = (uint8_t*)sc.hid_lo + (size_t)sc.rows_cap * sc.ldh;
   p.rows_pad_dev = rows_pad_dev;
   // blank == last class (NeMo: RNNTLoss._blank = num_classes): its dW row comes from joint_dfg, the GEMM covers V rows
   const bool blank_split = blank == Vp - 1 && Vp > 1 && (H % 32) == 0 &&
@@ -1612,8 +1696,8 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   p.dzb = blank_split ? sc.dzb : nullptr;
   p.db_acc = d_b_out;
   if (p.f16 && (mode == 2 || grad_out)) {   // fp16 operands: pre-scale dZ to O(1) (see joint_gscale_kernel)
-    rc = mode == 1 ? launch_joint_gscale(grad_out, B, (1.f + fastemit_lambda) * kScaleHeadroom, jw.gscale, s)
-                   : launch_joint_gscale(grad_cells, (int64_t)B * T * U1, 128.f, jw.gscale, s);
+    rc = mode == 1 ? launch_joint_gscale(grad_out, B, (1.f + fastemit_lambda) * kScaleHeadroom * m8_headroom(m8), jw.gscale, s)
+                   : launch_joint_gscale(grad_cells, (int64_t)B * T * U1, 128.f * m8_headroom(m8), jw.gscale, s);
     if (rc) return rc;
     p.gscale = jw.gscale;
   }
@@ -1632,12 +1716,14 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
     tw_lo = tw_hi;
   }
   const void* hid_hi = sc.hid_hi;
-  const void* hid_lo = sc.hid_lo;
+  const void* hid_lo = sc.hid_lo;            // FP16M8: the e4m3 hi8 array, lo8 follows at rows_cap * H bytes
+  const void* hid_l8 = p.hid_l8;
   if (stash) {
     // the forward call kept z and Hid (kMode 3): dZ is one streaming sweep over z
     JointStash st = joint_stash_carve(stash, B, T, U1, H, Vp, precision);
     p.zbuf = st.z; p.ldzf = st.ldzf;
     hid_hi = st.hid_hi; hid_lo = st.hid_lo;
+    hid_l8 = (const uint8_t*)st.hid_lo + (size_t)st.rows_cap * H;
     prof_begin("joint_dz_sweep", s);
     if (mode == 1) rc = x3 ? launch_joint_dz<3, 1>(p, s) : launch_joint_dz<1, 1>(p, s);
     else rc = x3 ? launch_joint_dz<3, 2>(p, s) : launch_joint_dz<1, 2>(p, s);
@@ -1662,15 +1748,17 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   prof_begin("gemm_dhid", s);
   // blank_split: the blank column (class V, the only one past a multiple of 64 in K when V = 1024) would cost a whole
   // extra K block; its rank-1 contribution dZ[., blank] x W[blank, :] is added by joint_dfg from dzb instead
-  if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 0, jw.w_hi, jw.w_lo, H, 1, (int)sc.rows_cap, H,
-                           blank_split ? Vp - 1 : Vp, sc.dhid, H, precision, 0, 1, s, rows_pad_dev, nullptr)))
+  if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 0, jw.w_hi, m8 ? jw.w_h8 : jw.w_lo, H, 1, (int)sc.rows_cap, H,
+                           blank_split ? Vp - 1 : Vp, sc.dhid, H, precision, 0, 1, s, rows_pad_dev, nullptr, nullptr,
+                           nullptr, nullptr, m8 ? p.dz_l8 : nullptr, m8 ? jw.w_l8 : nullptr)))
     return rc;
   prof_end("gemm_dhid", s);
   // ---- pass 2c: dW[Vp, H] = dZ^T . Hid       (both operands MN-major, split-K over the rows, fp32 atomics)
   prof_begin("gemm_dw", s);
   if ((rc = launch_gemm_tc(sc.dz_hi, sc.dz_lo, sc.ldz, 1, hid_hi, hid_lo, sc.ldh, 1, blank_split ? Vp - 1 : Vp, H,
                            (int)sc.rows_cap, d_w_out, H, precision, 1, /*auto split-K*/ 0, s, nullptr, rows_pad_dev,
-                           nullptr, p.gscale ? p.gscale + 1 : nullptr, p.ascale ? p.ascale + 1 : nullptr)))
+                           nullptr, p.gscale ? p.gscale + 1 : nullptr, p.ascale ? p.ascale + 1 : nullptr,
+                           m8 ? p.dz_l8 : nullptr, m8 ? hid_l8 : nullptr)))
     return rc;
   prof_end("gemm_dw", s);
   // ---- pass 2d: through the activation and the broadcast add: d_f = sum_u, d_g = sum_t of dHid * act'(f+g)

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -273,6 +274,26 @@ __device__ __forceinline__ void umma_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Dense 8-bit MMAs (kind::f8f6f4, e4m3 x e4m3 -> fp32, K = 32 per instruction): same operand forms as kind::f16; the
+// instruction descriptor has the layout of make_idesc_16 with a_format = b_format = 0 (E4M3).
+__device__ __forceinline__ void umma_f8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the barrier at this smem offset in the CTAs selected by cta_mask once all prior MMAs have completed
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -300,6 +321,17 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+// K-major operand, 64-byte swizzle: rows of 64 BYTES (64 e4m3 = one K block of the 8-bit correction operands), 8-row
+// groups of 512 B.  layout_type [61,64) = 4 (SWIZZLE_64B), SBO = 512 >> 4.  A K = 32 MMA advances the start by 32 B.
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
   return d;
 }
 // MN-major operand, 128-byte swizzle: the tile is stored as [K rows][64 MN elements = 128 B]; 8 K-rows form a
@@ -340,6 +372,16 @@ __device__ __forceinline__ void pack_hi_lo(float a, float b, int f16, uint32_t& 
     hi = *reinterpret_cast<const uint32_t*>(&hh);
     lo = *reinterpret_cast<const uint32_t*>(&ll);
   }
+}
+
+// FP16M8 operand triple of a pair of values that are already scaled to |x| < 2^14 (include/clasr_b200.h):
+//   h16 = fp16 pair, h8 = e4m3(x 2^-6) pair, l8 = e4m3((x - fp16(x)) 2^6) pair   (16-bit results: first value in the low byte)
+__device__ __forceinline__ void pack_m8(float a, float b, uint32_t& h16, uint16_t& h8, uint16_t& l8) {
+  const __half2 hh = __floats2half2_rn(a, b);
+  h16 = *reinterpret_cast<const uint32_t*>(&hh);
+  h8 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(a * 0.015625f, b * 0.015625f), __NV_SATFINITE, __NV_E4M3);
+  l8 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2((a - __low2float(hh)) * 64.f, (b - __high2float(hh)) * 64.f),
+                                          __NV_SATFINITE, __NV_E4M3);
 }
 
 // Byte offset of element (row, k) inside a K-major SWIZZLE_128B tile whose rows are 64 bf16 (128 B) wide and

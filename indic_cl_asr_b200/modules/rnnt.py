@@ -194,7 +194,7 @@ class RNNTJoint(torch.nn.Module):
         if x.is_cuda and str(self.activation).lower() != "relu":
             from ..linear import linear_x3
             # the projections' upstream gradients are not pre-scaled: they keep the range-safe bf16 split
-            return linear_x3(x, lin.weight, lin.bias, "bf16x3" if self.precision == "fp16x3" else self.precision)
+            return linear_x3(x, lin.weight, lin.bias, "bf16x3" if self.precision in ("fp16x3", "fp16m8") else self.precision)
         return lin(x)
 
     def project_encoder(self, encoder_output: torch.Tensor) -> torch.Tensor:

@@ -81,9 +81,10 @@ def test_full_size_gradients_and_properties(precision, stash_gib):
     assert torch.isfinite(d_W).all() and d_b[V].item() < 0.0
 
 
+@pytest.mark.parametrize("precision", ["fp16x3", "fp16m8"])
 @pytest.mark.parametrize("stash_gib", [None, 48.0], ids=["recompute", "stash"])
 @pytest.mark.parametrize("act", ["tanh", "relu"])
-def test_config2_default_precision_vs_fp64_oracle(act, stash_gib):
+def test_config2_default_precision_vs_fp64_oracle(act, stash_gib, precision):
     """BASELINE.json configs[1] shape (T=250, U=100, V=1024, H=640), the DEFAULT precision (fp16x3), both backward
     modes, tanh and the shipped checkpoint's ReLU — against the fp64 ORACLE itself (oracle/joint_oracle.py +
     rnnt_oracle.py), not against this repo's materialised path.  Two utterances (one full length, one ragged) keep the
@@ -101,7 +102,7 @@ def test_config2_default_precision_vs_fp64_oracle(act, stash_gib):
     al, ll = torch.tensor([T, 173]), torch.tensor([U, 61])
     wts = torch.tensor([0.35, 0.65])          # mean_batch x loss weight: upstream gradients well below 1
     leaves = [x.to(DEV).requires_grad_(True) for x in (f, gg, W, b)]
-    costs = fused_joint_rnnt_loss(*leaves, lab.to(DEV), al.to(DEV), ll.to(DEV), V, act, "fp16x3", stash_gib=stash_gib)
+    costs = fused_joint_rnnt_loss(*leaves, lab.to(DEV), al.to(DEV), ll.to(DEV), V, act, precision, stash_gib=stash_gib)
     (costs * wts.to(DEV)).sum().backward()
     torch.cuda.synchronize()
     ref_leaves = [x.double().requires_grad_(True) for x in (f, gg, W, b)]

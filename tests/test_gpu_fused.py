@@ -10,8 +10,9 @@ from oracle import joint_oracle
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-LOSS_TOL = {"bf16x3": 1e-5, "fp16x3": 1e-5, "bf16": 2e-3}
-GRAD_TOL = {"bf16x3": 1e-4, "fp16x3": 2e-5, "bf16": 3e-2}
+# fp16m8: fp16x3 forward (same costs), backward GEMMs as fp16 + two e4m3 correction terms: north_star's 1e-4 with margin
+LOSS_TOL = {"bf16x3": 1e-5, "fp16x3": 1e-5, "bf16": 2e-3, "fp16m8": 1e-5}
+GRAD_TOL = {"bf16x3": 1e-4, "fp16x3": 2e-5, "bf16": 3e-2, "fp16m8": 6e-5}
 
 
 def make(B, T, U, V, H, seed, ragged=True):
@@ -55,7 +56,7 @@ def test_forward_costs_and_sumsq(B, T, U, V, H, act, precision):
         assert rel_err(got[i, :Tb, :Ub1], ref_ssq[i, :Tb, :Ub1]) <= (2e-2 if precision == "bf16" else 1e-5)
 
 
-@pytest.mark.parametrize("precision", ["bf16", "bf16x3", "fp16x3"])
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3", "fp16x3", "fp16m8"])
 @pytest.mark.parametrize("B,T,U,V,H,act", [(2, 9, 4, 20, 64, "tanh"), (3, 40, 17, 256, 128, "relu"),
                                            (2, 33, 12, 1024, 640, "tanh")])
 @pytest.mark.parametrize("stash", ["48", "0"], ids=["stash", "recompute"])

@@ -63,3 +63,32 @@ def test_gemm_transposed_operands_and_split_k(M, N, K, splits, a_trans, b_trans,
     assert torch.isfinite(C).all()
     err = (C - ref).abs().max().item() / ref.abs().max().item()
     assert err <= tol, err
+
+
+def _to_m8_range(x):
+    """fp16m8 operands must sit at max|x| in [2^13, 2^14) (include/clasr_b200.h): exact power-of-two scale."""
+    e = int(np.ceil(np.log2(float(x.abs().max()))))
+    if 2.0 ** e == float(x.abs().max()):
+        e += 1
+    return x * 2.0 ** (14 - e), 2.0 ** (14 - e)
+
+
+@pytest.mark.parametrize("a_trans,b_trans", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K,splits", [(256, 256, 64, 1), (512, 640, 1088, 1), (1024, 640, 4096, 7), (300, 200, 500, 1),
+                                          (128, 256, 64, 1)])
+def test_gemm_fp16m8(M, N, K, splits, a_trans, b_trans):
+    """fp16 hi.hi + two dense e4m3 correction MMAs (kind::f8f6f4) in the CTA-pair GEMM, every operand orientation the
+    joint backward uses (dHid: A K-major, B MN-major; dW: both MN-major) plus the plain NT form: ~1e-5 of max|C|
+    (tools/fp8_const_scale_study.py), 30x better than a single fp16 pass."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g) / K ** 0.5
+    A, sa = _to_m8_range(A)
+    B, sb = _to_m8_range(B)
+    Ain = (A.t().contiguous() if a_trans else A).to(DEV)
+    Bin = (B.t().contiguous() if b_trans else B).to(DEV)
+    C = gemm_ex(Ain, Bin, M, N, K, a_trans, b_trans, splits, "fp16m8").cpu().double()
+    ref = A.double() @ B.double().t()
+    assert torch.isfinite(C).all()
+    err = (C - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 3e-5, err
