@@ -41,10 +41,15 @@ constexpr int kJStages = 2;
 // of shared memory per 48 clocks instead of 4 + 3 KB (the 1-CTA N = 96 MMA is smem-bandwidth-bound: r01b profile).
 template <int kTerms, int kPair, int kStash = 0>
 struct JointCfg {
+  // kTerms: 1 = one 16-bit MMA per product; 3 = hi/lo split, three 16-bit MMAs; 4 = FP16M8: one fp16 MMA (K = 16) plus
+  // two dense e4m3 correction MMAs (K = 32): A_hi8 . W_lo8 + A_lo8 . W_hi8 — 8 instead of 12 MMAs per 64-wide K block
   static constexpr int kBN = kTerms == 1 ? 256 : 96;          // accumulator tile width (TMEM columns)
-  static constexpr int kParts = kTerms == 1 ? 1 : 2;          // W parts streamed per stage (hi[,lo])
+  static constexpr int kParts = kTerms == 1 ? 1 : 2;          // W bytes streamed per stage = kParts 16-bit tiles (kTerms 4:
+                                                              // fp16 | e4m3 hi8 | e4m3 lo8 = the bytes of two 16-bit tiles)
   static constexpr int kAccCols = 2 * kBN;                    // two accumulator stages
-  static constexpr int kAloCol = kAccCols;                    // BF16X3: A_lo lives in TMEM columns [192, 192+H/2)
+  static constexpr int kAloCol = kAccCols;                    // kTerms 3: A_lo in TMEM columns [192, 192 + H/2);
+                                                              // kTerms 4: A_hi8 in [192, 192 + H/4), A_lo8 in [352, 352 + H/4)
+  static constexpr int kAlo8Col = kAccCols + kJMaxH / 4;
   static constexpr int kABlockBytes = kJM * kJK * 2;          // 16 KB per K block of A
   static constexpr int kBRows = kBN / (kPair ? 2 : 1);        // W rows this CTA loads per N tile
   static constexpr int kBStageBytes = kParts * kBRows * kJK * 2; // W ring stage (per CTA)
@@ -92,6 +97,7 @@ struct JointFwdParams {
   // {fp16 hi, fp16 lo}: dz_h8 / dz_l8 [rows_pad, ldz] and hid_h8 / hid_l8 [rows_pad, ldh], one byte per element, occupy
   // the memory of dz_lo / hid_lo.  Every operand is scaled to max < 2^14 (gscale / wscale / ascale).
   int m8;
+  int w8_rows;                // rows of the e4m3 hi8 part of the W tensor map (the lo8 part follows)
   uint8_t* dz_h8;
   uint8_t* dz_l8;
   uint8_t* hid_h8;
@@ -395,7 +401,22 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           CLASR_TRACE_WAIT(5, tc::mbar_wait(&empty[stage], phase ^ 1));
           if (tc::elect_one()) {
             uint8_t* st = b_ring + stage * C::kBStageBytes;
-            if (kPair) {
+            if (kTerms == 4) {
+              // fp16 tile [kBRows][64 k] (128-byte swizzle) | e4m3 hi8 [kBRows][64 B] | e4m3 lo8 (64-byte swizzle); the two
+              // e4m3 arrays are one tensor map: lo8 rows follow w8_rows below the hi8 rows
+              uint8_t* st8 = st + C::kBRows * kJK * 2;
+              if (kPair) {
+                if (leader) tc::mbar_expect_tx(&full[stage], 2 * C::kBStageBytes);
+                tc::tma_load_2d_2sm_hint(st, &tmW_hi, &full[stage], kb * kJK, n0, pol_keep);
+                tc::tma_load_2d_2sm_hint(st8, &tmW_lo, &full[stage], kb * kJK, n0, pol_keep);
+                tc::tma_load_2d_2sm_hint(st8 + C::kBRows * kJK, &tmW_lo, &full[stage], kb * kJK, n0 + p.w8_rows, pol_keep);
+              } else {
+                tc::mbar_expect_tx(&full[stage], C::kBStageBytes);
+                tc::tma_load_2d(st, &tmW_hi, &full[stage], kb * kJK, n0);
+                tc::tma_load_2d(st8, &tmW_lo, &full[stage], kb * kJK, n0);
+                tc::tma_load_2d(st8 + C::kBRows * kJK, &tmW_lo, &full[stage], kb * kJK, n0 + p.w8_rows);
+              }
+            } else if (kPair) {
               if (leader) tc::mbar_expect_tx(&full[stage], 2 * C::kBStageBytes);
               if (kMode >= 1) {  // the kernel streams GBs of stores through L2: keep the 2.6 MB of W resident
                 tc::tma_load_2d_2sm_hint(st, &tmW_hi, &full[stage], kb * kJK, n0, pol_keep);
@@ -455,15 +476,34 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               const uint32_t a_lo_t = tmem_base + C::kAloCol + kb * (kJK / 2) + kk * 8;
               if (kPair) {
                 tc::umma_ss_2sm(d_tmem, da, dbh, idesc, accum);
-                if (kTerms > 1) {
+                if (kTerms == 3) {
                   tc::umma_ss_2sm(d_tmem, da, dbl, idesc, 1u);
                   tc::umma_ts_2sm(d_tmem, a_lo_t, dbh, idesc, 1u);
                 }
               } else {
                 tc::umma_ss(d_tmem, da, dbh, idesc, accum);
-                if (kTerms > 1) {
+                if (kTerms == 3) {
                   tc::umma_ss(d_tmem, da, dbl, idesc, 1u);
                   tc::umma_ts(d_tmem, a_lo_t, dbh, idesc, 1u);
+                }
+              }
+            }
+            if (kTerms == 4) {
+              // correction terms: A_hi8 . W_lo8 + A_lo8 . W_hi8, e4m3 A operands from tensor memory (4 k per 32-bit column:
+              // 8 columns per K = 32 MMA), W tiles K-major with 64-byte rows
+              const uint32_t b_h8 = b_hi + C::kBRows * kJK * 2, b_l8 = b_h8 + C::kBRows * kJK;
+#pragma unroll
+              for (int k8 = 0; k8 < kJK / 32; ++k8) {
+                const uint64_t dh8 = tc::make_desc_kmajor_sw64(b_h8 + k8 * 32);
+                const uint64_t dl8 = tc::make_desc_kmajor_sw64(b_l8 + k8 * 32);
+                const uint32_t a_h8_t = tmem_base + C::kAloCol + kb * (kJK / 4) + k8 * 8;
+                const uint32_t a_l8_t = tmem_base + C::kAlo8Col + kb * (kJK / 4) + k8 * 8;
+                if (kPair) {
+                  tc::umma_f8_ts_2sm(d_tmem, a_h8_t, dl8, idesc, 1u);
+                  tc::umma_f8_ts_2sm(d_tmem, a_l8_t, dh8, idesc, 1u);
+                } else {
+                  tc::umma_f8_ts(d_tmem, a_h8_t, dl8, idesc, 1u);
+                  tc::umma_f8_ts(d_tmem, a_l8_t, dh8, idesc, 1u);
                 }
               }
             }
@@ -866,19 +906,14 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           tc::pack_hi_lo(h0, h1, p.f16, hw, lw);
           const int rimm = (i & 3) + 8 * (i >> 2);  // compile-time part of the row index
           tc::st_shared_u32(ablk + aoff[i & 3] + rimm * 128, hw);
-          if (kTerms > 1) tc::st_shared_u32(stg + soff[i & 3] + 8 * (i >> 2) * 64, lw);
-          if (kMode >= 1 && p.m8 && tile_ok) {
-            // FP16M8: the e4m3 operands of the dW GEMM go straight to global memory — a half-warp holds 32 consecutive k
-            // of one row, so each 16-bit store instruction writes one full 32-byte sector per half-warp
-            const __half2 hh = *reinterpret_cast<const __half2*>(&hw);
-            const uint16_t h8 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(h0 * 0.015625f, h1 * 0.015625f),
-                                                                  __NV_SATFINITE, __NV_E4M3);
-            const uint16_t l8 = (uint16_t)__nv_cvt_float2_to_fp8x2(
-                make_float2((h0 - __low2float(hh)) * 64.f, (h1 - __high2float(hh)) * 64.f), __NV_SATFINITE, __NV_E4M3);
-            const int64_t e = ((int64_t)tile * kJM + q * 32 + rimm + 4 * hs) * p.ldh + kb * kJK + half * 32 + 2 * c;
-            *reinterpret_cast<uint16_t*>(p.hid_h8 + e) = h8;
-            *reinterpret_cast<uint16_t*>(p.hid_l8 + e) = l8;
+          if (kTerms == 4) {
+            // FP16M8: the staging word of a feature pair is (e4m3 hi8 pair) | (e4m3 lo8 pair) << 16 (tc::pack_m8)
+            uint32_t h16;
+            uint16_t h8, l8;
+            tc::pack_m8(h0, h1, h16, h8, l8);
+            lw = (uint32_t)h8 | ((uint32_t)l8 << 16);
           }
+          if (kTerms > 1) tc::st_shared_u32(stg + soff[i & 3] + 8 * (i >> 2) * 64, lw);
         }
       };
       load_batch(0, 0, fa, ga);
@@ -919,13 +954,34 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             v1[0] = x2.x; v1[1] = x2.y; v1[2] = x2.z; v1[3] = x2.w;
             v1[4] = x3.x; v1[5] = x3.y; v1[6] = x3.z; v1[7] = x3.w;
           }
+          if (kTerms == 4) {
+            // de-interleave the 16 (hi8 pair | lo8 pair) words of this lane's row into 32 hi8 bytes and 32 lo8 bytes
+            // (k ascending from the least significant byte: 4 k per 32-bit TMEM column)
+            uint32_t vh[8], vl[8];
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+              vh[i2] = __byte_perm(v0[2 * i2], v0[2 * i2 + 1], 0x5410);
+              vl[i2] = __byte_perm(v0[2 * i2], v0[2 * i2 + 1], 0x7632);
+              vh[4 + i2] = __byte_perm(v1[2 * i2], v1[2 * i2 + 1], 0x5410);
+              vl[4 + i2] = __byte_perm(v1[2 * i2], v1[2 * i2 + 1], 0x7632);
+            }
+            const uint32_t t8 = tmem_base + ((uint32_t)(q * 32) << 16) + kb * (kJK / 4) + half * 8;
+            tc::tmem_st8(t8 + C::kAloCol, vh);
+            tc::tmem_st8(t8 + C::kAlo8Col, vl);
+            if (kMode >= 1 && tile_ok) {  // the e4m3 operands of the dW GEMM: 32 contiguous bytes of this lane's row each
+              const int64_t e = ((int64_t)tile * kJM + q * 32 + lane) * p.ldh + kb * kJK + half * 32;
+              st_global_256(p.hid_h8 + e, vh);
+              st_global_256(p.hid_l8 + e, vl);
+            }
+          } else {
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::kAloCol + kb * (kJK / 2) + half * 16;
           tc::tmem_st8(taddr, v0);
           tc::tmem_st8(taddr + 8, v1);
-          if (kMode >= 1 && tile_ok && !p.m8) {  // pass 2: the lo halves of this lane's row (32 k = 64 contiguous bytes) for dW
+          if (kMode >= 1 && tile_ok) {  // pass 2: the lo halves of this lane's row (32 k = 64 contiguous bytes) for dW
             __nv_bfloat16* dst = p.hid_lo + ((int64_t)tile * kJM + q * 32 + lane) * p.ldh + kb * kJK + half * 32;
             st_global_256(dst, v0);
             st_global_256(dst + 16, v1);
+          }
           }
           tc::tmem_st_wait();
           tc::tc_fence_before();
@@ -1412,8 +1468,8 @@ static inline JointWs joint_ws_carve(void* base, int B, int T, int U1, int H, in
   const size_t wbytes = ((size_t)j.vp_pad * H * 2 + 255) / 256 * 256;
   j.w_hi = p + off; off += wbytes;
   j.w_lo = p + off; off += prec_x3(precision) ? wbytes : 0;
-  j.w_h8 = p + off;                       // FP16M8: e4m3 hi8 | lo8 of W_out (one byte per element each)
-  j.w_l8 = p + off + wbytes / 2;
+  j.w_h8 = p + off;                       // FP16M8: e4m3 hi8 | lo8 of W_out, [2 vp_pad, H] bytes (ONE tensor map)
+  j.w_l8 = p + off + (size_t)j.vp_pad * H;
   off += prec_m8(precision) ? wbytes : 0;
   j.tile_offsets = (int*)(p + off);
   off += ((size_t)(B + 2) * sizeof(int) + 255) / 256 * 256;
@@ -1579,6 +1635,10 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
     CLASR_CHECK_LAUNCH("joint_ascale");
     wscale = jw.gscale + 2;
   }
+  if (m8) {   // the pad rows [Vp, vp_pad) of the hi8 part sit INSIDE the combined hi8 | lo8 tensor map: keep them zero
+    cudaError_t e0 = cudaMemsetAsync(jw.w_h8, 0, (size_t)2 * jw.vp_pad * H, s);
+    CLASR_CHECK_ARG(e0 == cudaSuccess, "joint_rnnt_fwd: memset failed");
+  }
   if ((rc = launch_split_bf16(w_out, Vp, H, H, jw.w_hi, x3 ? jw.w_lo : nullptr, H, s, prec_f16(precision), wscale,
                               m8 ? jw.w_h8 : nullptr, m8 ? jw.w_l8 : nullptr)))
     return rc;
@@ -1602,7 +1662,10 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   const int bn = joint_use_pair() ? (x3 ? JointCfg<3, 1>::kBRows : JointCfg<1, 1>::kBRows)
                                   : (x3 ? JointCfg<3, 0>::kBRows : JointCfg<1, 0>::kBRows);
   if ((rc = make_tmap_bf16_2d(&tw_hi, jw.w_hi, Vp, H, H, bn, kJK))) return rc;
-  if (x3) {
+  if (m8) {   // e4m3 hi8 | lo8 of W as ONE [2 vp_pad, H]-byte tensor, boxes [bn rows][64 B], 64-byte swizzle
+    p.w8_rows = jw.vp_pad;
+    if ((rc = make_tmap_2d(&tw_lo, jw.w_h8, 2 * (uint64_t)jw.vp_pad, H, H, bn, kJK, 1, 64))) return rc;
+  } else if (x3) {
     if ((rc = make_tmap_bf16_2d(&tw_lo, jw.w_lo, Vp, H, H, bn, kJK))) return rc;
   } else {
     tw_lo = tw_hi;
@@ -1618,11 +1681,13 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
     if ((rc = make_tmap_bf16_2d(&t_hid, st.hid_hi, (uint64_t)st.rows_cap, H, H, kJM, kJK))) return rc;
     // TMA-store view of z: [rows_cap, ldzf] fp32, box = 32 rows x 8 columns (32-byte rows, 32-byte swizzle)
     if ((rc = make_tmap_2d(&t_z, st.z, (uint64_t)st.rows_cap, st.ldzf, st.ldzf, 32, 8, 4, 32))) return rc;
-    rc = x3 ? launch_joint_kernel<3, 3>(activation, H, tw_hi, tw_lo, t_hid, t_z, p, s)
-            : launch_joint_kernel<1, 3>(activation, H, tw_hi, tw_lo, t_hid, t_z, p, s);
+    rc = m8 ? launch_joint_kernel<4, 3>(activation, H, tw_hi, tw_lo, t_hid, t_z, p, s)
+         : x3 ? launch_joint_kernel<3, 3>(activation, H, tw_hi, tw_lo, t_hid, t_z, p, s)
+              : launch_joint_kernel<1, 3>(activation, H, tw_hi, tw_lo, t_hid, t_z, p, s);
   } else {
-    rc = x3 ? launch_joint_kernel<3, 0>(activation, H, tw_hi, tw_lo, tw_hi /*unused in pass 1*/, tw_hi, p, s)
-            : launch_joint_kernel<1, 0>(activation, H, tw_hi, tw_lo, tw_hi, tw_hi, p, s);
+    rc = m8 ? launch_joint_kernel<4, 0>(activation, H, tw_hi, tw_lo, tw_hi /*unused in pass 1*/, tw_hi, p, s)
+         : x3 ? launch_joint_kernel<3, 0>(activation, H, tw_hi, tw_lo, tw_hi, tw_hi, p, s)
+              : launch_joint_kernel<1, 0>(activation, H, tw_hi, tw_lo, tw_hi, tw_hi, p, s);
   }
   if (rc) return rc;
   prof_end("joint_fwd", s);
@@ -1710,7 +1775,10 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   const int bn = joint_use_pair() ? (x3 ? JointCfg<3, 1>::kBRows : JointCfg<1, 1>::kBRows)
                                   : (x3 ? JointCfg<3, 0>::kBRows : JointCfg<1, 0>::kBRows);
   if ((rc = make_tmap_bf16_2d(&tw_hi, jw.w_hi, Vp, H, H, bn, kJK))) return rc;
-  if (x3) {
+  if (m8) {
+    p.w8_rows = jw.vp_pad;
+    if ((rc = make_tmap_2d(&tw_lo, jw.w_h8, 2 * (uint64_t)jw.vp_pad, H, H, bn, kJK, 1, 64))) return rc;
+  } else if (x3) {
     if ((rc = make_tmap_bf16_2d(&tw_lo, jw.w_lo, Vp, H, H, bn, kJK))) return rc;
   } else {
     tw_lo = tw_hi;
@@ -1734,11 +1802,13 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
     CUtensorMap t_hid;  // TMA-store view of Hid_hi: [rows_cap, H] bf16, box = one 128 x 64 A block
     if ((rc = make_tmap_bf16_2d(&t_hid, sc.hid_hi, (uint64_t)sc.rows_cap, H, sc.ldh, kJM, kJK))) return rc;
     if (mode == 1)
-      rc = x3 ? launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
-              : launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s);
+      rc = m8 ? launch_joint_kernel<4, 1>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+           : x3 ? launch_joint_kernel<3, 1>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+                : launch_joint_kernel<1, 1>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s);
     else
-      rc = x3 ? launch_joint_kernel<3, 2>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
-              : launch_joint_kernel<1, 2>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s);
+      rc = m8 ? launch_joint_kernel<4, 2>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+           : x3 ? launch_joint_kernel<3, 2>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+                : launch_joint_kernel<1, 2>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s);
     if (rc) return rc;
     prof_end("joint_bwd_dz", s);
     CLASR_CHECK_LAUNCH("joint_bwd_dz");
