@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configs[config-1]")
     ap.add_argument("--mode", default="tcgen05", choices=["tcgen05", "materialised"])
     ap.add_argument("--precision", default=None, choices=["auto", "bf16x3", "fp16x3", "fp16m8", "bf16"],
-                    help="default: the config's (auto = the module default, fp16x3)")
+                    help="default: the config's (auto = the module default, fp16m8)")
     ap.add_argument("--backward", default="recompute", choices=["recompute", "stash"],
                     help="recompute (module default): the logits never reach HBM; stash: keep them for the backward pass")
     ap.add_argument("--activation", default=None, choices=["tanh", "relu", "sigmoid"])
@@ -573,7 +573,7 @@ def main_b200(args):
     cells = float((el_d.double() * (tl_d.double() + 1)).sum().item())
     Vp = c["V"] + 1
     gemm_flops = 2.0 * cells * c["H"] * Vp          # one pass of the joint GEMM (algorithmic)
-    issue = 3 if x3 else 1
+    issue = 2 if precision == "fp16m8" else 3 if x3 else 1   # MMA issue-equivalents per product (an e4m3 K=32 MMA = 1/2)
     roofline = None
     extra = {}
     mode_key = f"joint_fwd|{args.backward}|{precision}|{c['activation']}|B{B_local}|T{c['T']}|U{c['U']}|V{c['V']}"
@@ -654,8 +654,14 @@ def main_b200(args):
             extra.update(standalone_probes(args, c, dev, pk))
 
     cpu = None
+    incumbent = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = run_cpu_baseline(c, args.cpu_sample, steps=1, warmup=0)
+        if args.config == 2 and not args.no_extras:
+            cpu["reference_cpu_rnnt_b1"] = run_cpu_reference_rnnt(c)
+    if rank == 0 and world == 1 and args.config == 2 and not args.no_extras:
+        torch.cuda.empty_cache()
+        incumbent = run_gpu_incumbent(c, dev)
 
     if rank == 0:
         metric = "RNNT+CTC+EWC fwd/bwd utts/s (B32,T250,U100,V1024)" if args.config == 2 else \
@@ -664,7 +670,9 @@ def main_b200(args):
             "metric": metric, "value": main_res["value"], "unit": "utts/s",
             "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": main_res["ms"],
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": (f"f32 (joint GEMM: {precision[:4]} hi/lo split x3 on tcgen05, fp32 accumulate)"
+            "dtype": ("f32 (joint GEMM: fp16 hi.hi + two e4m3 correction MMAs on tcgen05, fp32 accumulate)"
+                      if precision == "fp16m8" else
+                      f"f32 (joint GEMM: {precision[:4]} hi/lo split x3 on tcgen05, fp32 accumulate)"
                       if x3 else "bf16 joint GEMM, fp32 elsewhere"),
             "data": "synthetic",
             "config": {"workload": c["workload"] + (", ragged lengths" if c["ragged"] and args.config == 2 else ""),
@@ -679,7 +687,7 @@ def main_b200(args):
             "e2e": main_res.get("e2e"),
             "gpu_launches": main_res["launches_per_step"] * steps, "gpu_launches_per_step": main_res["launches_per_step"],
             "clocks": main_res["clocks"], "roofline": roofline, "roofline_more": extra, "kernel_ms": kern,
-            "cpu_baseline": cpu, "impl": "b200",
+            "cpu_baseline": cpu, "gpu_incumbent": incumbent, "impl": "b200",
         }
         print(json.dumps(line), flush=True)
     finish(world)
@@ -697,6 +705,100 @@ def finish(world):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def run_gpu_incumbent(c, dev, steps=3):
+    """The reference's own GPU path on the same B200 (the like-for-like bar): torch joint
+    in sub-batches of fused_batch_size = 4 (modules/rnnt.py:1425: cuBLAS GEMMs, materialised hidden + logits), the
+    reference's numba-CUDA RNNTLossNumba (staged byte-for-byte under oracle/_ref by oracle/stage_ref.py), ATen
+    torch.nn.CTCLoss, and the per-tensor EWC Python loop with its .item() (cl_baseline_ewc.py:69-81).  Returns a dict,
+    or {"unavailable": why}."""
+    try:
+        from oracle import stage_ref
+        if not stage_ref.available():
+            return {"unavailable": "oracle/_ref not staged"}
+        from numba import cuda as ncuda
+        if not ncuda.is_available():
+            return {"unavailable": "numba.cuda not available on this box"}
+        RNNTLossNumba = stage_ref.load_rnnt_loss_numba()
+        torch.manual_seed(1234)
+        B, V = c["B"], c["V"]
+        enc_l = torch.nn.Linear(c["D_enc"], c["H"]).to(dev)
+        pred_l = torch.nn.Linear(c["D_pred"], c["H"]).to(dev)
+        out_l = torch.nn.Linear(c["H"], V + 1).to(dev)
+        head = torch.nn.Conv1d(c["D_enc"], V + 1, kernel_size=1).to(dev)
+        params = {n: p_ for m_, pre in ((enc_l, "enc."), (pred_l, "pred."), (out_l, "out."), (head, "ctc."))
+                  for n, p_ in ((pre + k, v) for k, v in m_.named_parameters())}
+        star = {k: v.detach() + 0.01 * torch.randn_like(v) for k, v in params.items()}
+        fish = {k: torch.rand_like(v) for k, v in params.items()}
+        act = {"tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid}[c["activation"]]
+        loss_fn = RNNTLossNumba(blank=V, reduction="none")
+        ctc_fn = torch.nn.CTCLoss(blank=V, reduction="none", zero_infinity=True)
+        enc, dec, tr, el, tl = [x.to(dev) for x in synth(dict(c, ragged=False), B, 1234)]
+
+        def step():
+            for p_ in params.values():
+                p_.grad = None
+            e_ = enc.clone().requires_grad_(True)
+            d_ = dec.clone().requires_grad_(True)
+            f = enc_l(e_.transpose(1, 2))
+            g = pred_l(d_.transpose(1, 2))
+            losses = []
+            for b0 in range(0, B, 4):   # the reference's fused sub-batch loop
+                sl = slice(b0, b0 + 4)
+                z = out_l(act(f[sl].unsqueeze(2) + g[sl].unsqueeze(1)))
+                losses.append(loss_fn(z, tr[sl].contiguous(), el[sl], tl[sl]))
+            l_rnnt = torch.cat(losses).mean()
+            lp = head(e_).transpose(1, 2).log_softmax(-1)
+            l_ctc = ctc_fn(lp.transpose(0, 1), tr, el, tl).mean()
+            loss = (1 - CTC_WEIGHT) * l_rnnt + CTC_WEIGHT * l_ctc
+            pen_avg = 0.0
+            for k, p_ in params.items():   # get_penalty_grads + set_grads, per tensor, one host sync
+                p_.grad = E_LAMBDA * 2 * fish[k] * (p_.data - star[k])
+                pen_avg = pen_avg + torch.mean(torch.abs(p_.grad))
+            pen_avg = (pen_avg / len(params)).item()
+            loss.backward()
+            return loss
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            loss = step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        return {"value": B / (ms * 1e-3), "unit": "utts/s", "ms_per_step": ms, "loss": float(loss),
+                "what": "reference GPU path on this B200: torch joint (fused_batch_size 4, cuBLAS fp32) + the reference's "
+                        "numba-CUDA RNNTLossNumba (oracle/_ref) + ATen CTCLoss + per-tensor EWC loop"}
+    except Exception as ex:   # numba / NVVM mismatches must not take the bench line down
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+
+
+def run_cpu_reference_rnnt(c):
+    """The reference's OWN CPU transducer loss (un-jitted Python, cpu_rnnt.py:164-422 through RNNTLossNumba on CPU
+    tensors, staged under oracle/_ref) on ONE utterance of the named shape with a reduced vocabulary slice for the
+    log-softmax input — the loop the C port in cpu_baseline replaces.  ~20 s; strictly per-sample (cpu_rnnt.py:365)."""
+    try:
+        from oracle import stage_ref
+        if not stage_ref.available():
+            return {"unavailable": "oracle/_ref not staged"}
+        RNNTLossNumba = stage_ref.load_rnnt_loss_numba()
+        torch.manual_seed(0)
+        T, U, Vp = c["T"], c["U"], c["V"] + 1
+        z = torch.randn(1, T, U + 1, Vp, requires_grad=True)
+        lab = torch.randint(0, Vp - 1, (1, U))
+        t0 = time.perf_counter()
+        loss = RNNTLossNumba(blank=Vp - 1, reduction="sum")(z, lab, torch.tensor([T]), torch.tensor([U]))
+        loss.backward()
+        dt = time.perf_counter() - t0
+        return {"value": 1.0 / dt, "unit": "utts/s (transducer loss fwd+bwd only)", "seconds": dt, "kind": "reference",
+                "cores": 1, "sample": f"1 utterance, T={T} U={U} V={Vp - 1}: RNNTLossNumba on CPU tensors (log_softmax + "
+                                      "the pure-Python alpha/beta/grad loops)"}
+    except Exception as ex:
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
 
 
 def _time_ms(fn, iters=10, warm=3):

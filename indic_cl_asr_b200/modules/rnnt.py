@@ -98,11 +98,14 @@ class RNNTJoint(torch.nn.Module):
 
         if fused_impl not in ("tcgen05", "materialised"):
             raise ValueError("fused_impl must be 'tcgen05' or 'materialised'")
-        # "auto": the fp32-grade split that is cheapest — fp16 halves (2^-22 operands, measured 4-7 % faster per step
-        # than bf16 halves at the same MMA count); the kernels bring W_out, the hidden activations (ReLU) and dZ to
-        # O(1) with exact power-of-two scales, so fp16's range is not the caller's concern
+        # "auto": the cheapest fp32-grade scheme — "fp16m8": fp16 hi.hi plus two dense e4m3 correction MMAs (8 instead of
+        # 12 MMA issues per 64-wide K block of every GEMM-shaped kernel; gradient parity vs the fp64 oracle at the
+        # benchmark size ~1e-5, the same as the three-term fp16 split, tests/test_gpu_full_size.py).  The kernels bring
+        # W_out, the hidden activations and dZ to a fixed range with exact power-of-two scales, so neither fp16's nor
+        # e4m3's range is the caller's concern.  CLASR_AUTO_PRECISION overrides (A/B measurements).
         if precision == "auto":
-            precision = "fp16x3"
+            import os
+            precision = os.environ.get("CLASR_AUTO_PRECISION", "fp16m8")
         if precision not in _lib.PREC:
             raise ValueError(f"precision must be 'auto' or one of {sorted(_lib.PREC)}")
         if backward_mode not in ("recompute", "stash"):

@@ -110,9 +110,12 @@ def test_config2_default_precision_vs_fp64_oracle(act, stash_gib, precision):
                                    ref_leaves[2], ref_leaves[3])
     oc = joint_oracle.rnnt_loss(z, lab, al, ll, V)
     (oc * wts.double()).sum().backward()
-    assert rel_err(costs.detach().cpu().numpy(), oc.detach().numpy()) <= 1e-5
-    for nm, got, rf in zip(["d_f", "d_g", "d_W", "d_b"], leaves, ref_leaves):
-        assert rel_err(got.grad.cpu().numpy(), rf.grad.numpy()) <= 1e-4, (act, nm)
+    errs = {nm: rel_err(got.grad.cpu().numpy(), rf.grad.numpy()) for nm, got, rf in zip(["d_f", "d_g", "d_W", "d_b"], leaves, ref_leaves)}
+    errs["cost"] = rel_err(costs.detach().cpu().numpy(), oc.detach().numpy())
+    print(f"config2 {act} {precision} stash={stash_gib}: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+    assert errs["cost"] <= 1e-5
+    for nm in ("d_f", "d_g", "d_W", "d_b"):
+        assert errs[nm] <= 1e-4, (act, nm, errs)
 
 
 def _generic_costs(f, g, W, b, lab, al, ll, V, act, sub=2):
