@@ -55,6 +55,62 @@ class _LinearX3(torch.autograd.Function):
         return (dx.view(xshape) if need_x else None), dw, db, None
 
 
+class _LinearF16Fwd(torch.autograd.Function):
+    """Forward with fp16 halves (2^-22 per product: the pre-activation of a ReLU joint must be fp32-grade, see
+    RNNTJoint._project), backward with the range-safe bf16 split: upstream gradients are not pre-scaled and would
+    underflow fp16, and nothing downstream of the backward GEMMs has a kink.  x and W are re-split for the backward
+    pass (clasr_gemm_ex splits its fp32 operands itself; a tcgen05 MMA cannot mix an fp16 with a bf16 operand)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _lib.require_cuda(x, "x")
+        lead, K, N = x.shape[:-1], x.shape[-1], weight.shape[0]
+        if weight.shape[1] != K:
+            raise ValueError(f"linear: weight {tuple(weight.shape)} does not match input features {K}")
+        x2 = x.reshape(-1, K).contiguous().float()
+        w = weight.contiguous().float()
+        b = None if bias is None else bias.contiguous().float()
+        M = x2.shape[0]
+        prec = _lib.PREC["fp16x3"]
+        L = _lib.lib()
+        nbytes = L.clasr_linear_workspace_bytes(M, N, K, prec)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.clasr_linear_fwd(x2.data_ptr(), w.data_ptr(), _lib.ptr(b), y.data_ptr(), M, N, K, prec,
+                                          ws.data_ptr(), nbytes, _lib.stream_ptr(x.device)), "linear_fwd")
+        ctx.save_for_backward(x2, w)
+        ctx.dims = (M, N, K, tuple(x.shape), bias is not None)
+        return y.view(*lead, N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        M, N, K, xshape, has_bias = ctx.dims
+        dy2 = dy.reshape(M, N).contiguous().float()
+        L = _lib.lib()
+        prec = _lib.PREC["bf16x3"]
+        dev = dy.device
+
+        def gemm(A, B, m, n, k, a_t, b_t, splits):
+            nbytes = L.clasr_gemm_workspace_bytes(m, n, k, prec)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            C = torch.empty(m, n, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.clasr_gemm_ex(A.data_ptr(), B.data_ptr(), C.data_ptr(), m, n, k, a_t, b_t, splits, prec,
+                                           ws.data_ptr(), nbytes, _lib.stream_ptr(dev)), "gemm_ex")
+            return C
+
+        dx = gemm(dy2, w, M, K, N, 0, 1, 1).view(xshape) if ctx.needs_input_grad[0] else None        # dy . W
+        dw = gemm(dy2, x2, N, K, M, 1, 1, max(1, min(16, M // 1024))) if ctx.needs_input_grad[1] else None   # dy^T . x
+        db = dy2.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
 def linear_x3(x: torch.Tensor, weight: torch.Tensor, bias=None, precision: str = "bf16x3") -> torch.Tensor:
-    """``torch.nn.functional.linear(x, weight, bias)`` on the tcgen05 tensor cores (CUDA tensors only)."""
+    """``torch.nn.functional.linear(x, weight, bias)`` on the tcgen05 tensor cores (CUDA tensors only).
+    ``precision="fp16x3"``: fp16 halves in the forward GEMM only (operands must sit in fp16's normal range), bf16 split
+    in the backward GEMMs."""
+    if precision == "fp16x3":
+        return _LinearF16Fwd.apply(x, weight, bias)
     return _LinearX3.apply(x, weight, bias, precision)

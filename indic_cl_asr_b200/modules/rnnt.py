@@ -191,14 +191,23 @@ class RNNTJoint(torch.nn.Module):
     def _project(self, lin: torch.nn.Linear, x: torch.Tensor) -> torch.Tensor:
         """enc / pred Linear (reference modules/rnnt.py:1563-1585); parameters stay ``enc.*`` / ``pred.*``.
 
-        tanh / sigmoid joints run the projection on the tcgen05 GEMM (bf16 hi+lo split, ~2^-17 relative per product).
-        A ReLU joint keeps torch's true-fp32 GEMM: the pre-activation feeds a kink, and a 1e-5 perturbation of
-        f+g flips relu' for ~80x more elements than fp32 rounding does, which alone costs 3e-4 of gradient parity."""
-        if x.is_cuda and str(self.activation).lower() != "relu":
+        The projection runs on the tcgen05 GEMM as a three-term split (``linear_x3``).  tanh / sigmoid joints use bf16
+        halves (~2^-17 relative per product, any operand range).  A ReLU joint feeds the pre-activation into a kink: a
+        1e-5 perturbation of f+g flips relu' for ~80x more elements than fp32 rounding does, which alone costs 3e-4 of
+        gradient parity — there the split uses fp16 halves (2^-22 per product, i.e. fp32-grade), which is safe for
+        operands inside fp16's normal range; ``CLASR_RELU_PROJ=torch`` keeps torch's true-fp32 GEMM instead (inputs
+        far outside [6e-5, 6e4] in magnitude)."""
+        if not x.is_cuda:
+            return lin(x)
+        if str(self.activation).lower() != "relu":
             from ..linear import linear_x3
             # the projections' upstream gradients are not pre-scaled: they keep the range-safe bf16 split
-            return linear_x3(x, lin.weight, lin.bias, "bf16x3" if self.precision in ("fp16x3", "fp16m8") else self.precision)
-        return lin(x)
+            return linear_x3(x, lin.weight, lin.bias, "bf16" if self.precision == "bf16" else "bf16x3")
+        import os
+        if os.environ.get("CLASR_RELU_PROJ", "tcgen05") == "torch" or self.precision == "bf16":
+            return lin(x)
+        from ..linear import linear_x3
+        return linear_x3(x, lin.weight, lin.bias, "fp16x3")
 
     def project_encoder(self, encoder_output: torch.Tensor) -> torch.Tensor:
         return self._project(self.enc, encoder_output)

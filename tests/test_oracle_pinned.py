@@ -183,3 +183,28 @@ def test_conv_asr_vs_reference_run(golden):
     lp, z = joint_oracle.ctc_head(torch.tensor(c["x"]), torch.tensor(c["weight"]), torch.tensor(c["bias"]), idx)
     assert np.allclose(z.numpy(), c["logits"], atol=1e-6)
     assert np.allclose(lp.numpy(), c["log_probs"], atol=1e-6)
+
+
+def test_c_port_lattice_vs_kat_and_reference_runs(golden):
+    """oracle/lattice.c (the C/OpenMP port of cpu_rnnt.py that bench.py's cpu_baseline times) against the reference's
+    own known-answer vectors and reference runs: costs and gradients w.r.t. the logits (autograd through log_softmax,
+    exactly the reference's CPU composition, rnnt_pytorch.py:411-437)."""
+    from oracle import c_port
+
+    k = golden("ref_kat.npz")
+    for name, cost_key, acts_key in (("small", "rnnt_small_expected_cost", "rnnt_small_acts"),
+                                     ("big", "rnnt_big_expected_costs", "rnnt_big_activations")):
+        acts = torch.tensor(k[acts_key], dtype=torch.float32, requires_grad=True)
+        labels = torch.tensor(k[f"rnnt_{name}_labels"], dtype=torch.long)
+        B, T = acts.shape[0], acts.shape[1]
+        costs = c_port.rnnt_loss_cpu(acts, labels, torch.full((B,), T), torch.full((B,), labels.shape[1]), 0)
+        costs.sum().backward()
+        assert np.allclose(costs.detach().numpy().sum(), np.asarray(k[cost_key]).sum(), rtol=1e-6)
+        assert np.allclose(acts.grad.numpy(), k[f"rnnt_{name}_expected_grads"], atol=1e-6, rtol=1e-4)
+    c = split_cases(golden("ref_rnnt.npz"))["ragged_blank_last"]
+    acts = torch.tensor(c["acts"], requires_grad=True)
+    costs = c_port.rnnt_loss_cpu(acts, torch.tensor(c["labels"]), torch.tensor(c["act_lens"]), torch.tensor(c["label_lens"]),
+                                 int(c["blank"]))
+    costs.sum().backward()
+    assert np.allclose(costs.detach().numpy(), c["costs"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(acts.grad.numpy(), c["grads"], atol=2e-6, rtol=1e-4)
