@@ -46,8 +46,8 @@ def _materialised_costs(f, g, W, b, lab, al, ll, sub=4):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-# "fp16x3" is what RNNTJoint(precision="auto") resolves to, i.e. what bench.py measures
-@pytest.mark.parametrize("precision", ["fp16x3", "bf16x3"])
+# "fp16m8" is what RNNTJoint(precision="auto") resolves to, i.e. what bench.py measures
+@pytest.mark.parametrize("precision", ["fp16m8", "fp16x3", "bf16x3"])
 @pytest.mark.parametrize("ragged", [False, True])
 def test_full_size_costs_fused_vs_materialised(ragged, precision):
     f, g, W, b, lab, al, ll = _inputs(32, 11, ragged)
@@ -58,7 +58,7 @@ def test_full_size_costs_fused_vs_materialised(ragged, precision):
     assert ((fused - ref).abs() <= 1e-5 * ref.abs()).all(), ((fused - ref).abs() / ref.abs()).max().item()
 
 
-@pytest.mark.parametrize("precision,stash_gib", [("fp16x3", None), ("fp16x3", 48.0), ("bf16x3", None)])
+@pytest.mark.parametrize("precision,stash_gib", [("fp16m8", None), ("fp16m8", 48.0), ("fp16x3", None), ("bf16x3", None)])
 def test_full_size_gradients_and_properties(precision, stash_gib):
     B = 8
     f, g, W, b, lab, al, ll = _inputs(B, 5, True)
@@ -85,7 +85,7 @@ def test_full_size_gradients_and_properties(precision, stash_gib):
 @pytest.mark.parametrize("stash_gib", [None, 48.0], ids=["recompute", "stash"])
 @pytest.mark.parametrize("act", ["tanh", "relu"])
 def test_config2_default_precision_vs_fp64_oracle(act, stash_gib, precision):
-    """BASELINE.json configs[1] shape (T=250, U=100, V=1024, H=640), the DEFAULT precision (fp16x3), both backward
+    """BASELINE.json configs[1] shape (T=250, U=100, V=1024, H=640), the DEFAULT precision (fp16m8) and fp16x3, both backward
     modes, tanh and the shipped checkpoint's ReLU — against the fp64 ORACLE itself (oracle/joint_oracle.py +
     rnnt_oracle.py), not against this repo's materialised path.  Two utterances (one full length, one ragged) keep the
     fp64 joint (2 x 250 x 101 x 1025 logits) and the numpy lattice at a few seconds of CPU.
@@ -133,6 +133,7 @@ def _generic_costs(f, g, W, b, lab, al, ll, V, act, sub=2):
 @pytest.mark.parametrize("name,B,T_,U_,V_,act,precision,ltol,gtol", [
     # configs[2]: IndicConformer-medium shapes (16 s audio -> T'~400, per-language vocabulary 256, ReLU joint)
     ("config3", 4, 400, 80, 256, "relu", "bf16x3", 1e-5, 1e-4),
+    ("config3_default_precision", 4, 400, 80, 256, "relu", "fp16m8", 1e-5, 1e-4),
     # configs[4]: V=4096 multilingual tokenizer, T=500, U=200, bf16 joint GEMM (single MMA term: bf16 tolerances)
     ("config5", 2, 500, 200, 4096, "tanh", "bf16", 2e-3, 3e-2),
 ])

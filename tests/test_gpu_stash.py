@@ -28,7 +28,7 @@ def _grads(fn, tensors):
     (2, 50, 20, 1024, 320, "relu", {"dropout_p": 0.2, "dropout_seed": 1234}),
     (2, 19, 7, 4500, 64, "tanh", {}),          # more than 512 eight-column groups: two column chunks in the sweep
 ])
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16", "fp16x3"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16", "fp16x3", "fp16m8"])
 def test_loss_backward_modes_agree(B, T, U, V, H, act, kw, precision, monkeypatch):
     f, g, W, b, lab, al, ll = make(B, T, U, V, H, seed=3 * B + T + V)
     wts = torch.linspace(0.5, 1.5, B).to(DEV)
