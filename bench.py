@@ -453,7 +453,10 @@ def main_b200(args):
     # strong scaling: every rank draws the SAME global batch and keeps its slice; weak: its own batch
     host = host_inputs(B_local, b0, 1234) if strong else host_inputs(B_local, 0, 1234 + rank)
 
-    def measure(backward_mode, B_loc, B_glob, host_in, variant="ewc", want_e2e=False):
+    prof_names = ("joint_fwd", "joint_bwd_dz", "joint_dz_sweep", "gemm_dhid", "gemm_dw", "joint_dfg", "rnnt_lattice",
+                  "rnnt_lse", "rnnt_grad", "ctc_lattice", "ctc_grad", "cl_penalty_grad")
+
+    def measure(backward_mode, B_loc, B_glob, host_in, variant="ewc", want_e2e=False, want_profile=False):
         """Build the modules, capture the step, time K replays.  Returns a dict of results."""
         wl = Workload(c, args, dev, world, backward_mode)
         step = wl.make_step(B_loc, B_glob, variant)
@@ -463,8 +466,27 @@ def main_b200(args):
             step(*ins)
         torch.cuda.synchronize()
         launches_per_step = (_lib.launch_count() - n0) // warm
+        kern, n_prof = {}, min(steps, 5)
+        if want_profile:
+            # per-kernel durations (library-side CUDA events on the launch stream), EAGER launches, before the graph
+            # takes its memory; the CTC branch stays on the main stream so that no duration includes shared time
+            wl.hybrid.overlap_ctc = False
+            L.clasr_set_profiling(1)
+            L.clasr_profile_reset()
+            for _ in range(n_prof):
+                flush.zero_()
+                step(*ins)
+            torch.cuda.synchronize()
+            kern = {k: _lib.profile_ms(k) for k in prof_names}
+            kern = {k: v for k, v in kern.items() if v >= 0}
+            if "rnnt_lse" in kern:   # materialised mode: several launches per step (the reference's sub-batch loop)
+                kern["rnnt_lse+grad_per_step"] = sum(
+                    m * n for m, n in (_lib.profile_ms_count(k) for k in ("rnnt_lse", "rnnt_grad")) if n > 0) / n_prof
+            L.clasr_set_profiling(0)
+            wl.hybrid.overlap_ctc = not args.no_overlap_ctc
         gs, graph_error = None, None
         if not args.no_graph:
+            torch.cuda.empty_cache()
             try:
                 gs = GraphedStep(step, ins, warmup=1)
             except Exception as ex:   # report, then measure the eager step rather than nothing
@@ -484,7 +506,7 @@ def main_b200(args):
             torch.cuda.synchronize()
         res = dict(wl=wl, step=step, ins=ins, gs=gs, total_ms=total_ms, per=per, ms=total_ms / steps,
                    value=B_glob * steps / (total_ms / 1e3), launches_per_step=int(launches_per_step),
-                   clocks=clk.summary(), precision=wl.precision, n_params=wl.n_params, graph_error=graph_error)
+                   clocks=clk.summary(), precision=wl.precision, n_params=wl.n_params, graph_error=graph_error, kern=kern)
         if want_e2e:
             res["e2e"] = measure_e2e(wl, step, ins, gs, host_in, B_glob)
         return res
@@ -498,7 +520,7 @@ def main_b200(args):
         if gs is not None:   # second input set + its own graph (shared memory pool: the two never run concurrently)
             ins_b = device_inputs(host_in)
             sets.append(ins_b)
-            graphs.append(GraphedStep(step, ins_b, warmup=1, pool=gs.pool()))
+            graphs.append(GraphedStep(step, ins_b, warmup=0, pool=gs.pool()))
         main = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(device=dev)
         h2d = sum(x.numel() * x.element_size() for x in host_in)
@@ -549,26 +571,12 @@ def main_b200(args):
                 "l2_flush_inside_region": True,
                 "device_allocs_in_timed_region": int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - n_alloc0)}
 
-    main_res = measure(args.backward, B_local, B_global, host, want_e2e=not args.no_e2e)
+    main_res = measure(args.backward, B_local, B_global, host, want_e2e=not args.no_e2e, want_profile=True)
     wl, step, ins = main_res["wl"], main_res["step"], main_res["ins"]
     precision = main_res["precision"]
     x3 = precision in ("bf16x3", "fp16x3", "fp16m8")
 
-    # ---------------- per-kernel durations (library-side CUDA events on the launch stream, eager launches) -> roofline
-    wl.hybrid.overlap_ctc = False   # per-kernel durations must not include time shared with the side-stream CTC branch
-    L.clasr_set_profiling(1)
-    L.clasr_profile_reset()
-    n_prof = min(steps, 5)
-    for _ in range(n_prof):
-        flush.zero_()
-        step(*ins)
-    torch.cuda.synchronize()
-    names = ("joint_fwd", "joint_bwd_dz", "joint_dz_sweep", "gemm_dhid", "gemm_dw", "joint_dfg", "rnnt_lattice",
-             "rnnt_lse", "rnnt_grad", "ctc_lattice", "ctc_grad", "cl_penalty_grad")
-    kern = {k: _lib.profile_ms(k) for k in names}
-    kern = {k: v for k, v in kern.items() if v >= 0}
-    L.clasr_set_profiling(0)
-    wl.hybrid.overlap_ctc = not args.no_overlap_ctc
+    kern = main_res["kern"]
     el_d, tl_d = ins[3], ins[4]
     cells = float((el_d.double() * (tl_d.double() + 1)).sum().item())
     Vp = c["V"] + 1
@@ -611,7 +619,7 @@ def main_b200(args):
     elif "rnnt_lse" in kern:
         # materialised mode runs the reference's sub-batch loop (fused_batch_size = 4): several launches per step
         by = 3.0 * cells * Vp * 4
-        ms = sum(m * n for m, n in (_lib.profile_ms_count(k) for k in ("rnnt_lse", "rnnt_grad")) if n > 0) / n_prof
+        ms = kern["rnnt_lse+grad_per_step"]
         roofline = {"kernel": "rnnt_lse_gather + rnnt_grad (materialised logits)", "bound": "hbm",
                     "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": by / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "ms": ms}

@@ -40,10 +40,15 @@ class GraphedStep:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):   # allocator, lazily built device tables, autograd nodes: all in steady state
+            # allocator, lazily built device tables, autograd nodes: all in steady state before the capture
+            # (warmup = 0: the caller has already run fn eagerly, e.g. a second graph over another input set)
+            for _ in range(max(0, warmup)):
                 fn(*self.static_inputs)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # the warm-up's transient buffers (tens of GB of GEMM scratch at the large configs) sit in the caching allocator;
+        # the capture allocates its own copies from a private pool, so hand the cached ones back first
+        torch.cuda.empty_cache()
         kw = {} if pool is None else {"pool": pool}
         with torch.cuda.graph(self.graph, stream=side, **kw):
             self.outputs = fn(*self.static_inputs)

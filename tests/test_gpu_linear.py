@@ -15,7 +15,7 @@ def _rel(a, b):
 @pytest.mark.parametrize("lead,K,N", [((4, 25), 32, 64), ((32, 250), 512, 640), ((32, 101), 640, 640),
                                       ((8, 100), 512, 1025), ((3, 7), 20, 9)])
 @pytest.mark.parametrize("bias", [True, False])
-@pytest.mark.parametrize("precision,fwd_tol", [("bf16x3", 2e-5), ("fp16x3", 1e-6)])
+@pytest.mark.parametrize("precision,fwd_tol", [("bf16x3", 2e-5), ("fp16x3", 3e-6)])   # fp16 halves: the fp32 accumulation floor
 def test_linear_fwd_bwd(lead, K, N, bias, precision, fwd_tol):
     g = torch.Generator().manual_seed(K + N)
     x = torch.randn(*lead, K, generator=g)
