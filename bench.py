@@ -416,7 +416,10 @@ def main_b200(args):
                                 timeout=datetime.timedelta(seconds=120))
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
-    torch.backends.cudnn.allow_tf32 = False       # "fp32" config: torch's own small GEMMs/convs stay true fp32
+    # "fp32" config: torch's own small GEMMs/convs stay true fp32.  Config 3 runs the prediction network's LSTM (cuDNN,
+    # out of scope) inside the step: it keeps torch's DEFAULT cudnn.allow_tf32 = True, as the reference's drivers do —
+    # with it off cuDNN issues 101 SIMT-sgemm launches per direction (5.8 of 10.8 ms, profiles/r02e)
+    torch.backends.cudnn.allow_tf32 = args.config == 3
     torch.backends.cuda.matmul.allow_tf32 = False
     silence_side_stream_grad_warning()
     if args.config == 4:
