@@ -1762,7 +1762,9 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   p.db_acc = d_b_out;
   if (p.f16 && (mode == 2 || grad_out)) {   // fp16 operands: pre-scale dZ to O(1) (see joint_gscale_kernel)
     rc = mode == 1 ? launch_joint_gscale(grad_out, B, (1.f + fastemit_lambda) * kScaleHeadroom * m8_headroom(m8), jw.gscale, s)
-                   : launch_joint_gscale(grad_cells, (int64_t)B * T * U1, 128.f * m8_headroom(m8), jw.gscale, s);
+                   // dZ = 2 z upstream: headroom for |z| up to 64 (fp16 operands ~1) / up to 512 in FP16M8, whose operands
+                   // sit 2^14 higher and must stay below fp16's 65504
+                   : launch_joint_gscale(grad_cells, (int64_t)B * T * U1, (m8 ? 1024.f : 128.f) * m8_headroom(m8), jw.gscale, s);
     if (rc) return rc;
     p.gscale = jw.gscale;
   }
