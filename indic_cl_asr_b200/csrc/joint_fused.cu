@@ -592,11 +592,16 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         // columns this N tile must cover: up to Vp (stats) or up to the padded operand width ldz (gradient)
         const int width = (kGrad ? p.ldz : p.Vp);
         const int ncols = (nt == n_tiles - 1) ? (width - nt * C::kBN) : C::kBN;
+        bool acc_released = false;   // pass 2 hands the accumulator back from inside its piece loop
         if (kStats) {
+          // (TMEM reads run one piece ahead and the accumulator is released after the last one: see pass 2 below)
+          const int npieces = tile_ok ? (ncols + 31) >> 5 : 0;
+          const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN;
+          uint32_t rr[32];
+          if (npieces > 0) tc::tmem_ld32(tacc, rr);
+          acc_released = npieces > 0;
 #pragma unroll 1
-          for (int c = 0; tile_ok && c * 32 < ncols; ++c) {
-            uint32_t rr[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN + c * 32, rr);
+          for (int c = 0; c < npieces; ++c) {
             const int col0 = nt * C::kBN + c * 32;
             // branch-free per element; every special case (tail columns, blank, label, sum of squares) is a
             // warp-uniform branch around the whole piece.  bias_pad is zero-padded to whole pieces.
@@ -612,6 +617,16 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               z[4 * j4 + 1] = fmaf(__uint_as_float(rr[4 * j4 + 1]), inv_w, bv[j4].y);
               z[4 * j4 + 2] = fmaf(__uint_as_float(rr[4 * j4 + 2]), inv_w, bv[j4].z);
               z[4 * j4 + 3] = fmaf(__uint_as_float(rr[4 * j4 + 3]), inv_w, bv[j4].w);
+            }
+            if (c + 1 < npieces) {
+              tc::tmem_ld32(tacc + (c + 1) * 32, rr);
+            } else {
+              tc::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);
+                else tc::mbar_arrive(&tmem_empty[acc]);
+              }
             }
             const bool tail = col0 + 32 > p.Vp;
             if (p.sumsq) {
@@ -691,10 +706,16 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           // pass 2: 16-column pieces (register budget: 96 per thread in the 640-thread layout), branch-free per element;
           // every special case is a warp-uniform branch around a whole piece
           uint32_t m8_h8[4] = {0u, 0u, 0u, 0u}, m8_l8[4] = {0u, 0u, 0u, 0u};   // FP16M8: the even piece of a pair
+          // the TMEM read of piece c + 1 is issued as soon as piece c has left its registers, so its latency hides
+          // behind the exponentials / packing / stores of piece c; the accumulator goes back to the MMA warp after the
+          // LAST read, one piece of epilogue work earlier than the end of the tile
+          const int npieces = tile_ok ? (ncols + 15) >> 4 : 0;
+          const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN;
+          uint32_t rr[16];
+          if (npieces > 0) tc::tmem_ld16(tacc, rr);
+          acc_released = npieces > 0;
 #pragma unroll 1
-          for (int c = 0; tile_ok && c * 16 < ncols; ++c) {
-            uint32_t rr[16];
-            tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN + c * 16, rr);
+          for (int c = 0; c < npieces; ++c) {
             const int col0 = nt * C::kBN + c * 16;
             float gr[16];
             const float4* bias4 = reinterpret_cast<const float4*>(p.bias_pad + col0);  // zero-padded copy
@@ -708,6 +729,16 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               gr[4 * j4 + 1] = fmaf(__uint_as_float(rr[4 * j4 + 1]), inv_w, bv[j4].y);
               gr[4 * j4 + 2] = fmaf(__uint_as_float(rr[4 * j4 + 2]), inv_w, bv[j4].z);
               gr[4 * j4 + 3] = fmaf(__uint_as_float(rr[4 * j4 + 3]), inv_w, bv[j4].w);
+            }
+            if (c + 1 < npieces) {
+              tc::tmem_ld16(tacc + (c + 1) * 16, rr);
+            } else {
+              tc::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);
+                else tc::mbar_arrive(&tmem_empty[acc]);
+              }
             }
             if (kMode == 2) {
               // MAS importance objective: dZ = 2 z * upstream (go); nothing else to do per logit
@@ -799,11 +830,13 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               atomicAdd(p.db_acc + col0 + (lane >> 1), p.gscale ? gr[0] * __ldg(p.gscale + 1) : gr[0]);
           }
         }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's MMA warp owns the hand-off
-          else tc::mbar_arrive(&tmem_empty[acc]);
+        if (!acc_released) {
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's MMA warp owns the hand-off
+            else tc::mbar_arrive(&tmem_empty[acc]);
+          }
         }
       }
       if (kStats && valid) {
