@@ -564,6 +564,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     const uint64_t pol_stream = tc::l2_policy_evict_first();
     (void)pol_stream;
     const float inv_w = p.wscale ? __ldg(p.wscale + 4) : 1.f;   // 1 / (Sw Sa); 1.0: fmaf(acc, 1, b) == acc + b exactly
+    const float inv_gs = (kGrad && p.gscale) ? __ldg(p.gscale + 1) : 1.f;   // 1 / S of the pre-scaled dZ (exact power of two)
     const int row = q * 32 + lane;
     int acc_it = 0;
     for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
@@ -587,6 +588,15 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         const int acc = acc_it & 1;
         const uint32_t acc_phase = (acc_it >> 1) & 1;
         if (kWide && acc != egrp) continue;
+        // pass 2: the bias of a piece is in flight one piece ahead (with ~28 KB of L1 left beside 226 KB of shared memory
+        // these loads come from L2: ~280 cycles per piece were exposed in front of the first FFMA, r02e profile);
+        // the first piece's before the accumulator wait
+        float4 bv[4];
+        if (kGrad) {
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias_pad + nt * C::kBN);  // zero-padded copy
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) bv[j4] = __ldg(bias4 + j4);
+        }
         CLASR_TRACE_WAIT(3, tc::mbar_wait(&tmem_full[acc], acc_phase));
         tc::tc_fence_after();
         // columns this N tile must cover: up to Vp (stats) or up to the padded operand width ldz (gradient)
@@ -718,10 +728,6 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           for (int c = 0; c < npieces; ++c) {
             const int col0 = nt * C::kBN + c * 16;
             float gr[16];
-            const float4* bias4 = reinterpret_cast<const float4*>(p.bias_pad + col0);  // zero-padded copy
-            float4 bv[4];
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) bv[j4] = __ldg(bias4 + j4);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -812,6 +818,11 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               st_global_256(p.dz_hi + grow * p.ldz + col0, ph);
               if (kTerms > 1) st_global_256(p.dz_lo + grow * p.ldz + col0, pl);
             }
+            if (c + 1 < npieces) {   // next piece's bias: its registers are dead from the FFMAs above until here
+              const float4* bias4 = reinterpret_cast<const float4*>(p.bias_pad + col0 + 16);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) bv[j4] = __ldg(bias4 + j4);
+            }
             // bias gradient d_b[v] = sum over cells of dZ[., v]: transpose-reduce the warp's 32 rows x 16 columns with
             // 16 shuffles (lanes 2c and 2c+1 end up with the column-(col0 + c) sum), one coalesced fp32 RED per warp
 #pragma unroll
@@ -827,7 +838,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             }
             gr[0] += __shfl_xor_sync(0xffffffffu, gr[0], 1);
             if ((lane & 1) == 0 && col0 + (lane >> 1) < p.Vp)
-              atomicAdd(p.db_acc + col0 + (lane >> 1), p.gscale ? gr[0] * __ldg(p.gscale + 1) : gr[0]);
+              atomicAdd(p.db_acc + col0 + (lane >> 1), gr[0] * inv_gs);
           }
         }
         if (!acc_released) {
