@@ -321,6 +321,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   // kMode 0: forward statistics;  3: the same + keep z and Hid for the backward;  1 / 2: gradient passes (recompute)
   constexpr bool kStats = kMode == 0 || kMode == 3;
   constexpr bool kGrad = kMode == 1 || kMode == 2;
+  constexpr bool kHelp = kWide && kGrad;   // the A producers share the gradient epilogue of the N loop (see below)
+  constexpr int kTailTiles = 2;            // ... except for the last N tiles of a row tile
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   const int kblocks = p.H / kJK;
@@ -363,7 +365,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   if (warp == 1 && tc::elect_one()) {
     constexpr int kCtas = kPair ? 2 : 1;
     for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 4 * kCtas); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], (kHelp ? 12 : 4) * kCtas); }
     for (int i = 0; i < 10; ++i) {
       tc::mbar_init(&a_ready[i], kJProducerWarps * kCtas);
       tc::mbar_init(&a_free[i], kMode >= 1 ? 2 : 1);
@@ -553,8 +555,14 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     if (tc::elect_one()) tc::bulk_wait_group0();  // all stores complete before the CTA exits
     __syncwarp();
   }
-  } else if (warp < kProdWarp0) {
+  } else {
     if (kWide) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // Warps 4 .. kProdWarp0-1 are the epilogue warps, the rest the A producers.  kHelp (pass 2, 640-thread layout): the
+    // gradient epilogue is the bottleneck of the N loop (r02e profile: an epilogue warp needs ~16 K cycles per N tile
+    // against ~4.6 K of MMA time, while the producers idle 60 % of the kernel on a_free), so after writing a row tile's A
+    // blocks the two producer warps of a lane quarter take a third each of the pieces of that tile's N tiles — all but
+    // the last kTailTiles, during which they already produce the next row tile.  Both roles run the SAME code below.
+    const bool is_prod = warp >= kProdWarp0;
     // ============================ epilogue ============================
     // kMode 0: online log-sum-exp + gather of logit[blank] / logit[label]  (pass 1)
     // kMode 1: softmax-fused gradient dZ = clamp(exp(logp + occupancy) - blank/label terms) * grad_out, split into
@@ -566,8 +574,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     const float inv_w = p.wscale ? __ldg(p.wscale + 4) : 1.f;   // 1 / (Sw Sa); 1.0: fmaf(acc, 1, b) == acc + b exactly
     const float inv_gs = (kGrad && p.gscale) ? __ldg(p.gscale + 1) : 1.f;   // 1 / S of the pre-scaled dZ (exact power of two)
     const int row = q * 32 + lane;
-    int acc_it = 0;
-    for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
+    const int ehalf = (warp - kProdWarp0) >> 2;   // helper: which third of the pieces (producer warp's K half)
+    auto epilogue_tile = [&](const int tile, const int tile_it, const bool helper) {
+      int acc_it = tile_it * n_tiles;
       const bool tile_ok = tile < total_tiles;  // pair mode: a null tile past the end only does the hand-shakes
       const int b = find_utterance(p.tile_offsets, p.B, tile_ok ? tile : 0);
       const int Tb = (int)p.act_lens[b], Ub1 = (int)p.label_lens[b] + 1;
@@ -587,22 +596,33 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
         const int acc = acc_it & 1;
         const uint32_t acc_phase = (acc_it >> 1) & 1;
-        if (kWide && acc != egrp) continue;
+        const bool helped = kHelp && nt < n_tiles - kTailTiles;   // warp-uniform, the same for every role
+        if (helper ? !helped : (kWide && acc != egrp)) continue;
+        // columns this N tile must cover: up to Vp (stats) or up to the padded operand width ldz (gradient)
+        const int width = (kGrad ? p.ldz : p.Vp);
+        const int ncols = (nt == n_tiles - 1) ? (width - nt * C::kBN) : C::kBN;
+        // pass 2: this warp's range of 16-column pieces, in units of two (FP16M8 stores the e4m3 operands of a piece pair
+        // as one sector): a helped N tile is cut in three (helpers: unit ranges 0 and 1, the epilogue warp the rest)
+        const int npieces_all = tile_ok ? (ncols + 15) >> 4 : 0;
+        const int units = (npieces_all + 1) >> 1;
+        const int per = helped ? units / 3 : 0;
+        const int c_begin = helper ? 2 * ehalf * per : 2 * 2 * per;
+        const int c_end = helper ? min(npieces_all, c_begin + 2 * per) : npieces_all;
+        (void)c_end;
         // pass 2: the bias of a piece is in flight one piece ahead (with ~28 KB of L1 left beside 226 KB of shared memory
         // these loads come from L2: ~280 cycles per piece were exposed in front of the first FFMA, r02e profile);
         // the first piece's before the accumulator wait
         float4 bv[4];
         if (kGrad) {
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias_pad + nt * C::kBN);  // zero-padded copy
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias_pad + nt * C::kBN + c_begin * 16);  // zero-padded copy
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) bv[j4] = __ldg(bias4 + j4);
         }
         CLASR_TRACE_WAIT(3, tc::mbar_wait(&tmem_full[acc], acc_phase));
         tc::tc_fence_after();
-        // columns this N tile must cover: up to Vp (stats) or up to the padded operand width ldz (gradient)
-        const int width = (kGrad ? p.ldz : p.Vp);
-        const int ncols = (nt == n_tiles - 1) ? (width - nt * C::kBN) : C::kBN;
         bool acc_released = false;   // pass 2 hands the accumulator back from inside its piece loop
+        // arrivals this warp owes tmem_empty: kHelp counts three per lane quarter and N tile
+        const int n_arrive = (kHelp && !helper && !helped) ? 3 : 1;
         if (kStats) {
           // (TMEM reads run one piece ahead and the accumulator is released after the last one: see pass 2 below)
           const int npieces = tile_ok ? (ncols + 31) >> 5 : 0;
@@ -634,8 +654,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               tc::tc_fence_before();
               __syncwarp();
               if (lane == 0) {
-                if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);
-                else tc::mbar_arrive(&tmem_empty[acc]);
+                for (int a = 0; a < n_arrive; ++a) {
+                  if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);
+                  else tc::mbar_arrive(&tmem_empty[acc]);
+                }
               }
             }
             const bool tail = col0 + 32 > p.Vp;
@@ -719,13 +741,13 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           // the TMEM read of piece c + 1 is issued as soon as piece c has left its registers, so its latency hides
           // behind the exponentials / packing / stores of piece c; the accumulator goes back to the MMA warp after the
           // LAST read, one piece of epilogue work earlier than the end of the tile
-          const int npieces = tile_ok ? (ncols + 15) >> 4 : 0;
+          const int npieces = c_end;
           const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kBN;
           uint32_t rr[16];
-          if (npieces > 0) tc::tmem_ld16(tacc, rr);
-          acc_released = npieces > 0;
+          if (npieces > c_begin) tc::tmem_ld16(tacc + c_begin * 16, rr);
+          acc_released = npieces > c_begin;
 #pragma unroll 1
-          for (int c = 0; c < npieces; ++c) {
+          for (int c = c_begin; c < npieces; ++c) {
             const int col0 = nt * C::kBN + c * 16;
             float gr[16];
             tc::tmem_ld_wait();
@@ -742,8 +764,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               tc::tc_fence_before();
               __syncwarp();
               if (lane == 0) {
-                if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);
-                else tc::mbar_arrive(&tmem_empty[acc]);
+                for (int a = 0; a < n_arrive; ++a) {
+                  if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);
+                  else tc::mbar_arrive(&tmem_empty[acc]);
+                }
               }
             }
             if (kMode == 2) {
@@ -845,8 +869,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's MMA warp owns the hand-off
-            else tc::mbar_arrive(&tmem_empty[acc]);
+            for (int a = 0; a < n_arrive; ++a) {
+              if (kPair) tc::mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's MMA warp owns the hand-off
+              else tc::mbar_arrive(&tmem_empty[acc]);
+            }
           }
         }
       }
@@ -858,41 +884,35 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         p.w.pp[idx] = lat_make_prob(lpb, lpl);
         if (p.sumsq) p.sumsq[((int64_t)b * p.T + t) * p.U1 + u] = ssq;
       }
-    }
-    if (kZStage) {  // all z boxes written before the CTA (and its shared memory) goes away
-      if (lane == 0) tc::bulk_wait_group0();
-      __syncwarp();
-    }
-  } else {
-    if (kWide) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    };
     // ============================ A producers: act(f + g) -> bf16 UMMA tiles ============================
     // Warp pw owns the 32 rows [32q, 32q+32) of the tile (q = pw & 3: the TMEM lane quarter it may write) and the
     // 32-wide K half `half = pw >> 2` of every 64-wide K block.  Compute mapping: half-warp hs handles one row at a
     // time (16 lanes x 2 consecutive k = 128 contiguous bytes of ef / eg per row), 16 row pairs per K block.  The lo
     // halves are transposed through a warp-private smem tile (no block-level barrier) into the warp's TMEM lanes.
-    const int pw = warp - kProdWarp0;
-    const int q = pw & 3, half = pw >> 2;
-    const int hs = lane >> 4, c = lane & 15;
-    const uint32_t a_base = tc::smem_u32(a_smem);
-    // one table per lane quarter, shared by its two K-half warps.  They drift apart in time (only the a_free waits
-    // gate them), so the table of the next tile must not be written while the sibling still reads this tile's: a
-    // 64-thread named barrier per quarter at every tile start.  (Without it: occasional corrupted dZ rows in pass 2a,
-    // found by repeating the config-3 parity test — tests/test_gpu_repeatability.py.)
-    const uint32_t tab = tc::smem_u32(rowtab) + q * 256;
-    const uint32_t stg = tc::smem_u32(staging) + pw * 2048;
-    // hi: byte offset of (row = 32q + rl, k = 32*half + 2c) in the SW128 K-major block, rl = (i&3) + 8(i>>2) + 4hs
-    uint32_t aoff[4], soff[4];
-#pragma unroll
-    for (int mth = 0; mth < 4; ++mth) {
-      const int r7 = mth + 4 * hs;  // (row & 7)
-      aoff[mth] = (uint32_t)((q * 32 + 4 * hs) * 128 + (((half * 4 + (c >> 2)) ^ r7) * 16) + (c & 3) * 4);
-      // staging: physical row = rl ^ hs (rows rl, rl+4 of the two half-warps land in different bank halves),
-      // 16-byte chunk XORed with (rl >> 1) & 3 so that the row-per-lane read-back is conflict-free
-      soff[mth] = (uint32_t)((((mth ^ hs) + 4 * hs) * 64) + ((((c >> 2) ^ ((mth >> 1) | (hs << 1))) & 3) * 16) +
-                             (c & 3) * 4);
-    }
-    int tile_it = 0;
-    for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++tile_it) {
+    auto produce_tile = [&](const int tile, const int tile_it) {
+      // (per-warp constants are rebuilt per tile: a helper warp must not carry them through the epilogue code)
+      const int pw = (warp - kProdWarp0) & 7;   // (epilogue warps never use the producer state below)
+      const int half = pw >> 2;                  // q = pw & 3 = warp & 3: the same lane quarter as in the epilogue code
+      const int hs = lane >> 4, c = lane & 15;
+      const uint32_t a_base = tc::smem_u32(a_smem);
+      // one table per lane quarter, shared by its two K-half warps.  They drift apart in time (only the a_free waits
+      // gate them), so the table of the next tile must not be written while the sibling still reads this tile's: a
+      // 64-thread named barrier per quarter at every tile start.  (Without it: occasional corrupted dZ rows in pass 2a,
+      // found by repeating the config-3 parity test — tests/test_gpu_repeatability.py.)
+      const uint32_t tab = tc::smem_u32(rowtab) + q * 256;
+      const uint32_t stg = tc::smem_u32(staging) + pw * 2048;
+      // hi: byte offset of (row = 32q + rl, k = 32*half + 2c) in the SW128 K-major block, rl = (i&3) + 8(i>>2) + 4hs
+      uint32_t aoff[4], soff[4];
+  #pragma unroll
+      for (int mth = 0; mth < 4; ++mth) {
+        const int r7 = mth + 4 * hs;  // (row & 7)
+        aoff[mth] = (uint32_t)((q * 32 + 4 * hs) * 128 + (((half * 4 + (c >> 2)) ^ r7) * 16) + (c & 3) * 4);
+        // staging: physical row = rl ^ hs (rows rl, rl+4 of the two half-warps land in different bank halves),
+        // 16-byte chunk XORed with (rl >> 1) & 3 so that the row-per-lane read-back is conflict-free
+        soff[mth] = (uint32_t)((((mth ^ hs) + 4 * hs) * 64) + ((((c >> 2) ^ ((mth >> 1) | (hs << 1))) & 3) * 16) +
+                               (c & 3) * 4);
+      }
       const bool tile_ok = tile < total_tiles;
       const int b = find_utterance(p.tile_offsets, p.B, tile_ok ? tile : 0);
       const int Tb = (int)p.act_lens[b], Ub1 = (int)p.label_lens[b] + 1;
@@ -1044,6 +1064,18 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         { const long long t_ = clock64(); tr_acc[10] += (unsigned long long)(t_ - tp0); }
 #endif
       }
+    };
+    // ============================ the tile loop of both roles ============================
+    {
+      int tile_it = 0;
+      for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++tile_it) {
+        if (is_prod) produce_tile(tile, tile_it);
+        if (!is_prod || kHelp) epilogue_tile(tile, tile_it, is_prod);
+      }
+    }
+    if (kZStage && !is_prod) {  // all z boxes written before the CTA (and its shared memory) goes away
+      if (lane == 0) tc::bulk_wait_group0();
+      __syncwarp();
     }
   }
 #ifdef CLASR_TRACE
