@@ -93,6 +93,15 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
                "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+// 32 bytes per thread of read-once data (two 128-bit loads; p 32-byte aligned)
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4+16];"
+               : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
 __device__ __forceinline__ float ld_stream1(const float* p) {
   float r;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));

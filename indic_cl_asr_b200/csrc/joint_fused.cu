@@ -318,11 +318,16 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   constexpr int kProdWarp0 = 4 + kEpiWarps;          // first producer warp (a multiple of 4: warp % 4 = TMEM quarter)
   constexpr int kBatch = kWide ? 4 : 8;              // row pairs per producer load batch (register budget)
   constexpr int kNB = 16 / kBatch;
-  // kMode 0: forward statistics;  3: the same + keep z and Hid for the backward;  1 / 2: gradient passes (recompute)
-  constexpr bool kStats = kMode == 0 || kMode == 3;
-  constexpr bool kGrad = kMode == 1 || kMode == 2;
+  // kMode 0: forward statistics;  3: the same + keep z and Hid for the backward;  4: the same + keep Hid only;
+  // 1 / 2: gradient passes that rebuild the hidden activations (transducer loss / MAS sum of squares);
+  // 5 / 6: the same gradient passes with the A operands LOADED from the hidden activations a kMode-4 forward kept
+  constexpr bool kStats = kMode == 0 || kMode == 3 || kMode == 4;
+  constexpr bool kGrad = kMode == 1 || kMode == 2 || kMode == 5 || kMode == 6;
+  constexpr int kGMode = (kMode == 1 || kMode == 5) ? 1 : ((kMode == 2 || kMode == 6) ? 2 : 0);   // which gradient
+  constexpr bool kEmitHid = kMode >= 1 && kMode <= 4;   // this pass writes the hidden activations as GEMM operands
+  constexpr bool kLoadA = kMode >= 5;                   // ... or reads them back instead of evaluating act(f + g)
   constexpr bool kHelp = kWide && kGrad;   // the A producers share the gradient epilogue of the N loop (see below)
-  constexpr int kTailTiles = 2;            // ... except for the last N tiles of a row tile
+  constexpr int kTailTiles = kLoadA ? 0 : 2;   // ... except for the last N tiles of a row tile (nothing to produce: all)
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   const int kblocks = p.H / kJK;
@@ -342,7 +347,21 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
   uint64_t* hid_ready = a_free + 10;        // [kblocks <= 10] pass 2: A K-block written (local copy for the store warp)
   uint32_t* tmem_base_slot = (uint32_t*)(hid_ready + 10);
 
-  const int warp = tc::warp_idx_uniform();
+  // Roles: 0 TMA, 1 MMA, 2 TMEM alloc, 3 Hid store / load, 4.. epilogue warps, then the A producers.  The four control
+  // roles sit in the LAST warpgroup of the CTA: the sub-partition arbiter favours the highest warp id, and the MMA / TMA
+  // warps must issue the moment their barrier flips — as warps 0-3 they lost the issue slot to the 4 busy worker warps
+  // of their sub-partition (role trace of pass 2a: the MMA warp spent 3.6 M cycles issuing what takes 1.9 M in pass 1).
+  // A role keeps (warp index mod 4), i.e. the tensor-memory lane quarter it may touch.
+  const int hw_warp = tc::warp_idx_uniform();
+  constexpr int kNumWarps = (kWide ? kJThreadsWide : kJThreads) / 32;
+#ifndef CLASR_CTRL_LAST
+#define CLASR_CTRL_LAST 1
+#endif
+#if CLASR_CTRL_LAST
+  const int warp = hw_warp >= kNumWarps - 4 ? hw_warp - (kNumWarps - 4) : hw_warp + 4;   // role index
+#else
+  const int warp = hw_warp;
+#endif
   const int lane = threadIdx.x & 31;
   CLASR_TRACE_DECL
   const int total_tiles = (int)tc::uniform_u32((uint32_t)p.tile_offsets[p.B]);
@@ -367,8 +386,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], (kHelp ? 12 : 4) * kCtas); }
     for (int i = 0; i < 10; ++i) {
-      tc::mbar_init(&a_ready[i], kJProducerWarps * kCtas);
-      tc::mbar_init(&a_free[i], kMode >= 1 ? 2 : 1);
+      tc::mbar_init(&a_ready[i], kJProducerWarps * kCtas + (kLoadA ? 1 : 0));   // kLoadA: + the loader's expect_tx
+      tc::mbar_init(&a_free[i], kEmitHid ? 2 : 1);
       tc::mbar_init(&hid_ready[i], kJProducerWarps);
     }
     tc::fence_barrier_init();
@@ -443,8 +462,11 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
     // ============================ MMA issuer (whole warp loops, one elected lane issues; pair: leader CTA) ====
     const uint32_t idesc_full = tc::make_idesc_16(kPair ? 2 * kJM : kJM, C::kBN, 0, 0, p.f16);
     const uint32_t idesc_last = tc::make_idesc_16(kPair ? 2 * kJM : kJM, n_last, 0, 0, p.f16);
-    const uint32_t a_base = tc::smem_u32(a_smem);
-    const uint32_t b_base = tc::smem_u32(b_ring);
+    // descriptor words of the A tile / W ring bases (see the issue loop)
+    const uint32_t a_dlo = (uint32_t)tc::make_desc_kmajor_sw128(tc::smem_u32(a_smem));
+    const uint32_t b_dlo = (uint32_t)tc::make_desc_kmajor_sw128(tc::smem_u32(b_ring));
+    const uint32_t d_hi128 = (uint32_t)(tc::make_desc_kmajor_sw128(0) >> 32);
+    const uint32_t d_hi64 = (uint32_t)(tc::make_desc_kmajor_sw64(0) >> 32);
     int stage = 0;
     uint32_t phase = 0;
     int acc_it = 0;
@@ -464,48 +486,50 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           CLASR_TRACE_WAIT(2, tc::mbar_wait(&full[stage], phase));
           tc::tc_fence_after();
           if (tc::elect_one()) {
-            const uint32_t a_hi = a_base + kb * C::kABlockBytes;
-            const uint32_t b_hi = b_base + stage * C::kBStageBytes;
-            const uint32_t b_lo = b_hi + C::kBRows * kJK * 2;
+            // Descriptor LOW words by plain additions to two per-kernel bases: the start-address field is (byte address
+            // >> 4) and shared memory ends below 2^18 bytes, so an offset never carries into the next field.  (Building
+            // each of the 12 descriptors of a K block from its address cost ~90 uniform-datapath instructions per block
+            // — with 16 busy worker warps on the SM the issue loop, not the tensor pipe, then set the pace of pass 2a.)
+            const uint32_t da = a_dlo + kb * (C::kABlockBytes >> 4);
+            const uint32_t dbh = b_dlo + stage * (C::kBStageBytes >> 4);
+            const uint32_t dbl = dbh + ((C::kBRows * kJK * 2) >> 4);
 #pragma unroll
             for (int kk = 0; kk < kJK / 16; ++kk) {
-              const uint32_t koff = kk * 32;
               const uint32_t accum = (kb == 0 && kk == 0) ? 0u : 1u;
-              const uint64_t da = tc::make_desc_kmajor_sw128(a_hi + koff);
-              const uint64_t dbh = tc::make_desc_kmajor_sw128(b_hi + koff);
-              const uint64_t dbl = tc::make_desc_kmajor_sw128(b_lo + koff);
+              const uint64_t d_a = tc::desc_from_words(d_hi128, da + kk * 2);
+              const uint64_t d_bh = tc::desc_from_words(d_hi128, dbh + kk * 2);
+              const uint64_t d_bl = tc::desc_from_words(d_hi128, dbl + kk * 2);
               // A_lo from tensor memory: 16 bf16 of K = 8 packed 32-bit columns
               const uint32_t a_lo_t = tmem_base + C::kAloCol + kb * (kJK / 2) + kk * 8;
               if (kPair) {
-                tc::umma_ss_2sm(d_tmem, da, dbh, idesc, accum);
+                tc::umma_ss_2sm(d_tmem, d_a, d_bh, idesc, accum);
                 if (kTerms == 3) {
-                  tc::umma_ss_2sm(d_tmem, da, dbl, idesc, 1u);
-                  tc::umma_ts_2sm(d_tmem, a_lo_t, dbh, idesc, 1u);
+                  tc::umma_ss_2sm(d_tmem, d_a, d_bl, idesc, 1u);
+                  tc::umma_ts_2sm(d_tmem, a_lo_t, d_bh, idesc, 1u);
                 }
               } else {
-                tc::umma_ss(d_tmem, da, dbh, idesc, accum);
+                tc::umma_ss(d_tmem, d_a, d_bh, idesc, accum);
                 if (kTerms == 3) {
-                  tc::umma_ss(d_tmem, da, dbl, idesc, 1u);
-                  tc::umma_ts(d_tmem, a_lo_t, dbh, idesc, 1u);
+                  tc::umma_ss(d_tmem, d_a, d_bl, idesc, 1u);
+                  tc::umma_ts(d_tmem, a_lo_t, d_bh, idesc, 1u);
                 }
               }
             }
             if (kTerms == 4) {
               // correction terms: A_hi8 . W_lo8 + A_lo8 . W_hi8, e4m3 A operands from tensor memory (4 k per 32-bit column:
-              // 8 columns per K = 32 MMA), W tiles K-major with 64-byte rows
-              const uint32_t b_h8 = b_hi + C::kBRows * kJK * 2, b_l8 = b_h8 + C::kBRows * kJK;
+              // 8 columns per K = 32 MMA), W tiles K-major with 64-byte rows (hi8 tile, then lo8 tile, after the fp16 tile)
+              const uint32_t dh8 = dbl, dl8 = dbl + ((C::kBRows * kJK) >> 4);
+              const uint32_t a8 = tmem_base + kb * (kJK / 4);
 #pragma unroll
               for (int k8 = 0; k8 < kJK / 32; ++k8) {
-                const uint64_t dh8 = tc::make_desc_kmajor_sw64(b_h8 + k8 * 32);
-                const uint64_t dl8 = tc::make_desc_kmajor_sw64(b_l8 + k8 * 32);
-                const uint32_t a_h8_t = tmem_base + C::kAloCol + kb * (kJK / 4) + k8 * 8;
-                const uint32_t a_l8_t = tmem_base + C::kAlo8Col + kb * (kJK / 4) + k8 * 8;
+                const uint64_t d_h8 = tc::desc_from_words(d_hi64, dh8 + k8 * 2);
+                const uint64_t d_l8 = tc::desc_from_words(d_hi64, dl8 + k8 * 2);
                 if (kPair) {
-                  tc::umma_f8_ts_2sm(d_tmem, a_h8_t, dl8, idesc, 1u);
-                  tc::umma_f8_ts_2sm(d_tmem, a_l8_t, dh8, idesc, 1u);
+                  tc::umma_f8_ts_2sm(d_tmem, a8 + C::kAloCol + k8 * 8, d_l8, idesc, 1u);
+                  tc::umma_f8_ts_2sm(d_tmem, a8 + C::kAlo8Col + k8 * 8, d_h8, idesc, 1u);
                 } else {
-                  tc::umma_f8_ts(d_tmem, a_h8_t, dl8, idesc, 1u);
-                  tc::umma_f8_ts(d_tmem, a_l8_t, dh8, idesc, 1u);
+                  tc::umma_f8_ts(d_tmem, a8 + C::kAloCol + k8 * 8, d_l8, idesc, 1u);
+                  tc::umma_f8_ts(d_tmem, a8 + C::kAlo8Col + k8 * 8, d_h8, idesc, 1u);
                 }
               }
             }
@@ -529,7 +553,33 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         __syncwarp();
       }
     }
-  } else if (warp == 3 && kMode >= 1) {
+  } else if (warp == 3 && kLoadA) {
+    // ============================ kept hidden activations: A_hi load warp ============================
+    // The 16-bit A blocks are exactly the boxes the kMode-4 forward stored ([128 rows x 64 k], 128-byte swizzle): one
+    // TMA load per K block as soon as the previous row tile's last MMAs on that block have retired.  The bytes are
+    // counted on a_ready[kb] (pair: the leader's copy, which also collects both CTAs' correction-operand arrivals).
+    int tile_it = 0;
+    for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++tile_it) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        if (tile_it > 0) tc::mbar_wait(&a_free[kb], (tile_it - 1) & 1);
+        if (tc::elect_one()) {
+          // (a null tile of a pair lies past the tensor's last row: the TMA zero-fills it and still counts the bytes)
+          if (kPair) {
+            if (leader) tc::mbar_expect_tx(&a_ready[kb], 2 * C::kABlockBytes);
+            tc::tma_load_2d_2sm(a_smem + kb * C::kABlockBytes, &tmHid, &a_ready[kb], kb * kJK, tile * kJM);
+          } else {
+            tc::mbar_expect_tx(&a_ready[kb], C::kABlockBytes);
+            tc::tma_load_2d(a_smem + kb * C::kABlockBytes, &tmHid, &a_ready[kb], kb * kJK, tile * kJM);
+          }
+          if (tile + tile_stride < total_tiles)   // the next row tile's block: towards L2 a whole tile time ahead
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmHid), "r"(kb * kJK),
+                         "r"((tile + tile_stride) * kJM)
+                         : "memory");
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 3 && kEmitHid) {
     // ============================ pass 2: Hid_hi store warp ============================
     // The bf16 hi halves of act(f+g) that the dW GEMM consumes ARE the A tile in shared memory (128-byte-swizzled
     // [128 rows x 64 k] blocks = exactly a TMA box): one elected lane stores each block with a TMA store as soon as
@@ -590,24 +640,45 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       const int64_t grow = (int64_t)tile * kJM + row;  // compact tile-row index of this thread's row
       // pass-2 per-row scalars (joint_row_grad)
       constexpr float kLog2e = 1.4426950408889634f;
-      const RowGrad rg = joint_row_grad<kGrad ? kMode : 0>(p, b, t, u, Tb, Ub1, valid);
+      const RowGrad rg = joint_row_grad<kGMode>(p, b, t, u, Tb, Ub1, valid);
       const float base2 = rg.base2, fe_base2 = rg.fe_base2, fe_coef = rg.fe_coef, blank_sub = rg.blank_sub,
                   label_sub = rg.label_sub, go = rg.go;
       for (int nt = 0; nt < n_tiles; ++nt, ++acc_it) {
         const int acc = acc_it & 1;
         const uint32_t acc_phase = (acc_it >> 1) & 1;
-        const bool helped = kHelp && nt < n_tiles - kTailTiles;   // warp-uniform, the same for every role
-        if (helper ? !helped : (kWide && acc != egrp)) continue;
+        // Who works on this N tile (warp-uniform).  Its 16-column pieces are cut into three ranges of piece PAIRS
+        // (FP16M8 stores the e4m3 operands of a pair as one sector); tmem_empty counts three arrivals per lane quarter.
+        //   no helpers:             the epilogue warp of this accumulator buffer takes all three ranges
+        //   helpers that produce:   on helped N tiles the producer warp bound to this accumulator buffer takes range 0 —
+        //                           with the ~33 K cycles of A production per row tile that evens out the four warps' loads
+        //   helpers that only load: the four warps of a lane quarter are equals, three of them serve an N tile (rotating)
+        // A warp must never skip a phase of a barrier it waits on later (a parity wait cannot tell phase n from n + 2):
+        // a helper that produces only ever touches ITS buffer's barrier (the N tiles it leaves out at the end of a row tile
+        // have completed long before it is back: its own A blocks gate the next row tile's MMAs), and a warp whose turn it
+        // is to sit out an N tile in the rotation still observes that tile's tmem_full phase.
+        int k_lo = 0, k_hi = 3;
+        bool mine;
+        if (!kHelp) {
+          mine = !kWide || acc == egrp;
+        } else if (kLoadA) {
+          const int k = ((helper ? 2 + ehalf : egrp) - acc_it) & 3;
+          mine = k < 3;
+          k_lo = k; k_hi = k + 1;
+          if (!mine) tc::mbar_wait(&tmem_full[acc], acc_phase);
+        } else {
+          const bool helped = nt < n_tiles - kTailTiles;
+          if (helper) { mine = helped && acc == ehalf; k_hi = 1; }
+          else { mine = acc == egrp; k_lo = helped ? 1 : 0; }
+        }
+        if (!mine) continue;
         // columns this N tile must cover: up to Vp (stats) or up to the padded operand width ldz (gradient)
         const int width = (kGrad ? p.ldz : p.Vp);
         const int ncols = (nt == n_tiles - 1) ? (width - nt * C::kBN) : C::kBN;
-        // pass 2: this warp's range of 16-column pieces, in units of two (FP16M8 stores the e4m3 operands of a piece pair
-        // as one sector): a helped N tile is cut in three (helpers: unit ranges 0 and 1, the epilogue warp the rest)
+        // pass 2: this warp's range of 16-column pieces
         const int npieces_all = tile_ok ? (ncols + 15) >> 4 : 0;
         const int units = (npieces_all + 1) >> 1;
-        const int per = helped ? units / 3 : 0;
-        const int c_begin = helper ? 2 * ehalf * per : 2 * 2 * per;
-        const int c_end = helper ? min(npieces_all, c_begin + 2 * per) : npieces_all;
+        const int c_begin = 2 * (k_lo * units / 3);
+        const int c_end = min(npieces_all, 2 * (k_hi * units / 3));
         (void)c_end;
         // pass 2: the bias of a piece is in flight one piece ahead (with ~28 KB of L1 left beside 226 KB of shared memory
         // these loads come from L2: ~280 cycles per piece were exposed in front of the first FFMA, r02e profile);
@@ -622,7 +693,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         tc::tc_fence_after();
         bool acc_released = false;   // pass 2 hands the accumulator back from inside its piece loop
         // arrivals this warp owes tmem_empty: kHelp counts three per lane quarter and N tile
-        const int n_arrive = (kHelp && !helper && !helped) ? 3 : 1;
+        const int n_arrive = kHelp ? k_hi - k_lo : 1;
         if (kStats) {
           // (TMEM reads run one piece ahead and the accumulator is released after the last one: see pass 2 below)
           const int npieces = tile_ok ? (ncols + 31) >> 5 : 0;
@@ -770,7 +841,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
                 }
               }
             }
-            if (kMode == 2) {
+            if (kGMode == 2) {
               // MAS importance objective: dZ = 2 z * upstream (go); nothing else to do per logit
             } else if (p.fastemit_lambda > 0.f) {
 #pragma unroll
@@ -786,18 +857,18 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
               for (int j = 0; j < 16; ++j)
                 if (col0 + j >= p.Vp) gr[j] = 0.f;
             }
-            if (kMode == 1 && p.blank >= col0 && p.blank < col0 + 16) {
+            if (kGMode == 1 && p.blank >= col0 && p.blank < col0 + 16) {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 if (col0 + j == p.blank) gr[j] -= blank_sub;
             }
-            if (kMode == 1 && __any_sync(0xffffffffu, label >= col0 && label < col0 + 16)) {
+            if (kGMode == 1 && __any_sync(0xffffffffu, label >= col0 && label < col0 + 16)) {
               const int jl = label - col0;
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 if (j == jl) gr[j] -= label_sub;
             }
-            if (kMode == 1 && p.clamp > 0.f) {
+            if (kGMode == 1 && p.clamp > 0.f) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) gr[j] = fmaxf(fminf(gr[j], p.clamp), -p.clamp);
             }
@@ -914,6 +985,74 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
                                (c & 3) * 4);
       }
       const bool tile_ok = tile < total_tiles;
+      if (kLoadA) {
+        // Kept hidden activations: the 16-bit A blocks arrive by TMA (warp 3); this warp moves the correction operands of
+        // its 32 rows and K half — 32 B of e4m3 hi8 + 32 B of lo8 per row and K block (64 B of the 16-bit lo halves in the
+        // three-term modes), as the kMode-4 forward stored them — from global memory into tensor memory.
+        const int64_t erow = ((int64_t)tile * kJM + q * 32 + lane) * p.ldh + half * 32;
+        constexpr int kPf = 3;                 // K blocks of correction operands in flight per lane (16 registers each)
+        constexpr int kMaxKb = kJMaxH / kJK;   // the loops are unrolled over the largest H: register arrays, no indexing
+        uint32_t v0[kPf][8], v1[kPf][8];
+        auto load_kb = [&](int kb, uint32_t (&a0)[8], uint32_t (&a1)[8]) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a0[j] = 0u; a1[j] = 0u; }
+          if (kTerms == 4 && tile_ok) {
+            ld_global_256(p.hid_h8 + erow + kb * kJK, a0);
+            ld_global_256(p.hid_l8 + erow + kb * kJK, a1);
+          } else if (kTerms == 3 && tile_ok) {
+            ld_global_256(p.hid_lo + erow + kb * kJK, a0);
+            ld_global_256(p.hid_lo + erow + kb * kJK + 16, a1);
+          }
+        };
+#pragma unroll
+        for (int j = 0; j < kPf; ++j)
+          if (j < kblocks) load_kb(j, v0[j], v1[j]);
+#pragma unroll
+        for (int kb = 0; kb < kMaxKb; ++kb) {
+          if (kb < kblocks) {
+            if (tile_it > 0) {   // (also in the one-term mode: an arrival must not land in the previous tile's phase)
+              CLASR_TRACE_WAIT(4, tc::mbar_wait(&a_free[kb], (tile_it - 1) & 1));
+              tc::tc_fence_after();
+            }
+#ifdef CLASR_TRACE
+            const long long tl0 = clock64();
+#endif
+            if (kTerms == 4) {
+              const uint32_t t8 = tmem_base + ((uint32_t)(q * 32) << 16) + kb * (kJK / 4) + half * 8;
+              tc::tmem_st8(t8 + C::kAloCol, v0[kb % kPf]);
+              tc::tmem_st8(t8 + C::kAlo8Col, v1[kb % kPf]);
+            } else if (kTerms == 3) {
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::kAloCol + kb * (kJK / 2) + half * 16;
+              tc::tmem_st8(taddr, v0[kb % kPf]);
+              tc::tmem_st8(taddr + 8, v1[kb % kPf]);
+            }
+            if (kTerms > 1) {
+              tc::tmem_st_wait();
+              tc::tc_fence_before();
+            }
+            __syncwarp();
+            if (lane == 0) {
+              if (kPair) tc::mbar_arrive_cluster(&a_ready[kb], 0);
+              else tc::mbar_arrive(&a_ready[kb]);
+            }
+            if (kb + kPf < kblocks) load_kb(kb + kPf, v0[kb % kPf], v1[kb % kPf]);
+#ifdef CLASR_TRACE
+            tr_acc[9] += (unsigned long long)(clock64() - tl0);   // slot 9: operand arrival + tensor-memory store + hand-off
+#endif
+          }
+        }
+        // the next row tile's correction operands: towards L2 now, while this warp works on this tile's epilogue share
+        // (half 0 asks for the hi8 / first 64 bytes of its rows' blocks, half 1 for the lo8 / second 64 bytes)
+        if (kTerms > 1 && tile + tile_stride < total_tiles) {
+          const int64_t nrow = ((int64_t)(tile + tile_stride) * kJM + q * 32 + lane) * p.ldh;
+          const char* base = kTerms == 4 ? (const char*)(half ? p.hid_l8 : p.hid_h8) + nrow
+                                         : (const char*)p.hid_lo + 2 * nrow + half * 128;
+          const int nlines = kTerms == 4 ? (p.H + 127) / 128 : (2 * p.H + 255) / 256;
+          const int step = kTerms == 4 ? 128 : 256;
+          for (int j = 0; j < nlines; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + j * step));
+        }
+        return;
+      }
       const int b = find_utterance(p.tile_offsets, p.B, tile_ok ? tile : 0);
       const int Tb = (int)p.act_lens[b], Ub1 = (int)p.label_lens[b] + 1;
       const int r0 = (tile - p.tile_offsets[b]) * kJM;
@@ -1032,7 +1171,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
             const uint32_t t8 = tmem_base + ((uint32_t)(q * 32) << 16) + kb * (kJK / 4) + half * 8;
             tc::tmem_st8(t8 + C::kAloCol, vh);
             tc::tmem_st8(t8 + C::kAlo8Col, vl);
-            if (kMode >= 1 && tile_ok) {  // the e4m3 operands of the dW GEMM: 32 contiguous bytes of this lane's row each
+            if (kEmitHid && tile_ok) {  // the e4m3 operands of the dW GEMM: 32 contiguous bytes of this lane's row each
               const int64_t e = ((int64_t)tile * kJM + q * 32 + lane) * p.ldh + kb * kJK + half * 32;
               st_global_256(p.hid_h8 + e, vh);
               st_global_256(p.hid_l8 + e, vl);
@@ -1041,7 +1180,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::kAloCol + kb * (kJK / 2) + half * 16;
           tc::tmem_st8(taddr, v0);
           tc::tmem_st8(taddr + 8, v1);
-          if (kMode >= 1 && tile_ok) {  // pass 2: the lo halves of this lane's row (32 k = 64 contiguous bytes) for dW
+          if (kEmitHid && tile_ok) {  // pass 2: the lo halves of this lane's row (32 k = 64 contiguous bytes) for dW
             __nv_bfloat16* dst = p.hid_lo + ((int64_t)tile * kJM + q * 32 + lane) * p.ldh + kb * kJK + half * 32;
             st_global_256(dst, v0);
             st_global_256(dst + 16, v1);
@@ -1058,7 +1197,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
         if (lane == 0) {
           if (kPair) tc::mbar_arrive_cluster(&a_ready[kb], 0);  // the leader's MMA warp waits for both CTAs' A blocks
           else tc::mbar_arrive(&a_ready[kb]);
-          if (kMode >= 1) tc::mbar_arrive(&hid_ready[kb]);      // the local store warp
+          if (kEmitHid) tc::mbar_arrive(&hid_ready[kb]);      // the local store warp
         }
 #ifdef CLASR_TRACE
         { const long long t_ = clock64(); tr_acc[10] += (unsigned long long)(t_ - tp0); }
@@ -1519,7 +1658,8 @@ struct JointStash {
   size_t total;
 };
 
-static inline JointStash joint_stash_carve(void* base, int B, int T, int U1, int H, int Vp, int precision) {
+static inline JointStash joint_stash_carve(void* base, int B, int T, int U1, int H, int Vp, int precision,
+                                           bool hid_only = false) {
   JointStash st;
   const bool x3 = prec_x3(precision);
   st.rows_cap = (int64_t)B * ((((int64_t)T * U1) + kJM - 1) / kJM) * kJM;
@@ -1527,7 +1667,7 @@ static inline JointStash joint_stash_carve(void* base, int B, int T, int U1, int
   char* p = (char*)base;
   size_t off = 0;
   auto take = [&](size_t bytes) { void* r = p + off; off += (bytes + 255) / 256 * 256; return r; };
-  st.z = (float*)take((size_t)st.rows_cap * st.ldzf * 4);
+  st.z = hid_only ? nullptr : (float*)take((size_t)st.rows_cap * st.ldzf * 4);
   st.hid_hi = take((size_t)st.rows_cap * H * 2);
   st.hid_lo = x3 ? take((size_t)st.rows_cap * H * 2) : st.hid_hi;
   st.total = off;
@@ -1618,7 +1758,22 @@ static int launch_joint_kernel(int activation, int H, const CUtensorMap& tw_hi, 
                                const CUtensorMap& t_hid, const CUtensorMap& t_z, const JointFwdParams& p,
                                cudaStream_t s) {
   // pass 2 (kMode 1 / 2) runs the 640-thread layout with two epilogue warpgroups unless CLASR_JOINT_WIDE=0
-  constexpr int kW = (kMode == 1 || kMode == 2) ? 1 : 0;
+  constexpr int kW = (kMode == 1 || kMode == 2 || kMode >= 5) ? 1 : 0;
+#ifdef CLASR_FAST_BUILD
+  // developer builds (20 s instead of 3.5 min of ptxas): FP16M8, tanh, CTA pairs, the default thread layouts only
+  if constexpr (kTerms == 4 && (kMode == 0 || kMode == 1 || kMode == 4 || kMode == 5)) {
+    if (activation == CLASR_ACT_TANH && joint_use_pair())
+      return launch_joint_variant<kTerms, kMode, CLASR_ACT_TANH, 1, kW>(H, tw_hi, tw_lo, t_hid, t_z, p, s);
+  }
+  set_error("joint kernel: this variant is not part of a CLASR_FAST_BUILD library");
+  return CLASR_STATUS_INVALID_VALUE;
+#else
+  if constexpr (kMode >= 4) {
+    // kept-hidden-activation modes: built as CTA pairs (and, for the gradient passes, the 640-thread layout) only
+    if (activation == CLASR_ACT_RELU) return launch_joint_variant<kTerms, kMode, CLASR_ACT_RELU, 1, kW>(H, tw_hi, tw_lo, t_hid, t_z, p, s);
+    if (activation == CLASR_ACT_SIGMOID) return launch_joint_variant<kTerms, kMode, CLASR_ACT_SIGMOID, 1, kW>(H, tw_hi, tw_lo, t_hid, t_z, p, s);
+    return launch_joint_variant<kTerms, kMode, CLASR_ACT_TANH, 1, kW>(H, tw_hi, tw_lo, t_hid, t_z, p, s);
+  }
   const char* we = getenv("CLASR_JOINT_WIDE");
   const bool wide = kW && (we ? atoi(we) != 0 : true);
 #define CLASR_LAUNCH_JOINT(ACT)                                                                             \
@@ -1631,6 +1786,7 @@ static int launch_joint_kernel(int activation, int H, const CUtensorMap& tw_hi, 
   if (activation == CLASR_ACT_SIGMOID) return CLASR_LAUNCH_JOINT(CLASR_ACT_SIGMOID);
   return CLASR_LAUNCH_JOINT(CLASR_ACT_TANH);
 #undef CLASR_LAUNCH_JOINT
+#endif
 }
 
 // scaled pre-activations (see joint_prep_kernel); relu needs none
@@ -1679,6 +1835,28 @@ static int check_joint_args(const char* who, const void* f, const void* g, const
   return CLASR_STATUS_SUCCESS;
 }
 
+extern "C" size_t clasr_joint_stash_bytes(int B, int T, int U1, int H, int Vp, int precision);
+// EXPERIMENT, not built by default (-DCLASR_KEEP_HIDDEN): a stash that holds only the hidden activations (kMode 4 forward,
+// kMode 5 / 6 backward passes that LOAD their A operands instead of evaluating act(f + g)).  Parity-tested against the
+// recompute mode at config-2 size, but measured SLOWER on B200 (pass 2a 4.9 vs 2.8 ms, profiles/r02f): with all 16
+// worker warps busy for the whole N loop the MMA warp's issue loop, not the tensor pipe, sets the pace.
+#ifdef CLASR_KEEP_HIDDEN
+extern "C" __attribute__((visibility("default"))) size_t clasr_joint_hidden_bytes(int B, int T, int U1, int H, int Vp,
+                                                                                  int precision) {
+  if (B <= 0 || T <= 0 || U1 <= 0 || H <= 0 || Vp <= 0) return 0;
+  return joint_stash_carve(nullptr, B, T, U1, H, Vp, precision, true).total;
+}
+#endif
+// What a `stash` of `bytes` bytes holds: 1 = logits + hidden activations (>= clasr_joint_stash_bytes), 2 = hidden
+// activations only (CLASR_KEEP_HIDDEN builds), 0 = too small.
+static int joint_stash_kind(size_t bytes, int B, int T, int U1, int H, int Vp, int precision) {
+  if (bytes >= clasr_joint_stash_bytes(B, T, U1, H, Vp, precision)) return 1;
+#ifdef CLASR_KEEP_HIDDEN
+  if (bytes >= clasr_joint_hidden_bytes(B, T, U1, H, Vp, precision)) return 2;
+#endif
+  return 0;
+}
+
 extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float* w_out, const float* b_out,
                                     const int64_t* labels, const int64_t* act_lens, const int64_t* label_lens, int B,
                                     int T, int U1, int H, int Vp, int blank, int activation, int precision,
@@ -1689,8 +1867,9 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
                             activation, precision, workspace, workspace_bytes);
   if (rc) return rc;
   CLASR_CHECK_ARG(costs, "joint_rnnt_fwd: null costs");
+  const int stash_kind = stash ? joint_stash_kind(stash_bytes, B, T, U1, H, Vp, precision) : 0;
   if (stash) {
-    CLASR_CHECK_ARG(stash_bytes >= clasr_joint_stash_bytes(B, T, U1, H, Vp, precision), "joint_rnnt_fwd: stash too small");
+    CLASR_CHECK_ARG(stash_kind != 0, "joint_rnnt_fwd: stash too small");
     CLASR_CHECK_ARG((((uintptr_t)stash) & 255) == 0, "joint_rnnt_fwd: stash must be 256-byte aligned");
   }
   cudaStream_t s = (cudaStream_t)stream;
@@ -1735,7 +1914,7 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   p.sumsq = sumsq;
   if ((rc = set_dropout(p, dropout_p, dropout_seed))) return rc;
   CUtensorMap tw_hi, tw_lo;
-  const int bn = joint_use_pair() ? (x3 ? JointCfg<3, 1>::kBRows : JointCfg<1, 1>::kBRows)
+  const int bn = (joint_use_pair() || stash_kind == 2) ? (x3 ? JointCfg<3, 1>::kBRows : JointCfg<1, 1>::kBRows)
                                   : (x3 ? JointCfg<3, 0>::kBRows : JointCfg<1, 0>::kBRows);
   if ((rc = make_tmap_bf16_2d(&tw_hi, jw.w_hi, Vp, H, H, bn, kJK))) return rc;
   if (m8) {   // e4m3 hi8 | lo8 of W as ONE [2 vp_pad, H]-byte tensor, boxes [bn rows][64 B], 64-byte swizzle
@@ -1747,6 +1926,19 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
     tw_lo = tw_hi;
   }
   prof_begin("joint_fwd", s);
+#ifdef CLASR_KEEP_HIDDEN
+  if (stash_kind == 2) {  // keep the hidden activations (as GEMM operands) for the backward (kMode 4); no logits
+    JointStash st = joint_stash_carve(stash, B, T, U1, H, Vp, precision, true);
+    CLASR_CHECK_ARG(st.rows_cap < 2147483647LL, "joint_rnnt_fwd: too many lattice cells");
+    p.hid_hi = (__nv_bfloat16*)st.hid_hi; p.hid_lo = (__nv_bfloat16*)st.hid_lo; p.ldh = H;
+    p.hid_h8 = (uint8_t*)st.hid_lo; p.hid_l8 = (uint8_t*)st.hid_lo + (size_t)st.rows_cap * H;   // FP16M8: in hid_lo's place
+    CUtensorMap t_hid;
+    if ((rc = make_tmap_bf16_2d(&t_hid, st.hid_hi, (uint64_t)st.rows_cap, H, H, kJM, kJK))) return rc;
+    rc = m8 ? launch_joint_kernel<4, 4>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+         : x3 ? launch_joint_kernel<3, 4>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+              : launch_joint_kernel<1, 4>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s);
+  } else
+#endif
   if (stash) {  // keep z and Hid for the backward (kMode 3)
     JointStash st = joint_stash_carve(stash, B, T, U1, H, Vp, precision);
     CLASR_CHECK_ARG(st.rows_cap < 2147483647LL, "joint_rnnt_fwd: too many lattice cells");
@@ -1771,7 +1963,7 @@ extern "C" int clasr_joint_rnnt_fwd(const float* f, const float* g, const float*
   return launch_rnnt_lattice(p.w, act_lens, label_lens, B, T, U1, fastemit_lambda, costs, s);
 }
 
-extern "C" size_t clasr_joint_stash_bytes(int B, int T, int U1, int H, int Vp, int precision) {
+size_t clasr_joint_stash_bytes(int B, int T, int U1, int H, int Vp, int precision) {
   if (B <= 0 || T <= 0 || U1 <= 0 || H <= 0 || Vp <= 0) return 0;
   return joint_stash_carve(nullptr, B, T, U1, H, Vp, precision).total;
 }
@@ -1798,8 +1990,9 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
                   "joint_rnnt_bwd: scratch too small");
   CLASR_CHECK_ARG((((uintptr_t)scratch) & 255) == 0, "joint_rnnt_bwd: scratch must be 256-byte aligned");
   CLASR_CHECK_ARG((H & 3) == 0, "joint_rnnt_bwd: H must be a multiple of 4");
+  const int stash_kind = stash ? joint_stash_kind(stash_bytes, B, T, U1, H, Vp, precision) : 0;
   if (stash) {
-    CLASR_CHECK_ARG(stash_bytes >= clasr_joint_stash_bytes(B, T, U1, H, Vp, precision), "joint_rnnt_bwd: stash too small");
+    CLASR_CHECK_ARG(stash_kind != 0, "joint_rnnt_bwd: stash too small");
     CLASR_CHECK_ARG((((uintptr_t)stash) & 255) == 0, "joint_rnnt_bwd: stash must be 256-byte aligned");
   }
   cudaStream_t s = (cudaStream_t)stream;
@@ -1850,7 +2043,7 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
     CLASR_CHECK_ARG(e1 == cudaSuccess && e2 == cudaSuccess, "joint_rnnt_bwd: memset failed");
   }
   CUtensorMap tw_hi, tw_lo;
-  const int bn = joint_use_pair() ? (x3 ? JointCfg<3, 1>::kBRows : JointCfg<1, 1>::kBRows)
+  const int bn = (joint_use_pair() || stash_kind == 2) ? (x3 ? JointCfg<3, 1>::kBRows : JointCfg<1, 1>::kBRows)
                                   : (x3 ? JointCfg<3, 0>::kBRows : JointCfg<1, 0>::kBRows);
   if ((rc = make_tmap_bf16_2d(&tw_hi, jw.w_hi, Vp, H, H, bn, kJK))) return rc;
   if (m8) {
@@ -1864,6 +2057,31 @@ static int joint_bwd_impl(int mode, const float* f, const float* g, const float*
   const void* hid_hi = sc.hid_hi;
   const void* hid_lo = sc.hid_lo;            // FP16M8: the e4m3 hi8 array, lo8 follows at rows_cap * H bytes
   const void* hid_l8 = p.hid_l8;
+#ifdef CLASR_KEEP_HIDDEN
+  if (stash_kind == 2) {
+    // the forward call kept the hidden activations (kMode 4): the logits are recomputed tile-wise with the A operands
+    // LOADED (TMA + tensor-memory stores) instead of rebuilt from f and g (kMode 5 / 6)
+    JointStash st = joint_stash_carve(stash, B, T, U1, H, Vp, precision, true);
+    hid_hi = st.hid_hi; hid_lo = st.hid_lo;
+    hid_l8 = (const uint8_t*)st.hid_lo + (size_t)st.rows_cap * H;
+    p.hid_hi = (__nv_bfloat16*)st.hid_hi; p.hid_lo = (__nv_bfloat16*)st.hid_lo; p.ldh = H;
+    p.hid_h8 = (uint8_t*)st.hid_lo; p.hid_l8 = (uint8_t*)st.hid_lo + (size_t)st.rows_cap * H;
+    prof_begin("joint_bwd_dz", s);
+    CUtensorMap t_hid;  // TMA-load view of Hid_hi: [rows_cap, H] 16-bit, box = one 128 x 64 A block
+    if ((rc = make_tmap_bf16_2d(&t_hid, st.hid_hi, (uint64_t)st.rows_cap, H, H, kJM, kJK))) return rc;
+    if (mode == 1)
+      rc = m8 ? launch_joint_kernel<4, 5>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+           : x3 ? launch_joint_kernel<3, 5>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+                : launch_joint_kernel<1, 5>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s);
+    else
+      rc = m8 ? launch_joint_kernel<4, 6>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+           : x3 ? launch_joint_kernel<3, 6>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s)
+                : launch_joint_kernel<1, 6>(activation, H, tw_hi, tw_lo, t_hid, tw_hi, p, s);
+    if (rc) return rc;
+    prof_end("joint_bwd_dz", s);
+    CLASR_CHECK_LAUNCH("joint_bwd_dz");
+  } else
+#endif
   if (stash) {
     // the forward call kept z and Hid (kMode 3): dZ is one streaming sweep over z
     JointStash st = joint_stash_carve(stash, B, T, U1, H, Vp, precision);

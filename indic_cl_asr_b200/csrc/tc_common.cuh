@@ -367,6 +367,8 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// a descriptor from its two 32-bit words (low: start address >> 4 and LBO, high: SBO, version, layout type)
+__device__ __forceinline__ uint64_t desc_from_words(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 // K-major operand, 64-byte swizzle: rows of 64 BYTES (64 e4m3 = one K block of the 8-bit correction operands), 8-row
 // groups of 512 B.  layout_type [61,64) = 4 (SWIZZLE_64B), SBO = 512 >> 4.  A K = 32 MMA advances the start by 32 B.
 __device__ __forceinline__ uint64_t make_desc_kmajor_sw64(uint32_t smem_addr) {
