@@ -102,6 +102,10 @@ __device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
                : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "l"(p));
 }
+// 128-bit vector reduction (sm_90+): four fp32 adds to consecutive, 16-byte-aligned addresses in one instruction
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ float ld_stream1(const float* p) {
   float r;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));

@@ -292,8 +292,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int col0 = n0 + c * 32;
         if (row < Mdyn && col0 < p.N) {
           if (p.atomic_add) {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(crow + col0 + j, alpha * __uint_as_float(r[j]));
+            if (vec_ok && col0 + 32 <= p.N) {   // 128-bit vector reductions: a quarter of the atomic instructions
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                red_add_v4(crow + col0 + j, alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]),
+                           alpha * __uint_as_float(r[j + 2]), alpha * __uint_as_float(r[j + 3]));
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(crow + col0 + j, alpha * __uint_as_float(r[j]));
+            }
           } else if (vec_ok && col0 + 32 <= p.N) {
             if (p.bias) {
 #pragma unroll
@@ -577,8 +584,15 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int col0 = n0 + c * 32;
         if (row < Mdyn && col0 < p.N) {
           if (p.atomic_add) {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(crow + col0 + j, alpha * __uint_as_float(r[j]));
+            if (vec_ok && col0 + 32 <= p.N) {   // 128-bit vector reductions: a quarter of the atomic instructions
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                red_add_v4(crow + col0 + j, alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]),
+                           alpha * __uint_as_float(r[j + 2]), alpha * __uint_as_float(r[j + 3]));
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(crow + col0 + j, alpha * __uint_as_float(r[j]));
+            }
           } else if (vec_ok && col0 + 32 <= p.N) {
             if (p.bias) {
 #pragma unroll
@@ -883,17 +897,13 @@ extern "C" int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db
       return rc;
   }
   if (dw) {  // A = dy given as [K_gemm = M rows, M_gemm = N cols]; B = x given as [K_gemm = M rows, N_gemm = K cols]
-    const int mn_tiles = ((N + 127) / 128) * ((K + 255) / 256);
-    int splits = (kNumSMs + mn_tiles - 1) / mn_tiles;
-    const int kb_total = (M + 63) / 64;
-    if (splits > kb_total) splits = kb_total;
-    if (splits < 1) splits = 1;
-    if (splits > 1) {
-      cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), s);
-      CLASR_CHECK_ARG(e == cudaSuccess, "linear_bwd: memset failed");
-    }
+    // split-K over the rows with launch_gemm_tc's own heuristic (>= 16 K blocks per slice, best fill of the persistent
+    // grid): a slice pays a whole 256 x 256 tile of fp32 reductions, so short slices (B_local = 4: 16 K blocks in all)
+    // cost more in atomics than they gain in parallelism.  The accumulator starts from zero either way.
+    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), s);
+    CLASR_CHECK_ARG(e == cudaSuccess, "linear_bwd: memset failed");
     if ((rc = launch_gemm_tc(ws.dy_hi, ws.dy_lo, pad8(N), 1, ws.x_hi, ws.x_lo, pad8(K), 1, N, K, M, dw, K, precision,
-                             splits > 1, splits, s, nullptr, nullptr, nullptr, nullptr, nullptr)))
+                             1, /*auto split-K*/ 0, s, nullptr, nullptr, nullptr, nullptr, nullptr)))
       return rc;
   }
   if (db) {
