@@ -1839,7 +1839,8 @@ extern "C" size_t clasr_joint_stash_bytes(int B, int T, int U1, int H, int Vp, i
 // EXPERIMENT, not built by default (-DCLASR_KEEP_HIDDEN): a stash that holds only the hidden activations (kMode 4 forward,
 // kMode 5 / 6 backward passes that LOAD their A operands instead of evaluating act(f + g)).  Parity-tested against the
 // recompute mode at config-2 size, but measured SLOWER on B200 (pass 2a 4.9 vs 2.8 ms, profiles/r02f): with all 16
-// worker warps busy for the whole N loop the MMA warp's issue loop, not the tensor pipe, sets the pace.
+// worker warps busy for the whole N loop the MMA warp's issue loop, not the tensor pipe, sets the pace.  Loose end: its last
+// builds passed the parity tests but bench.py at B = 32 ended in a CUDA error that was not investigated.
 #ifdef CLASR_KEEP_HIDDEN
 extern "C" __attribute__((visibility("default"))) size_t clasr_joint_hidden_bytes(int B, int T, int U1, int H, int Vp,
                                                                                   int precision) {
