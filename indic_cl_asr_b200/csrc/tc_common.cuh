@@ -450,7 +450,7 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 // so the library still loads on a GPU-less host for the ABI test).
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                       uint32_t box_rows, uint32_t box_cols);
-// general form: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 128, 64 or 32 (>= box_cols * elem_bytes)
+// general form: elem_bytes 1, 2 (bf16) or 4 (fp32); swizzle_bytes 128, 64 or 32 (>= box_cols * elem_bytes), or 0 = none
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                  uint32_t box_rows, uint32_t box_cols, int elem_bytes, int swizzle_bytes);
 
