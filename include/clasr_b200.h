@@ -202,6 +202,11 @@ CLASR_API int clasr_linear_fwd(const float* x, const float* w, const float* bias
 CLASR_API int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db, int M, int N, int K, int precision,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* y[b, c, r] = x[b, r, c] for contiguous fp32 x [B, R, C]: the NeMo layouts [B, D, T'] / [B, D, U+1] of the encoder and
+ * prediction-network outputs (modules/rnnt.py:1457-1459, conv_asr.py:467) to the row-major [B*T, D] operand of the linear
+ * layers and back for their input gradients (32 x 32 tiles through shared memory, both sides coalesced). */
+CLASR_API int clasr_transpose_last2(const float* x, float* y, int64_t B, int R, int C, void* stream);
+
 /* Design tool (not on the product path): cycles per tcgen05.mma M=128 x N x K=16 issued back to back on an otherwise
  * idle SM.  pattern 0: SS, 1: TS (A from TMEM), 2: SS,SS,TS.  out_dev[0] = cycles, out_dev[1] = MMA count. */
 CLASR_API int clasr_debug_mma_rate(int N, int pattern, int iters, long long* out_dev, void* stream);

@@ -55,6 +55,7 @@ _PROTOS: Dict[str, Tuple[object, List[object]]] = {
     "clasr_linear_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "clasr_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "clasr_linear_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "clasr_transpose_last2": (_i, [_vp, _vp, C.c_int64, _i, _i, _vp]),
     "clasr_joint_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "clasr_joint_rnnt_fwd": (_i, [_vp] * 7 + [_i] * 8 + [_f, C.c_uint64, _f, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "clasr_joint_stash_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),

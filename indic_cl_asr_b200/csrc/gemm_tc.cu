@@ -960,6 +960,41 @@ extern "C" int clasr_linear_bwd(const float* dy, float* dx, float* dw, float* db
 }
 
 // ------------------------------------------------------------------------------------------------
+// y[b, c, r] = x[b, r, c]: 32 x 32 tiles through shared memory, 128-byte coalesced on both sides
+// ------------------------------------------------------------------------------------------------
+namespace clasr {
+__global__ void __launch_bounds__(256) transpose_last2_kernel(const float* __restrict__ x, float* __restrict__ y, int R,
+                                                              int C) {
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.z;
+  const float* xb = x + b * (int64_t)R * C;
+  float* yb = y + b * (int64_t)R * C;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i, c = c0 + tx;
+    if (r < R && c < C) tile[ty + i][tx] = xb[(int64_t)r * C + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, r = r0 + tx;
+    if (r < R && c < C) yb[(int64_t)c * R + r] = tile[tx][ty + i];
+  }
+}
+}  // namespace clasr
+
+extern "C" int clasr_transpose_last2(const float* x, float* y, int64_t B, int R, int C, void* stream) {
+  CLASR_CHECK_ARG(x && y, "transpose_last2: null pointer");
+  CLASR_CHECK_ARG(B > 0 && R > 0 && C > 0 && B <= 65535, "transpose_last2: bad dimensions");
+  const dim3 grid((C + 31) / 32, (R + 31) / 32, (unsigned)B);
+  clasr::transpose_last2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, R, C);
+  CLASR_CHECK_LAUNCH("transpose_last2");
+  return CLASR_STATUS_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Micro-benchmark (design tool, not on the product path): cycles per tcgen05.mma M=128 x N x K=16 for a given
 // operand pattern, issued back to back by one thread with nothing else running on the SM.
 //   pattern 0: SS only   1: TS only (A from TMEM)   2: SS,SS,TS (the BF16X3 joint sequence)
