@@ -124,3 +124,20 @@ def test_joint_stash_size_and_limit(monkeypatch):
     assert fused._stash_limit_bytes() == 3 << 29
     # no gradient wanted -> nothing is kept, whatever the limit
     assert fused._stash(torch.empty(1), B, T, U1, H, Vp, _lib.PREC["bf16x3"], False) == (None, 0)
+
+
+def test_nemo_layout_view_detection():
+    """linear.py::_is_transposed_view (host logic): only `base.transpose(1, 2)` of a contiguous fp32 [B, K, T] tensor takes
+    the tiled-transpose path; everything else keeps torch's own layout handling."""
+    import torch
+    from indic_cl_asr_b200.linear import _is_transposed_view
+
+    base = torch.randn(3, 8, 5)
+    assert _is_transposed_view(base.transpose(1, 2))
+    assert _is_transposed_view(base[1:3].transpose(1, 2))            # a batch slice is still one contiguous block
+    assert not _is_transposed_view(base)                               # already [B, T, K]
+    assert not _is_transposed_view(base.transpose(1, 2).contiguous())
+    assert not _is_transposed_view(base[:, :, 1:4].transpose(1, 2))    # narrowed time axis: rows are not K*T apart
+    assert not _is_transposed_view(base.double().transpose(1, 2))      # fp32 only
+    assert not _is_transposed_view(torch.randn(8, 5).t())              # rank 2
+    assert not _is_transposed_view(torch.randn(3, 1, 5).transpose(1, 2))
