@@ -8,11 +8,12 @@
 //
 // One persistent CTA per SM walks 128-row tiles of VALID lattice cells (ragged utterances are compacted: a tile
 // never contains padding cells except at an utterance's tail), and for each tile
-//   producer warps   synthesise the A operand on the fly: act(f + g) -> bf16 (hi[,lo]) straight into the
-//                    128-byte-swizzled K-major UMMA layout in shared memory (A is not TMA-loadable: it does not
-//                    exist in memory); in BF16X3 mode the lo halves go to TENSOR MEMORY (tcgen05.st) and feed
-//                    the MMA as a TMEM A-operand, because hi+lo of a 128 x 640 tile does not fit in 227 KB smem
-//   TMA warp         streams W_out (bf16 hi[,lo], K-major) through an mbarrier ring
+//   producer warps   synthesise the A operand on the fly: act(f + g) -> 16-bit hi halves (fp16 or bf16) straight into
+//                    the 128-byte-swizzled K-major UMMA layout in shared memory (A is not TMA-loadable: it does not
+//                    exist in memory); the correction operands (e4m3 hi8 / lo8 in FP16M8, 16-bit lo halves in the
+//                    three-term modes) go to TENSOR MEMORY (tcgen05.st) and feed the MMA as TMEM A-operands,
+//                    because more than the hi halves of a 128 x 640 tile does not fit in 227 KB of shared memory
+//   TMA warp         streams W_out (the matching operand set, K-major) through an mbarrier ring
 //   MMA warp         one thread issues tcgen05.mma M=128 x N=BN x K=16 into double-buffered TMEM accumulators
 //   epilogue warps   tcgen05.ld the accumulators, add the bias and keep a running (max, sum-exp) per row across the
 //                    N tiles (online log-sum-exp), pick out logit[blank] and logit[label_u] (and sum z^2 for MAS);
@@ -30,7 +31,8 @@ int launch_split_bf16(const float* src, int64_t rows, int cols, int64_t src_ld, 
 constexpr int kJM = 128;            // rows (lattice cells) per tile
 constexpr int kJK = 64;             // K block (one 128-byte swizzle span of bf16)
 constexpr int kJMaxH = 640;         // A tile (128 x H bf16) must stay resident in shared memory
-constexpr int kJThreads = 512;      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 Hid store, 4-7 epilogue, 8-15 A producers
+// ROLE indices (the kernel maps hardware warps to roles so that the four control roles are the LAST warpgroup):
+constexpr int kJThreads = 512;      // roles: 0 TMA, 1 MMA, 2 TMEM alloc, 3 Hid store, 4-7 epilogue, 8-15 A producers
 constexpr int kJThreadsWide = 640;  // kWide: 4-7 epilogue of accumulator 0, 8-11 of accumulator 1, 12-19 A producers
 constexpr int kJProducerWarps = 8;
 constexpr int kJStages = 2;
@@ -986,7 +988,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_consta
       }
       const bool tile_ok = tile < total_tiles;
       if (kLoadA) {
-        // Kept hidden activations: the 16-bit A blocks arrive by TMA (warp 3); this warp moves the correction operands of
+        // Kept hidden activations: the 16-bit A blocks arrive by TMA (role 3); this warp moves the correction operands of
         // its 32 rows and K half — 32 B of e4m3 hi8 + 32 B of lo8 per row and K block (64 B of the 16-bit lo halves in the
         // three-term modes), as the kMode-4 forward stored them — from global memory into tensor memory.
         const int64_t erow = ((int64_t)tile * kJM + q * 32 + lane) * p.ldh + half * 32;
